@@ -1,0 +1,464 @@
+#!/usr/bin/env python
+"""Benchmark of the preprocessing feature-extraction hot path (BASELINE.json metric:
+audio-seconds per second, log-mel + energy + phone-level averaging, at N B200s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one batch of synthetic utterances per rank:
+fused log-spectrogram + energy kernel -> phone-level averaging of energy by durations ->
+{count,sum,sumsq,min,max} reduction -> (N>1: NCCL all-reduce of those five numbers) ->
+in-place normalisation.  Ranks hold independent shards (weak scaling); `value` is the
+whole-job audio-seconds processed per second, timed on the device, max over ranks.
+
+`--impl reference` times the CPU implementation of the same path (the oracle port of the
+reference, which on CPU is bit-identical to it; /root/reference itself cannot travel to
+the GPU box) on all host cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+# name -> (spec_type, sample_rate, n_fft, win, hop, n_mels, f_min, f_max, n_utts, min_s, max_s)
+WORKLOADS = {
+    # BASELINE.json configs[1]: 1k synthetic 1-10 s utterances at 22.05 kHz, 80-mel log-mel + energy
+    "mel80_22k_1k_ragged": ("mel", 22050, 1024, 1024, 256, 80, 0, 8000, 1000, 1.0, 10.0),
+    # configs[2]: 44.1 kHz n_fft 2048 hop 512 128 mels
+    "mel128_44k_1k_ragged": ("mel", 44100, 2048, 2048, 512, 128, 0, 8000, 1000, 1.0, 10.0),
+    # configs[3]: linear spectrogram + energy + phone averaging
+    "linear_22k_1k_ragged": ("linear", 22050, 1024, 1024, 256, 80, 0, 8000, 1000, 1.0, 10.0),
+}
+DEFAULT_WORKLOAD = "mel80_22k_1k_ragged"
+METRIC = "audio-sec/sec (log-mel+energy+phone-avg)"
+UNIT = "audio-s/s"
+
+
+def algorithmic_bytes_per_frame(spec_type, hop, n_mels, n_fft, sample_bytes=4):
+    """every input sample read once, every output written once."""
+    n_out = n_mels if spec_type in ("mel", "mel-librosa") else n_fft // 2 + 1
+    return hop * sample_bytes + n_out * 4 + 4
+
+
+def make_lengths(w, seed):
+    from everyvoice_b200 import synth
+
+    spec_type, sr, n_fft, win, hop, n_mels, f_min, f_max, n_utts, min_s, max_s = w
+    return synth.utterance_lengths(n_utts, sr, hop, seed, min_s, max_s)
+
+
+def make_durations(lengths, hop, seed):
+    from everyvoice_b200 import synth
+
+    durs = [synth.synthetic_durations(int(L) // hop, seed=seed + i) for i, L in enumerate(lengths)]
+    return synth.pack_ragged(durs)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx = float(parts[2])
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side (oracle port of the reference): cpu_baseline leg and --impl reference
+# ------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(w, n_sample, seed):
+    """Build the bounded CPU sample (shared by fork with the workers)."""
+    import torch
+
+    from everyvoice_b200 import synth
+    from oracle import ev_oracle as O
+
+    spec_type, sr, n_fft, win, hop, n_mels, f_min, f_max, n_utts, min_s, max_s = w
+    lengths = make_lengths(w, seed)[:n_sample]
+    rng = np.random.default_rng(seed)
+    _CPU["audio"] = [torch.from_numpy(rng.uniform(-0.95, 0.95, size=int(L)).astype(np.float32)) for L in lengths]
+    _CPU["durs"] = [torch.from_numpy(synth.synthetic_durations(int(L) // hop, seed=seed + i)) for i, L in enumerate(lengths)]
+    _CPU["tf"] = O.get_spectral_transform(spec_type, n_fft, win, hop, sr, n_mels, f_min, f_max)
+    _CPU["hop"] = hop
+    return float(sum(int(L) for L in lengths)) / sr
+
+
+def _cpu_chunk(idx_range):
+    """What one loky worker of the reference does for its items (process_spec + process_energy,
+    preprocessor.py:917-928, 641-650), in memory, one intra-op thread."""
+    import torch
+
+    from oracle import ev_oracle as O
+
+    torch.set_num_threads(1)
+    acc = 0.0
+    vals = []
+    for i in range(*idx_range):
+        spec, energy, phone = O.features_one(_CPU["audio"][i], _CPU["tf"], _CPU["hop"], _CPU["durs"][i])
+        acc += float(spec[0, 0])
+        vals.append(phone)
+    return acc, vals
+
+
+def _cpu_step(pool, n_items, cpus):
+    import torch
+
+    from oracle import ev_oracle as O
+
+    if pool is None:
+        chunks = [(0, n_items)]
+        results = [_cpu_chunk(c) for c in chunks]
+    else:
+        bs = min(100, 1 + n_items // (cpus * 2))  # the reference's batch rule, preprocessor.py:1198
+        chunks = [(a, min(a + bs, n_items)) for a in range(0, n_items, bs)]
+        results = pool.map(_cpu_chunk, chunks)
+    # stats + normalise (Scaler, helpers.py:86-106; normalize_stats preprocessor.py:453-490)
+    s = O.Scaler()
+    for _, vals in results:
+        for v in vals:
+            s.append(v)
+    s.calculate_stats()
+    return [s.normalize(v) for v in s.data]
+
+
+def cpu_baseline_single_thread(w, seed, n_sample=250):
+    """Oracle port, 1 thread, in process, on a bounded sample of the same workload."""
+    import torch
+
+    audio_s = _cpu_init(w, n_sample, seed)
+    nthreads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        _cpu_step(None, min(8, n_sample), 1)  # warm-up
+        t0 = time.perf_counter()
+        _cpu_step(None, n_sample, 1)
+        dt = time.perf_counter() - t0
+    finally:
+        torch.set_num_threads(nthreads)
+    return {
+        "value": audio_s / dt,
+        "unit": UNIT,
+        "cores": 1,
+        "kind": "port",
+        "sample": f"first {n_sample} utterances of the workload ({audio_s:.0f} audio-s), oracle port of the reference, "
+                  f"torch {torch.__version__} CPU, 1 thread, in memory (no file I/O)",
+        "seconds": dt,
+    }
+
+
+def run_reference_arm(args, w, wname):
+    """--impl reference: the CPU path on all host cores (fork pool standing in for loky)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+
+    import torch
+
+    n_sample = 256
+    audio_s = _cpu_init(w, n_sample, seed=1234)
+    cpus = os.cpu_count() or 1
+    try:
+        cpus = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(1)
+    pool = mp.get_context("fork").Pool(cpus) if cpus > 1 else None
+    try:
+        for _ in range(args.warmup):
+            _cpu_step(pool, n_sample, cpus)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            _cpu_step(pool, n_sample, cpus)
+        dt = time.perf_counter() - t0
+    finally:
+        if pool is not None:
+            pool.terminate()
+    value = audio_s * args.steps / dt
+    spec_type, sr, n_fft, win, hop, n_mels, *_ = w
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": wname, "spec_type": spec_type, "sample_rate": sr, "n_fft": n_fft, "hop": hop,
+                   "n_mels": n_mels, "utterances_per_step": n_sample, "audio_s_per_step": audio_s},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpus, "kind": "port",
+                         "sample": f"{n_sample} utterances ({audio_s:.0f} audio-s) per step; oracle port of the reference "
+                                   f"(bit-identical to it on CPU), fork pool of {cpus} workers with the reference's "
+                                   "batch rule, 1 intra-op thread each, in memory"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, w, wname):
+    import torch
+    import torch.distributed as dist
+
+    import everyvoice_b200 as ev
+    from everyvoice_b200 import _lib
+
+    spec_type, sr, n_fft, win, hop, n_mels, f_min, f_max, n_utts, min_s, max_s = w
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    _lib.load()
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    # CPU baseline first (rank 0, N == 1 only), before the GPU gets busy
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline_single_thread(w, seed=1234)
+
+    # ---- synthetic shard of this rank, resident in HBM --------------------------------------
+    seed = 1234 + rank
+    lengths = make_lengths(w, seed)
+    sample_offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    total_samples = int(sample_offsets[-1])
+    audio_s_rank = total_samples / sr
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    samples = (torch.rand(total_samples, device=device, generator=gen) * 1.9 - 0.95).contiguous()
+    d_packed, phone_offsets = make_durations(lengths, hop, seed)
+    durations_dev = torch.from_numpy(d_packed.astype(np.int64)).to(device)
+    phone_offsets_dev = torch.from_numpy(phone_offsets).to(device)
+
+    pre = ev.Preprocessor(ev.AudioConfig(input_sampling_rate=sr, output_sampling_rate=sr, n_fft=n_fft,
+                                         fft_window_size=win, fft_hop_size=hop, n_mels=n_mels, f_min=f_min,
+                                         f_max=f_max, spec_type=spec_type), device=device)
+    tf = pre.input_spectral_transform
+    batch = tf.make_batch(sample_offsets, device, apply_log=True, keep_last=False)
+    frame_offsets_dev = torch.from_numpy(batch.frame_offsets).to(device)
+    total_frames = batch.total_frames
+    spec = torch.empty((total_frames, batch.plan.row_floats), dtype=torch.float32, device=device)
+    energy = torch.empty(total_frames, dtype=torch.float32, device=device)
+    scaler = ev.Scaler(device)
+    stream = torch.cuda.current_stream(device)
+    launches = 0
+    feat_events = []
+
+    def step(timed: bool):
+        nonlocal launches
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        tf.run(batch, samples, spec, energy)                                           # 1 launch
+        if timed:
+            e1.record(stream)
+            feat_events.append((e0, e1))
+        phone = pre.average_data_by_durations_ragged(energy, frame_offsets_dev, durations_dev, phone_offsets_dev)  # 1
+        scaler.clear_data()
+        scaler.append(phone)
+        stats5 = scaler.partial_stats()                                                # 2 (init + reduce)
+        if world > 1:
+            from everyvoice_b200.distributed import allreduce_stats
+            stats5, _ = allreduce_stats(stats5, len(lengths))
+        scaler.normalize_by_device_stats_(phone, stats5)                               # 1 (mean/std derived on device)
+        launches += 5
+        return phone
+
+    def sync_all():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    for _ in range(args.warmup):
+        step(False)
+    launches = 0
+    sync_all()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    t_end.record(stream)
+    sync_all()
+    clock_info = clocks.stop() if rank == 0 else None
+    elapsed_ms = t_start.elapsed_time(t_end)
+    feat_ms = float(np.mean([a.elapsed_time(b) for a, b in feat_events]))
+    if world > 1:
+        t = torch.tensor([elapsed_ms, feat_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, feat_ms = float(t[0]), float(t[1])
+        tot = torch.tensor([audio_s_rank, float(total_frames)], dtype=torch.float64, device=device)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        audio_s_all = float(tot[0])
+    else:
+        audio_s_all = audio_s_rank
+    value = audio_s_all * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers --------------------------------
+    host_samples = torch.empty(total_samples, dtype=torch.float32).pin_memory()
+    host_samples.copy_(samples)
+    host_durs = torch.from_numpy(d_packed.astype(np.int64)).pin_memory()
+    host_spec = torch.empty((total_frames, batch.plan.row_floats), dtype=torch.float32).pin_memory()
+    host_energy = torch.empty(total_frames, dtype=torch.float32).pin_memory()
+    host_phone = torch.empty(int(phone_offsets[-1]), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        feats = pre.process_spec_batch(host_samples, sample_offsets)            # H2D + batch tables + fused kernel
+        phone, _ = pre.process_energy_batch(feats, host_durs.to(device, non_blocking=True), phone_offsets)
+        host_spec.copy_(feats.spec, non_blocking=True)                         # D2H: what process_spec would save
+        host_energy.copy_(feats.energy, non_blocking=True)
+        host_phone.copy_(phone, non_blocking=True)                             # D2H: what process_energy would save
+        torch.cuda.synchronize(device)
+        return float(host_phone[0])
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_value = audio_s_all * e2e_steps / e2e_s
+    h2d = total_samples * 4 + d_packed.size * 8
+    d2h = host_spec.numel() * 4 + host_energy.numel() * 4 + host_phone.numel() * 4
+
+    if rank == 0:
+        bpf = algorithmic_bytes_per_frame(spec_type, hop, n_mels, n_fft)
+        peaks_path = ROOT / "MEASURED_PEAKS.json"
+        if peaks_path.exists():
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = total_frames * bpf / (feat_ms * 1e-3) / 1e9
+        traffic = None
+        tp = ROOT / "profiles" / "traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.load(open(tp)).get(wname)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": wname, "spec_type": spec_type, "sample_rate": sr, "n_fft": n_fft, "win": win, "hop": hop,
+                "n_mels": n_mels, "utterances_per_gpu": int(len(lengths)), "audio_s_per_gpu": audio_s_rank,
+                "frames_per_gpu": int(total_frames), "sample_dtype": "f32",
+                "step": "features(log-spec+energy) -> phone averaging -> stats -> allreduce(N>1) -> normalise",
+                "l2_policy": f"inputs larger than L2 ({total_samples * 4 / 1e6:.0f} MB read + {spec.numel() * 4 / 1e6:.0f} MB written per step)",
+                "parallelism": f"utterance shards x{world}, stats all-reduce only",
+            },
+            "realtime_factor_per_gpu": value / world,
+            "roofline": {
+                "bound": "hbm", "kernel": "features_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_frame": bpf, "frames_per_launch": int(total_frames),
+                "kernel_ms": feat_ms, "kernel_share_of_step": feat_ms / (elapsed_ms / args.steps),
+            },
+            "cpu_baseline": cpu_base,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "api": "Preprocessor.process_spec_batch + process_energy_batch, pinned host buffers"},
+            "gpu_launches": launches,
+            "clocks": clock_info,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=list(WORKLOADS), default=DEFAULT_WORKLOAD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference_arm(args, w, args.workload)
+    return run_ours(args, w, args.workload)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,499 @@
+// C ABI of libevfeat.so (see include/evfeat.h): plan / batch management and entry points.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "evfeat_fft.cuh"
+#include "evfeat_internal.h"
+
+struct evf_plan {
+  evf_config cfg;
+  int device = 0;
+  int mode = 0;
+  int n_freq = 0;
+  int row_floats = 0;
+  int frames_per_tile = 0;
+  int num_sms = 0;
+  int smem_bytes = 0;
+  int k_used = 0;
+  evf::FeatParams carve{};
+  // device tables
+  float* d_window = nullptr;
+  float2* d_tw = nullptr;
+  float2* d_wpost = nullptr;
+  float2* d_melw = nullptr;
+  int* d_kstart = nullptr;
+  int* d_vwm = nullptr;
+};
+
+struct evf_batch {
+  int device = 0;
+  int n_utts = 0;
+  int n_tiles = 0;
+  int64_t total_frames = 0;
+  std::vector<int64_t> frame_off;  // host copy
+  long long* d_sample_off = nullptr;
+  long long* d_frame_off = nullptr;
+  int2* d_tiles = nullptr;
+};
+
+namespace evf {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  g_last_error = buf;
+  return (e == cudaErrorMemoryAllocation) ? EVF_ERR_OUT_OF_MEMORY : EVF_ERR_CUDA;
+}
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+template <typename T>
+int upload(const std::vector<T>& h, T** d) {
+  *d = nullptr;
+  if (h.empty()) return EVF_OK;
+  EVF_CUDA(cudaMalloc(reinterpret_cast<void**>(d), h.size() * sizeof(T)));
+  EVF_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return EVF_OK;
+}
+
+// Compress a dense [n_freq][n_mels] triangular filterbank: every frequency bin lies in
+// exactly one interval between adjacent filter centres, so it feeds at most two adjacent
+// filters.  j(k) = interval index (monotone in k); a[k] = fb[k][j], b[k] = fb[k][j-1].
+int compress_filterbank(const float* fb, int n_freq, int n_mels, int n_vw, PlanTables* t) {
+  std::vector<int> jk(n_freq, 0);
+  std::vector<float2> w(n_freq, make_float2(0.f, 0.f));
+  int j_prev = 0, k_used = 0;
+  for (int k = 0; k < n_freq; ++k) {
+    const float* row = fb + (size_t)k * n_mels;
+    int nz[3], cnt = 0;
+    for (int m = 0; m < n_mels; ++m) {
+      if (row[m] != 0.0f) {
+        if (!(row[m] == row[m]) || std::isinf(row[m])) {
+          set_error("mel filterbank contains NaN/Inf");
+          return EVF_ERR_FILTERBANK;
+        }
+        if (cnt < 3) nz[cnt] = m;
+        ++cnt;
+      }
+    }
+    int j = j_prev;
+    float a = 0.f, b = 0.f;
+    if (cnt == 1) {
+      const int m = nz[0];
+      if (j_prev <= m) { j = m; a = row[m]; }
+      else if (j_prev == m + 1) { j = m + 1; b = row[m]; }
+      else cnt = 99;
+    } else if (cnt == 2) {
+      if (nz[1] == nz[0] + 1 && nz[1] >= j_prev) { j = nz[1]; b = row[nz[0]]; a = row[nz[1]]; }
+      else cnt = 99;
+    }
+    if (cnt > 2) {
+      char buf[256];
+      snprintf(buf, sizeof(buf),
+               "mel filterbank row %d is not covered by two adjacent, monotonically ordered "
+               "triangular filters; only torchaudio/librosa style banks are supported", k);
+      set_error(buf);
+      return EVF_ERR_FILTERBANK;
+    }
+    jk[k] = j;
+    w[k] = make_float2(a, b);
+    if (cnt > 0) k_used = k + 1;
+    j_prev = j;
+  }
+  if (k_used == 0) k_used = 1;  // all-zero bank: keep one (zero-weight) bin so tables are non-empty
+  t->k_used = k_used;
+  t->melw.assign(w.begin(), w.begin() + k_used);
+  t->kstart.assign(n_mels + 2, k_used);
+  {
+    int k = 0;
+    for (int j = 0; j <= n_mels; ++j) {
+      while (k < k_used && jk[k] < j) ++k;
+      t->kstart[j] = k;
+    }
+    t->kstart[n_mels + 1] = k_used;
+  }
+  // Split the mels over the projection workers, balanced by the bins each has to walk.
+  std::vector<long long> prefix(n_mels + 1, 0);
+  for (int m = 0; m < n_mels; ++m)
+    prefix[m + 1] = prefix[m] + (t->kstart[m + 1] - t->kstart[m]) + 2;
+  t->vw_m.assign(n_vw + 1, n_mels);
+  t->vw_m[0] = 0;
+  int m = 0;
+  for (int v = 1; v < n_vw; ++v) {
+    const long long target = prefix[n_mels] * v / n_vw;
+    while (m < n_mels && prefix[m] < target) ++m;
+    t->vw_m[v] = m;
+  }
+  t->vw_m[n_vw] = n_mels;
+  return EVF_OK;
+}
+
+void free_plan_tables(evf_plan* p) {
+  cudaFree(p->d_window);
+  cudaFree(p->d_tw);
+  cudaFree(p->d_wpost);
+  cudaFree(p->d_melw);
+  cudaFree(p->d_kstart);
+  cudaFree(p->d_vwm);
+}
+
+}  // namespace
+}  // namespace evf
+
+using namespace evf;
+
+extern "C" {
+
+int evf_abi_version(void) { return EVF_ABI_VERSION; }
+
+const char* evf_last_error(void) { return g_last_error.c_str(); }
+
+int evf_plan_create(const evf_config* cfg, const float* window_host, const float* mel_fb_host,
+                    int device, evf_plan** plan_out) {
+  if (plan_out) *plan_out = nullptr;
+  if (!cfg || !window_host || !plan_out) {
+    set_error("evf_plan_create: null argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  const bool mel = (cfg->spec_type == EVF_SPEC_MEL || cfg->spec_type == EVF_SPEC_MEL_LIBROSA);
+  if (cfg->spec_type < EVF_SPEC_MEL || cfg->spec_type > EVF_SPEC_RAW) {
+    set_error("evf_plan_create: unknown spec_type");
+    return EVF_ERR_UNSUPPORTED;
+  }
+  if (cfg->n_fft != 1024 && cfg->n_fft != 2048) {
+    set_error("evf_plan_create: n_fft must be 1024 or 2048");
+    return EVF_ERR_UNSUPPORTED;
+  }
+  if (cfg->hop_length < 1 || cfg->hop_length > cfg->n_fft || cfg->win_length < 1 ||
+      cfg->win_length > cfg->n_fft) {
+    set_error("evf_plan_create: need 1 <= hop_length, win_length <= n_fft");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (cfg->n_fft == 2048 && (cfg->hop_length & 1)) {
+    set_error("evf_plan_create: n_fft 2048 needs an even hop_length");
+    return EVF_ERR_UNSUPPORTED;
+  }
+  if (cfg->sample_format != EVF_SAMPLES_F32 && cfg->sample_format != EVF_SAMPLES_S16) {
+    set_error("evf_plan_create: unknown sample_format");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (mel && (!mel_fb_host || cfg->n_mels < 1)) {
+    set_error("evf_plan_create: mel spec types need a filterbank and n_mels >= 1");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+    cudaGetLastError();
+    set_error("evf_plan_create: no such CUDA device; libevfeat has no CPU path");
+    return EVF_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  EVF_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("evf_plan_create: device is not sm_100 (Blackwell B200); libevfeat is built for sm_100a only");
+    return EVF_ERR_NO_DEVICE;
+  }
+  DeviceGuard guard(device);
+  if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+
+  evf_plan* p = new (std::nothrow) evf_plan();
+  if (!p) return EVF_ERR_OUT_OF_MEMORY;
+  p->cfg = *cfg;
+  p->device = device;
+  p->mode = (cfg->n_fft == 1024) ? MODE_PACK2 : MODE_HALF;
+  p->n_freq = cfg->n_fft / 2 + 1;
+  p->frames_per_tile = kWarps * (p->mode == MODE_PACK2 ? 2 : 1);
+  p->num_sms = prop.multiProcessorCount;
+  p->row_floats = mel ? cfg->n_mels : (cfg->spec_type == EVF_SPEC_RAW ? 2 * p->n_freq : p->n_freq);
+
+  PlanTables t;
+  t.window.resize(cfg->n_fft);
+  for (int i = 0; i < cfg->n_fft; ++i) t.window[i] = 0.5f * window_host[i];  // exact scaling
+  t.tw.resize(kFftSize);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int pos = 0; pos < 32; ++pos) {
+    const int k1 = bitrev5(pos);
+    for (int lane = 0; lane < 32; ++lane) {
+      const double ang = -two_pi * (double)((lane * k1) % kFftSize) / (double)kFftSize;
+      t.tw[pos * 32 + lane] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+  }
+  if (p->mode == MODE_HALF) {
+    t.wpost.resize(513);
+    for (int k = 0; k <= 512; ++k) {
+      const double ang = two_pi * (double)k / 2048.0;
+      t.wpost[k] = make_float2((float)std::cos(ang), (float)(-std::sin(ang)));
+    }
+  }
+  int rc = EVF_OK;
+  if (mel) {
+    const int n_vw = kWarps * (32 / p->frames_per_tile);
+    rc = compress_filterbank(mel_fb_host, p->n_freq, cfg->n_mels, n_vw, &t);
+    if (rc != EVF_OK) { delete p; return rc; }
+    p->k_used = t.k_used;
+  }
+  p->smem_bytes = features_smem_bytes(p->mode, cfg->spec_type, cfg->hop_length, cfg->n_fft,
+                                      cfg->n_mels, p->k_used, &p->carve);
+  if (p->smem_bytes < 0) {
+    delete p;
+    set_error("evf_plan_create: this n_fft / hop_length / n_mels combination needs more than 227 KB of shared memory per CTA");
+    return EVF_ERR_UNSUPPORTED;
+  }
+  rc = features_configure(p->mode, cfg->spec_type, cfg->sample_format, p->smem_bytes);
+  if (rc == EVF_OK) rc = upload(t.window, &p->d_window);
+  if (rc == EVF_OK) rc = upload(t.tw, &p->d_tw);
+  if (rc == EVF_OK) rc = upload(t.wpost, &p->d_wpost);
+  if (rc == EVF_OK) rc = upload(t.melw, &p->d_melw);
+  if (rc == EVF_OK) rc = upload(t.kstart, &p->d_kstart);
+  if (rc == EVF_OK) rc = upload(t.vw_m, &p->d_vwm);
+  if (rc != EVF_OK) {
+    free_plan_tables(p);
+    delete p;
+    return rc;
+  }
+  *plan_out = p;
+  return EVF_OK;
+}
+
+int evf_plan_destroy(evf_plan* plan) {
+  if (!plan) return EVF_OK;
+  DeviceGuard guard(plan->device);
+  free_plan_tables(plan);
+  delete plan;
+  return EVF_OK;
+}
+
+int evf_plan_row_floats(const evf_plan* plan, int32_t* row_floats_out) {
+  if (!plan || !row_floats_out) {
+    set_error("evf_plan_row_floats: null argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  *row_floats_out = plan->row_floats;
+  return EVF_OK;
+}
+
+int64_t evf_plan_num_frames(const evf_plan* plan, int64_t n_samples) {
+  if (!plan || n_samples < 0) return -1;
+  return n_samples / plan->cfg.hop_length + (plan->cfg.keep_last_frame ? 1 : 0);
+}
+
+int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, int32_t n_utts,
+                     evf_batch** batch_out) {
+  if (batch_out) *batch_out = nullptr;
+  if (!plan || !batch_out || n_utts < 0 || (n_utts > 0 && !sample_offsets_host)) {
+    set_error("evf_batch_create: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  const int hop = plan->cfg.hop_length, n_fft = plan->cfg.n_fft, fr = plan->frames_per_tile;
+  std::vector<long long> s_off(n_utts + 1, 0), f_off(n_utts + 1, 0);
+  std::vector<int2> tiles;
+  for (int b = 0; b < n_utts; ++b) {
+    const int64_t L = sample_offsets_host[b + 1] - sample_offsets_host[b];
+    if (L <= n_fft / 2) {
+      char buf[256];
+      snprintf(buf, sizeof(buf),
+               "utterance %d has %lld samples; reflect padding needs more than n_fft/2 = %d "
+               "(torch.stft raises for the same input)", b, (long long)L, n_fft / 2);
+      set_error(buf);
+      return EVF_ERR_SHORT_INPUT;
+    }
+    const int64_t T = L / hop + (plan->cfg.keep_last_frame ? 1 : 0);
+    if (T > 0x7fffffff - fr) {
+      set_error("evf_batch_create: utterance too long");
+      return EVF_ERR_INVALID_ARGUMENT;
+    }
+    f_off[b + 1] = f_off[b] + T;
+    for (int64_t f0 = 0; f0 < T; f0 += fr) tiles.push_back(make_int2(b, (int)f0));
+  }
+  for (int b = 0; b <= n_utts; ++b) s_off[b] = n_utts ? sample_offsets_host[b] : 0;
+
+  DeviceGuard guard(plan->device);
+  evf_batch* bt = new (std::nothrow) evf_batch();
+  if (!bt) return EVF_ERR_OUT_OF_MEMORY;
+  bt->device = plan->device;
+  bt->n_utts = n_utts;
+  bt->n_tiles = (int)tiles.size();
+  bt->total_frames = f_off[n_utts];
+  bt->frame_off.assign(f_off.begin(), f_off.end());
+  int rc = upload(s_off, &bt->d_sample_off);
+  if (rc == EVF_OK) rc = upload(f_off, &bt->d_frame_off);
+  if (rc == EVF_OK) rc = upload(tiles, &bt->d_tiles);
+  if (rc != EVF_OK) {
+    evf_batch_destroy(bt);
+    return rc;
+  }
+  *batch_out = bt;
+  return EVF_OK;
+}
+
+int evf_batch_destroy(evf_batch* batch) {
+  if (!batch) return EVF_OK;
+  DeviceGuard guard(batch->device);
+  cudaFree(batch->d_sample_off);
+  cudaFree(batch->d_frame_off);
+  cudaFree(batch->d_tiles);
+  delete batch;
+  return EVF_OK;
+}
+
+int evf_batch_total_frames(const evf_batch* batch, int64_t* total_frames_out) {
+  if (!batch || !total_frames_out) {
+    set_error("evf_batch_total_frames: null argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  *total_frames_out = batch->total_frames;
+  return EVF_OK;
+}
+
+int evf_batch_frame_offsets(const evf_batch* batch, int64_t* frame_offsets_host_out) {
+  if (!batch || !frame_offsets_host_out) {
+    set_error("evf_batch_frame_offsets: null argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  memcpy(frame_offsets_host_out, batch->frame_off.data(), batch->frame_off.size() * sizeof(int64_t));
+  return EVF_OK;
+}
+
+int evf_batch_frame_offsets_dev(const evf_batch* batch, const int64_t** frame_offsets_dev_out) {
+  if (!batch || !frame_offsets_dev_out) {
+    set_error("evf_batch_frame_offsets_dev: null argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  *frame_offsets_dev_out = reinterpret_cast<const int64_t*>(batch->d_frame_off);
+  return EVF_OK;
+}
+
+int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* samples_dev,
+                     float* spec_out_dev, float* energy_out_dev, void* stream) {
+  if (!plan || !batch) {
+    set_error("evf_features_run: null plan or batch");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (batch->device != plan->device) {
+    set_error("evf_features_run: plan and batch live on different devices");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (batch->n_tiles == 0) return EVF_OK;
+  if (!samples_dev || !spec_out_dev) {
+    set_error("evf_features_run: null sample or output pointer");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  DeviceGuard guard(plan->device);
+  FeatParams p = plan->carve;
+  p.samples = samples_dev;
+  p.sample_off = batch->d_sample_off;
+  p.frame_off = batch->d_frame_off;
+  p.tiles = batch->d_tiles;
+  p.n_tiles = batch->n_tiles;
+  p.spec_out = spec_out_dev;
+  p.energy_out = (plan->cfg.spec_type == EVF_SPEC_RAW) ? nullptr : energy_out_dev;
+  p.window = plan->d_window;
+  p.tw = plan->d_tw;
+  p.wpost = plan->d_wpost;
+  p.melw = plan->d_melw;
+  p.kstart = plan->d_kstart;
+  p.vw_m = plan->d_vwm;
+  p.hop = plan->cfg.hop_length;
+  p.n_mels = plan->cfg.n_mels;
+  p.n_freq = plan->n_freq;
+  p.k_used = plan->k_used;
+  p.row_floats = plan->row_floats;
+  p.apply_log = (plan->cfg.spec_type == EVF_SPEC_RAW) ? 0 : plan->cfg.apply_log;
+  p.log_clip = plan->cfg.log_clip;
+  const int grid = batch->n_tiles < plan->num_sms ? batch->n_tiles : plan->num_sms;
+  return features_launch(plan->mode, plan->cfg.spec_type, plan->cfg.sample_format, p, grid,
+                         plan->smem_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int evf_features_ragged(const evf_plan* plan, const void* samples_dev,
+                        const int64_t* sample_offsets_host, int32_t n_utts, float* spec_out_dev,
+                        float* energy_out_dev, int64_t* frame_offsets_host_out, void* stream) {
+  evf_batch* bt = nullptr;
+  int rc = evf_batch_create(plan, sample_offsets_host, n_utts, &bt);
+  if (rc != EVF_OK) return rc;
+  if (frame_offsets_host_out) evf_batch_frame_offsets(bt, frame_offsets_host_out);
+  rc = evf_features_run(plan, bt, samples_dev, spec_out_dev, energy_out_dev, stream);
+  // The kernel reads the batch tables asynchronously: wait before freeing them.
+  if (rc == EVF_OK) {
+    DeviceGuard guard(plan->device);
+    cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+  }
+  evf_batch_destroy(bt);
+  return rc;
+}
+
+int evf_energy_from_spec(const float* spec_dev, int64_t n_frames, int32_t row_floats,
+                         float* energy_out_dev, void* stream) {
+  if (n_frames < 0 || row_floats < 1 || (n_frames > 0 && (!spec_dev || !energy_out_dev))) {
+    set_error("evf_energy_from_spec: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_energy_from_spec(spec_dev, n_frames, row_floats, energy_out_dev,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int evf_log_compress(const float* in_dev, float* out_dev, int64_t n, float c, float clip_val,
+                     void* stream) {
+  if (n < 0 || (n > 0 && (!in_dev || !out_dev))) {
+    set_error("evf_log_compress: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_log_compress(in_dev, out_dev, n, c, clip_val, static_cast<cudaStream_t>(stream));
+}
+
+int evf_segment_mean(const float* values_dev, const int64_t* value_offsets_dev,
+                     const int64_t* durations_dev, const int64_t* phone_offsets_dev,
+                     int32_t n_utts, float* out_dev, void* stream) {
+  if (n_utts < 0 || (n_utts > 0 && (!value_offsets_dev || !phone_offsets_dev))) {
+    set_error("evf_segment_mean: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_segment_mean(values_dev, value_offsets_dev, durations_dev, phone_offsets_dev,
+                             n_utts, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int evf_stats_partial(const float* values_dev, int64_t n, double* out5_dev, int32_t accumulate,
+                      void* stream) {
+  if (n < 0 || !out5_dev || (n > 0 && !values_dev)) {
+    set_error("evf_stats_partial: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_stats_partial(values_dev, n, out5_dev, accumulate, static_cast<cudaStream_t>(stream));
+}
+
+int evf_normalize_inplace(float* values_dev, int64_t n, float mean, float std, void* stream) {
+  if (n < 0 || (n > 0 && !values_dev)) {
+    set_error("evf_normalize_inplace: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_normalize(values_dev, n, mean, std, static_cast<cudaStream_t>(stream));
+}
+
+int evf_normalize_by_stats(float* values_dev, int64_t n, const double* stats5_dev, void* stream) {
+  if (n < 0 || !stats5_dev || (n > 0 && !values_dev)) {
+    set_error("evf_normalize_by_stats: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_normalize_by_stats(values_dev, n, stats5_dev, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,451 @@
+// Fused framing -> window -> FFT -> |X|^2 -> mel -> log -> energy kernel (sm_100a).
+//
+// Replaces, for a ragged batch of utterances in one launch, what the reference does per
+// utterance through torchaudio on the CPU:
+//   everyvoice/utils/heavy.py:47-113            get_spectral_transform (mel / mel-librosa / linear / raw)
+//   everyvoice/utils/heavy.py:39-40             dynamic_range_compression_torch
+//   everyvoice/preprocessor/preprocessor.py:220-233, 921-927   extract_spectral_features + [:, :L//hop]
+//   everyvoice/preprocessor/preprocessor.py:302-309            extract_energy
+//
+// Work decomposition
+//   grid   : persistent, one CTA of 16 warps per SM, static round-robin over frame tiles
+//   tile   : 16 FFT jobs of one utterance = 32 consecutive frames (n_fft 1024: two real
+//            frames ride as re/im of one complex FFT) or 16 frames (n_fft 2048: one frame
+//            = 1024 complex points + real-FFT split)
+//   phase 0: the tile's sample span ((FR-1)*hop + n_fft samples; every sample is read from
+//            HBM once, the 4x frame overlap is served from shared memory) is staged with
+//            reflect padding resolved by index mirroring at the utterance edges
+//   phase A: one warp per FFT job: window * samples -> registers, 32x32 four-step FFT
+//            (in-register radix-2 DFT-32, transpose + twiddle through shared memory),
+//            real-FFT separation with the mirrored bin fetched by warp shuffle, |X|^2
+//            (or sqrt(|X|^2+1e-9) for mel-librosa) -> shared P[bin][frame];
+//            linear / raw write straight to HBM (lanes = consecutive bins, coalesced)
+//   phase B: mel projection with lane = frame: all lanes walk the same bins, weights are
+//            warp-uniform; each bin lies between two adjacent filter centres so it feeds
+//            exactly two filters: two running FMAs per bin, no atomics, no divergence
+//   phase C: log-mel tile -> HBM (coalesced rows) + per-frame energy = sqrt(sum log^2)
+#include "evfeat_fft.cuh"
+#include "evfeat_internal.h"
+
+namespace evf {
+
+namespace {
+
+template <int MODE>
+struct ModeTraits;
+template <>
+struct ModeTraits<MODE_PACK2> {
+  static constexpr int kNfft = 1024;
+  static constexpr int kFramesPerJob = 2;
+};
+template <>
+struct ModeTraits<MODE_HALF> {
+  static constexpr int kNfft = 2048;
+  static constexpr int kFramesPerJob = 1;
+};
+
+__device__ __forceinline__ float load_sample(const float* p, long long i) { return __ldg(p + i); }
+__device__ __forceinline__ float load_sample(const short* p, long long i) {
+  return (float)__ldg(p + i) * (1.0f / 32768.0f);
+}
+
+__device__ __forceinline__ float compress(float v, int apply_log, float clip) {
+  if (apply_log) {
+    v = (v < clip) ? clip : v;  // torch.clamp(min=clip): NaN propagates
+    v = __logf(v);
+  }
+  return v;
+}
+
+// 1024-point complex FFT of the 32x32 values held by one warp.
+// In : lane n2 holds z[32*n1 + n2] at index n1.
+// Out: lane k1 holds Z[k1 + 32*k2] at index bitrev5(k2).
+__device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32],
+                                             const float2* __restrict__ s_tw,
+                                             float* __restrict__ scr, int lane) {
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    dft32_dif(re, im);
+    if (pass == 0) {
+      // index p now holds k1 = bitrev5(p); multiply by W_1024^(n2*k1) (table is stored
+      // by register position) and hand element k1 to lane k1.
+#pragma unroll
+      for (int p = 1; p < 32; ++p) {
+        float2 t = s_tw[p * 32 + lane];
+        float a = fmaf(-im[p], t.y, re[p] * t.x);
+        float b = fmaf(re[p], t.y, im[p] * t.x);
+        re[p] = a;
+        im[p] = b;
+      }
+#pragma unroll
+      for (int p = 0; p < 32; ++p) scr[bitrev5(p) * kScrStride + lane] = re[p];
+      __syncwarp();
+#pragma unroll
+      for (int n = 0; n < 32; ++n) re[n] = scr[lane * kScrStride + n];
+      __syncwarp();
+#pragma unroll
+      for (int p = 0; p < 32; ++p) scr[bitrev5(p) * kScrStride + lane] = im[p];
+      __syncwarp();
+#pragma unroll
+      for (int n = 0; n < 32; ++n) im[n] = scr[lane * kScrStride + n];
+      __syncwarp();
+    }
+  }
+}
+
+template <int MODE, int SPEC, typename SampleT>
+__global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams p) {
+  using MT = ModeTraits<MODE>;
+  constexpr int NFFT = MT::kNfft;
+  constexpr int FPJ = MT::kFramesPerJob;
+  constexpr int FR = kWarps * FPJ;        // frames per tile
+  constexpr int FS = FR + 1;              // padded frame stride of the P tile
+  constexpr int PARTS = 32 / FR;          // projection workers per warp
+  constexpr bool kMel = (SPEC == EVF_SPEC_MEL || SPEC == EVF_SPEC_MEL_LIBROSA);
+
+  extern __shared__ __align__(16) float smem[];
+  float* s_in = smem + p.off_in;
+  float* s_win = smem + p.off_win;
+  float2* s_tw = reinterpret_cast<float2*>(smem + p.off_tw);
+  float2* s_wpost = reinterpret_cast<float2*>(smem + p.off_wpost);
+  float2* s_melw = reinterpret_cast<float2*>(smem + p.off_melw);
+  int* s_kstart = reinterpret_cast<int*>(smem + p.off_kstart);
+  int* s_vwm = reinterpret_cast<int*>(smem + p.off_vwm);
+  float* s_p = smem + p.off_p;
+  float* s_out = smem + p.off_sout;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  float* scr = smem + p.off_scr + warp * (32 * kScrStride);
+
+  // ---- one-time table copy ------------------------------------------------------------
+  for (int i = tid; i < NFFT; i += kThreads) s_win[i] = p.window[i];
+  for (int i = tid; i < kFftSize; i += kThreads) s_tw[i] = p.tw[i];
+  if constexpr (MODE == MODE_HALF) {
+    for (int i = tid; i <= 512; i += kThreads) s_wpost[i] = p.wpost[i];
+  }
+  if constexpr (kMel) {
+    for (int i = tid; i < p.k_used; i += kThreads) s_melw[i] = p.melw[i];
+    for (int i = tid; i < p.n_mels + 2; i += kThreads) s_kstart[i] = p.kstart[i];
+    for (int i = tid; i < kWarps * PARTS + 1; i += kThreads) s_vwm[i] = p.vw_m[i];
+  }
+
+  const int hop = p.hop;
+  const SampleT* __restrict__ samples = static_cast<const SampleT*>(p.samples);
+
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int2 tl = p.tiles[tile];
+    const int utt = tl.x, f0 = tl.y;
+    const long long s_off = p.sample_off[utt];
+    const long long L = p.sample_off[utt + 1] - s_off;
+    const long long fr_off = p.frame_off[utt];
+    const int T = (int)(p.frame_off[utt + 1] - fr_off);
+    const int nvalid = min(FR, T - f0);
+    const long long out_frame0 = fr_off + f0;
+
+    // ---- phase 0: stage the sample span, reflect padding by index mirroring ------------
+    {
+      const int njobs = (nvalid + FPJ - 1) / FPJ;
+      const int span = (njobs * FPJ - 1) * hop + NFFT;
+      const long long start = (long long)f0 * hop - NFFT / 2;
+      const SampleT* src = samples + s_off;
+      for (int i = tid; i < span; i += kThreads) {
+        long long j = start + i;
+        j = (j < 0) ? -j : j;
+        j = (j >= L) ? 2 * (L - 1) - j : j;
+        j = (j < 0) ? 0 : j;  // only reachable for frames beyond the last valid one
+        s_in[i] = load_sample(src, j);
+      }
+    }
+    __syncthreads();
+
+    // ---- phase A: one FFT job per warp ------------------------------------------------
+    if (warp * FPJ < nvalid) {
+      float re[32], im[32];
+      if constexpr (MODE == MODE_PACK2) {
+        const float* xa = s_in + (2 * warp) * hop + lane;
+        const float* xb = xa + hop;
+        const float* wv = s_win + lane;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          float w = wv[32 * n1];
+          re[n1] = w * xa[32 * n1];
+          im[n1] = w * xb[32 * n1];
+        }
+      } else {
+        const float2* x2 = reinterpret_cast<const float2*>(s_in + warp * hop) + lane;
+        const float2* w2 = reinterpret_cast<const float2*>(s_win) + lane;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          float2 w = w2[32 * n1];
+          float2 x = x2[32 * n1];
+          re[n1] = w.x * x.x;
+          im[n1] = w.y * x.y;
+        }
+      }
+      warp_fft1024(re, im, s_tw, scr, lane);
+
+      // ---- real-FFT separation; the mirrored bin lives in lane (32 - lane) % 32 -------
+      const int src_lane = (32 - lane) & 31;
+      const int fa = warp * FPJ;  // tile-local frame of this job (PACK2: fa and fa + 1)
+      float esum_a = 0.f, esum_b = 0.f;
+      float* ga = p.spec_out + (out_frame0 + fa) * (long long)p.row_floats;
+      float* gb = ga + p.row_floats;
+      const bool b_valid = (MODE == MODE_PACK2) && (fa + 1 < nvalid);
+      const int kcap = kMel ? p.k_used : (NFFT / 2 + 1);
+
+#pragma unroll
+      for (int j = 0; j <= 16; ++j) {
+        const int k = lane + 32 * j;
+        {  // warp-uniform: does any lane of this row own a bin that is consumed?
+          bool need = 32 * j < kcap;
+          if constexpr (MODE == MODE_HALF) need = need || (1024 - 32 * j - 31 < kcap);
+          if (!need) continue;
+        }
+        float zr, zi, pr, pi;
+        if (j < 16) {
+          zr = re[bitrev5(j)];
+          zi = im[bitrev5(j)];
+          pr = __shfl_sync(0xffffffffu, re[bitrev5(31 - j)], src_lane);
+          pi = __shfl_sync(0xffffffffu, im[bitrev5(31 - j)], src_lane);
+          if (lane == 0) {
+            pr = re[bitrev5((32 - j) & 31)];
+            pi = im[bitrev5((32 - j) & 31)];
+          }
+        } else {  // bin 512 (lane 0 only): its own mirror
+          zr = pr = re[bitrev5(16)];
+          zi = pi = im[bitrev5(16)];
+          if (lane != 0) continue;
+        }
+        if constexpr (MODE == MODE_PACK2) {
+          // window was pre-scaled by 1/2: X_a = Z[k] + conj(Z[N-k]), X_b = (Z[k] - conj(Z[N-k])) / i
+          const float ar = zr + pr, ai = zi - pi;
+          const float br = zi + pi, bi = pr - zr;
+          if constexpr (SPEC == EVF_SPEC_RAW) {
+            if (k <= 512) {
+              reinterpret_cast<float2*>(ga)[k] = make_float2(ar, ai);
+              if (b_valid) reinterpret_cast<float2*>(gb)[k] = make_float2(br, bi);
+            }
+          } else {
+            float pa = fmaf(ar, ar, ai * ai);
+            float pb = fmaf(br, br, bi * bi);
+            if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
+              pa = sqrtf(pa + 1e-9f);
+              pb = sqrtf(pb + 1e-9f);
+            }
+            if constexpr (kMel) {
+              if (k < kcap) {
+                s_p[k * FS + fa] = pa;
+                s_p[k * FS + fa + 1] = pb;
+              }
+            } else {
+              if (k <= 512) {
+                const float va = compress(pa, p.apply_log, p.log_clip);
+                const float vb = compress(pb, p.apply_log, p.log_clip);
+                ga[k] = va;
+                esum_a = fmaf(va, va, esum_a);
+                if (b_valid) {
+                  gb[k] = vb;
+                  esum_b = fmaf(vb, vb, esum_b);
+                }
+              }
+            }
+          }
+        } else {
+          // X[k] = E - T, X[M-k] = conj(E + T), E = Z[k] + conj(Z[M-k]), T = i * w_k * (Z[k] - conj(Z[M-k]))
+          const float er = zr + pr, ei = zi - pi;
+          const float orr = zr - pr, oi = zi + pi;
+          const float2 w = s_wpost[k];  // (cos, -sin)(2 pi k / 2048)
+          const float tr = -fmaf(w.x, oi, w.y * orr);
+          const float ti = fmaf(w.x, orr, -w.y * oi);
+          const float x0r = er - tr, x0i = ei - ti;      // bin k
+          const float x1r = er + tr, x1i = -(ei + ti);   // bin 1024 - k
+          const int km = 1024 - k;
+          const bool has_mirror = (j < 16);              // k == 512 is its own mirror
+          if constexpr (SPEC == EVF_SPEC_RAW) {
+            reinterpret_cast<float2*>(ga)[k] = make_float2(x0r, x0i);
+            if (has_mirror) reinterpret_cast<float2*>(ga)[km] = make_float2(x1r, x1i);
+          } else {
+            float p0 = fmaf(x0r, x0r, x0i * x0i);
+            float p1 = fmaf(x1r, x1r, x1i * x1i);
+            if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
+              p0 = sqrtf(p0 + 1e-9f);
+              p1 = sqrtf(p1 + 1e-9f);
+            }
+            if constexpr (kMel) {
+              if (k < kcap) s_p[k * FS + fa] = p0;
+              if (has_mirror && km < kcap) s_p[km * FS + fa] = p1;
+            } else {
+              const float v0 = compress(p0, p.apply_log, p.log_clip);
+              ga[k] = v0;
+              esum_a = fmaf(v0, v0, esum_a);
+              if (has_mirror) {
+                const float v1 = compress(p1, p.apply_log, p.log_clip);
+                ga[km] = v1;
+                esum_a = fmaf(v1, v1, esum_a);
+              }
+            }
+          }
+        }
+      }
+      if constexpr (SPEC == EVF_SPEC_LINEAR) {
+        if (p.energy_out != nullptr) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            esum_a += __shfl_xor_sync(0xffffffffu, esum_a, o);
+            esum_b += __shfl_xor_sync(0xffffffffu, esum_b, o);
+          }
+          if (lane == 0) {
+            p.energy_out[out_frame0 + fa] = sqrtf(esum_a);
+            if (b_valid) p.energy_out[out_frame0 + fa + 1] = sqrtf(esum_b);
+          }
+        }
+      }
+    }
+
+    if constexpr (kMel) {
+      __syncthreads();
+      // ---- phase B: mel projection, lane = frame ---------------------------------------
+      {
+        const int fr = lane % FR;
+        const int vw = warp * PARTS + lane / FR;
+        const int m0 = s_vwm[vw], m1 = s_vwm[vw + 1];
+        if (m0 < m1) {
+          const float* pcol = s_p + fr;
+          float sa_prev = 0.f;
+          for (int j = m0; j <= m1; ++j) {
+            const int kb = s_kstart[j], ke = s_kstart[j + 1];
+            float sa = 0.f, sb = 0.f;
+            for (int k = kb; k < ke; ++k) {
+              const float pv = pcol[k * FS];
+              const float2 w = s_melw[k];
+              sa = fmaf(w.x, pv, sa);
+              sb = fmaf(w.y, pv, sb);
+            }
+            if (j > m0) s_out[fr * p.sout_stride + (j - 1)] = compress(sa_prev + sb, p.apply_log, p.log_clip);
+            sa_prev = sa;
+          }
+        }
+      }
+      __syncthreads();
+      // ---- phase C: coalesced store of the log-mel rows + per-frame energy --------------
+#pragma unroll
+      for (int q = 0; q < FPJ; ++q) {
+        const int f = warp * FPJ + q;
+        if (f < nvalid) {
+          const float* row = s_out + f * p.sout_stride;
+          float* dst = p.spec_out + (out_frame0 + f) * (long long)p.row_floats;
+          float acc = 0.f;
+          for (int m = lane; m < p.n_mels; m += 32) {
+            const float v = row[m];
+            dst[m] = v;
+            acc = fmaf(v, v, acc);
+          }
+          if (p.energy_out != nullptr) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) p.energy_out[out_frame0 + f] = sqrtf(acc);
+          }
+        }
+      }
+    } else {
+      __syncthreads();  // the input tile is about to be overwritten
+    }
+  }
+}
+
+template <int MODE, int SPEC, typename SampleT>
+int launch_t(const FeatParams& p, int grid, int smem, cudaStream_t stream, bool configure_only) {
+  auto kern = features_kernel<MODE, SPEC, SampleT>;
+  if (configure_only) {
+    EVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return EVF_OK;
+  }
+  kern<<<grid, kThreads, smem, stream>>>(p);
+  EVF_CUDA(cudaGetLastError());
+  return EVF_OK;
+}
+
+template <int MODE, int SPEC>
+int launch_s(int fmt, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
+  if (fmt == EVF_SAMPLES_S16) return launch_t<MODE, SPEC, short>(p, grid, smem, st, cfg);
+  return launch_t<MODE, SPEC, float>(p, grid, smem, st, cfg);
+}
+
+template <int MODE>
+int launch_m(int spec, int fmt, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
+  switch (spec) {
+    case EVF_SPEC_MEL: return launch_s<MODE, EVF_SPEC_MEL>(fmt, p, grid, smem, st, cfg);
+    case EVF_SPEC_MEL_LIBROSA: return launch_s<MODE, EVF_SPEC_MEL_LIBROSA>(fmt, p, grid, smem, st, cfg);
+    case EVF_SPEC_LINEAR: return launch_s<MODE, EVF_SPEC_LINEAR>(fmt, p, grid, smem, st, cfg);
+    case EVF_SPEC_RAW: return launch_s<MODE, EVF_SPEC_RAW>(fmt, p, grid, smem, st, cfg);
+  }
+  set_error("unknown spec_type");
+  return EVF_ERR_UNSUPPORTED;
+}
+
+int dispatch(int mode, int spec, int fmt, const FeatParams& p, int grid, int smem, cudaStream_t st,
+             bool cfg) {
+  if (mode == MODE_PACK2) return launch_m<MODE_PACK2>(spec, fmt, p, grid, smem, st, cfg);
+  if (mode == MODE_HALF) return launch_m<MODE_HALF>(spec, fmt, p, grid, smem, st, cfg);
+  set_error("unknown FFT mode");
+  return EVF_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+// Computes the shared-memory carve-up for a plan; returns bytes (or -1 if it cannot fit).
+int features_smem_bytes(int mode, int spec_type, int hop, int n_fft, int n_mels, int k_used,
+                        FeatParams* c) {
+  const bool mel = (spec_type == EVF_SPEC_MEL || spec_type == EVF_SPEC_MEL_LIBROSA);
+  const int fpj = (mode == MODE_PACK2) ? 2 : 1;
+  const int fr = kWarps * fpj;
+  const int parts = 32 / fr;
+  auto up4 = [](int w) { return (w + 3) & ~3; };
+  int w = 0;
+  c->off_in = w;
+  c->in_words = up4((fr - 1) * hop + n_fft);
+  w += c->in_words;
+  c->off_win = w;
+  w += up4(n_fft);
+  c->off_tw = w;
+  w += 2 * kFftSize;
+  c->off_wpost = w;
+  if (mode == MODE_HALF) w += up4(2 * 513);
+  c->off_melw = w;
+  c->off_kstart = w;
+  c->off_vwm = w;
+  c->off_p = w;
+  c->off_sout = w;
+  c->sout_stride = 1;
+  if (mel) {
+    w += up4(2 * k_used);
+    c->off_kstart = w;
+    w += up4(n_mels + 2);
+    c->off_vwm = w;
+    w += up4(kWarps * parts + 1);
+    c->off_p = w;
+    w += up4(k_used * (fr + 1));
+    c->off_sout = w;
+    c->sout_stride = n_mels | 1;
+    w += up4(fr * c->sout_stride);
+  }
+  c->off_scr = w;
+  w += kWarps * 32 * kScrStride;
+  const long long bytes = 4ll * w;
+  if (bytes > 227 * 1024) return -1;
+  return (int)bytes;
+}
+
+int features_configure(int mode, int spec_type, int sample_format, int smem_bytes) {
+  FeatParams dummy{};
+  return dispatch(mode, spec_type, sample_format, dummy, 1, smem_bytes, nullptr, true);
+}
+
+int features_launch(int mode, int spec_type, int sample_format, const FeatParams& p, int grid,
+                    int smem_bytes, cudaStream_t stream) {
+  return dispatch(mode, spec_type, sample_format, p, grid, smem_bytes, stream, false);
+}
+
+}  // namespace evf

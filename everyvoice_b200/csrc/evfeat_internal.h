@@ -1,0 +1,86 @@
+// Internal (non-ABI) declarations shared by the translation units of libevfeat.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "evfeat.h"
+
+namespace evf {
+
+constexpr int kWarps = 16;           // warps per CTA; one 1024-point complex FFT per warp per tile
+constexpr int kThreads = kWarps * 32;
+constexpr int kFftSize = 1024;       // complex points per warp-level FFT
+constexpr int kScrStride = 33;       // padded row stride of the per-warp transpose scratch
+
+enum FftMode : int {
+  MODE_PACK2 = 0,  // n_fft == 1024: two real frames packed as re/im of one complex FFT
+  MODE_HALF = 1,   // n_fft == 2048: one real frame as a 1024-point complex FFT + split
+};
+
+// Kernel parameters (passed by value; lives in the constant bank).
+struct FeatParams {
+  const void* samples;
+  const long long* sample_off;  // [B+1]
+  const long long* frame_off;   // [B+1]
+  const int2* tiles;            // (utterance, first frame)
+  int n_tiles;
+  float* spec_out;
+  float* energy_out;
+  // plan tables (global memory; copied to shared memory once per CTA)
+  const float* window;   // [n_fft], pre-scaled by 0.5
+  const float2* tw;      // [32][32] inter-pass twiddles, indexed [register position][lane]
+  const float2* wpost;   // MODE_HALF: exp(-2 pi i k / n_fft), k = 0..512
+  const float2* melw;    // [k_used] (rising weight -> mel j(k), falling weight -> mel j(k)-1)
+  const int* kstart;     // [n_mels + 2] first bin of every inter-centre interval
+  const int* vw_m;       // [n_vw + 1] mel range of every virtual worker of the projection phase
+  int hop;
+  int n_mels;
+  int n_freq;
+  int k_used;            // bins [0, k_used) carry a non-zero mel weight
+  int row_floats;
+  int apply_log;
+  float log_clip;
+  // shared-memory carve-up, in 4-byte words from the start of dynamic shared memory
+  int off_in, off_win, off_tw, off_wpost, off_melw, off_kstart, off_vwm, off_p, off_scr, off_sout;
+  int in_words;          // capacity of the input tile
+  int sout_stride;       // odd row stride of the output staging tile
+};
+
+struct PlanTables {
+  std::vector<float> window;      // n_fft, pre-scaled
+  std::vector<float2> tw;         // 1024
+  std::vector<float2> wpost;      // 513 (MODE_HALF) or empty
+  std::vector<float2> melw;       // k_used
+  std::vector<int> kstart;        // n_mels + 2
+  std::vector<int> vw_m;          // n_vw + 1
+  int k_used = 0;
+};
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+#define EVF_CUDA(call)                                          \
+  do {                                                          \
+    cudaError_t e_ = (call);                                    \
+    if (e_ != cudaSuccess) return ::evf::cuda_fail(e_, #call);  \
+  } while (0)
+
+// evfeat_features.cu
+int features_smem_bytes(int mode, int spec_type, int hop, int n_fft, int n_mels, int k_used,
+                        FeatParams* carve);
+int features_configure(int mode, int spec_type, int sample_format, int smem_bytes);
+int features_launch(int mode, int spec_type, int sample_format, const FeatParams& p, int grid,
+                    int smem_bytes, cudaStream_t stream);
+
+// evfeat_aux.cu
+int launch_energy_from_spec(const float* spec, int64_t n_frames, int row, float* out, cudaStream_t s);
+int launch_segment_mean(const float* values, const int64_t* value_off, const int64_t* durations,
+                        const int64_t* phone_off, int n_utts, float* out, cudaStream_t s);
+int launch_stats_partial(const float* values, int64_t n, double* out5, int accumulate, cudaStream_t s);
+int launch_normalize(float* values, int64_t n, float mean, float std, cudaStream_t s);
+int launch_normalize_by_stats(float* values, int64_t n, const double* stats5, cudaStream_t s);
+int launch_log_compress(const float* in, float* out, int64_t n, float c, float clip, cudaStream_t s);
+
+}  // namespace evf

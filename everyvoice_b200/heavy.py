@@ -1,0 +1,313 @@
+"""Drop-in for the hot-path half of ``everyvoice/utils/heavy.py`` on a B200.
+
+Same names, same arguments, same shapes as the reference:
+
+* ``get_spectral_transform(spec_type, n_fft, win_length, hop_length, sample_rate=None,
+  n_mels=None, f_min=0, f_max=8000)``  (reference: utils/heavy.py:47-119) returns a
+  callable ``y = t(x)``, ``x[..., L] -> y[..., F, 1 + L//hop]`` or ``None`` for an
+  unsupported type (so ``Preprocessor.__init__`` raises its ``ConfigError``);
+* ``dynamic_range_compression_torch(x, C=1, clip_val=1e-5)``  (utils/heavy.py:39-40).
+
+Everything numeric runs in ``libevfeat.so`` (hand-written sm_100a kernels) through the C
+ABI of ``include/evfeat.h``.  There is no CPU / PyTorch fallback: without the library or a
+CUDA device these calls raise.  CPU tensors are accepted for drop-in compatibility with
+the reference's call sites (they are copied to the GPU and the result is copied back).
+
+The batched, ragged entry points (``SpectralTransform.make_batch`` / ``run`` /
+``features_ragged``) are the throughput path used by ``Preprocessor`` and ``bench.py``:
+one launch computes log-spectrogram + energy for a whole packed batch of utterances.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, filterbanks
+from .config import AudioSpecTypeEnum
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "everyvoice_b200 needs a CUDA sm_100 (B200) device; it has no CPU or PyTorch fallback"
+        )
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"everyvoice_b200 only runs on CUDA devices, not {device}")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def _stream_ptr(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class _Plan:
+    """Owns one ``evf_plan`` (immutable after creation)."""
+
+    def __init__(self, tf: "SpectralTransform", device: torch.device, apply_log: bool,
+                 keep_last: bool, sample_format: int):
+        lib = _lib.load()
+        cfg = _lib.evf_config(
+            spec_type=_lib.SPEC_TYPES[tf.spec_type],
+            sample_rate=int(tf.sample_rate or 0),
+            n_fft=tf.n_fft,
+            win_length=tf.win_length,
+            hop_length=tf.hop_length,
+            n_mels=int(tf.n_mels or 0),
+            apply_log=int(apply_log),
+            keep_last_frame=int(keep_last),
+            sample_format=sample_format,
+            log_clip=1e-5,
+        )
+        win = tf.window.contiguous()
+        fb = tf.mel_fb.contiguous() if tf.mel_fb is not None else None
+        handle = C.c_void_p()
+        _lib.check(lib.evf_plan_create(C.byref(cfg), _ptr(win), _ptr(fb), device.index, C.byref(handle)))
+        self._lib = lib
+        self.handle = handle
+        self.device = device
+        self.apply_log = apply_log
+        self.keep_last = keep_last
+        self.sample_format = sample_format
+        rf = C.c_int32()
+        _lib.check(lib.evf_plan_row_floats(handle, C.byref(rf)))
+        self.row_floats = rf.value
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                self._lib.evf_plan_destroy(h)
+            except Exception:
+                pass
+
+
+class RaggedBatch:
+    """Owns one ``evf_batch``: per-utterance frame counts / offsets and the tile work list
+    for a packed ragged batch (utterance ``b`` = samples ``[offsets[b], offsets[b+1])``)."""
+
+    def __init__(self, plan: _Plan, sample_offsets):
+        off = np.ascontiguousarray(np.asarray(sample_offsets, dtype=np.int64))
+        if off.ndim != 1 or off.size < 1:
+            raise ValueError("sample_offsets must be a 1-D array of B+1 offsets")
+        lib = plan._lib
+        self._lib = lib
+        self.plan = plan
+        self.n_utts = int(off.size - 1)
+        self.sample_offsets = off
+        handle = C.c_void_p()
+        _lib.check(lib.evf_batch_create(plan.handle, off.ctypes.data_as(C.c_void_p), self.n_utts, C.byref(handle)))
+        self.handle = handle
+        tf = C.c_int64()
+        _lib.check(lib.evf_batch_total_frames(handle, C.byref(tf)))
+        self.total_frames = int(tf.value)
+        fo = np.zeros(self.n_utts + 1, dtype=np.int64)
+        _lib.check(lib.evf_batch_frame_offsets(handle, fo.ctypes.data_as(C.c_void_p)))
+        self.frame_offsets = fo
+        dev = C.c_void_p()
+        _lib.check(lib.evf_batch_frame_offsets_dev(handle, C.byref(dev)))
+        self.frame_offsets_dev_ptr = dev.value  # int64[n_utts+1] on the device, owned by the batch
+
+    @property
+    def total_samples(self) -> int:
+        return int(self.sample_offsets[-1] - self.sample_offsets[0])
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                self._lib.evf_batch_destroy(h)
+            except Exception:
+                pass
+
+
+@dataclass
+class RaggedFeatures:
+    spec: torch.Tensor            # [total_frames, row_floats] time-major, packed
+    energy: torch.Tensor | None   # [total_frames]
+    frame_offsets: np.ndarray     # int64[B+1]
+    n_rows: int                   # F (n_mels or n_fft//2+1)
+    is_complex: bool = False
+
+    def utterance(self, b: int) -> torch.Tensor:
+        """``[F, T_b]`` view of utterance ``b`` -- the layout the reference returns."""
+        s = self.spec[self.frame_offsets[b] : self.frame_offsets[b + 1]]
+        if self.is_complex:
+            s = torch.view_as_complex(s.view(s.shape[0], self.n_rows, 2))
+        return s.transpose(0, 1)
+
+    def utterance_energy(self, b: int) -> torch.Tensor:
+        return self.energy[self.frame_offsets[b] : self.frame_offsets[b + 1]]
+
+
+class SpectralTransform:
+    """The object ``get_spectral_transform`` returns.  ``t(x)`` mirrors the torchaudio
+    transform the reference builds (linear-domain output, all ``1 + L//hop`` frames);
+    ``t.features(...)`` / ``t.run(...)`` are the fused log + energy paths."""
+
+    def __init__(self, spec_type, n_fft, win_length, hop_length, sample_rate=None, n_mels=None,
+                 f_min=0, f_max=8000, device=None):
+        spec_type = getattr(spec_type, "value", spec_type)
+        if spec_type not in _lib.SPEC_TYPES:
+            raise ValueError(f"unsupported spec_type {spec_type!r}")
+        self.spec_type = spec_type
+        self.n_fft, self.win_length, self.hop_length = int(n_fft), int(win_length), int(hop_length)
+        self.sample_rate, self.n_mels, self.f_min, self.f_max = sample_rate, n_mels, f_min, f_max
+        self.n_freqs = self.n_fft // 2 + 1
+        self.window = filterbanks.hann_window_padded(self.win_length, self.n_fft)
+        if spec_type == "mel":  # heavy.py:57-68
+            self.mel_fb = filterbanks.melscale_fbanks_htk_slaney(
+                self.n_freqs, float(f_min), float(f_max if f_max is not None else sample_rate // 2),
+                int(n_mels), int(sample_rate))
+        elif spec_type == "mel-librosa":  # heavy.py:69-100
+            self.mel_fb = filterbanks.librosa_mel_basis(int(sample_rate), self.n_fft, int(n_mels), f_min, f_max)
+        else:
+            self.mel_fb = None
+        self.is_complex = spec_type == "raw"
+        self.n_rows = int(n_mels) if self.mel_fb is not None else self.n_freqs
+        self._device = None if device is None else _require_cuda(device)
+        self._plans: dict = {}
+
+    # -- nn.Module-ish surface the reference relies on -----------------------------------
+    def to(self, device):
+        self._device = _require_cuda(device)
+        return self
+
+    def __repr__(self):
+        return (f"SpectralTransform(spec_type={self.spec_type!r}, n_fft={self.n_fft}, win_length={self.win_length}, "
+                f"hop_length={self.hop_length}, sample_rate={self.sample_rate}, n_mels={self.n_mels}, "
+                f"f_min={self.f_min}, f_max={self.f_max})")
+
+    # -- plans / batches --------------------------------------------------------------------
+    def _resolve_device(self, x: torch.Tensor | None = None) -> torch.device:
+        if x is not None and x.is_cuda:
+            return x.device
+        return self._device if self._device is not None else _require_cuda(None)
+
+    def plan(self, device=None, apply_log=True, keep_last=False, sample_format=_lib.SAMPLES_F32) -> _Plan:
+        device = _require_cuda(device if device is not None else self._device)
+        key = (device.index, bool(apply_log), bool(keep_last), int(sample_format))
+        p = self._plans.get(key)
+        if p is None:
+            p = self._plans[key] = _Plan(self, device, bool(apply_log), bool(keep_last), int(sample_format))
+        return p
+
+    def num_frames(self, n_samples: int, keep_last=False) -> int:
+        """``L // hop`` (what ``process_spec`` keeps, preprocessor.py:921) or ``L // hop + 1``."""
+        return int(n_samples) // self.hop_length + (1 if keep_last else 0)
+
+    def make_batch(self, sample_offsets, device=None, apply_log=True, keep_last=False,
+                   sample_dtype=torch.float32) -> RaggedBatch:
+        fmt = _lib.SAMPLES_S16 if sample_dtype == torch.int16 else _lib.SAMPLES_F32
+        return RaggedBatch(self.plan(device, apply_log, keep_last, fmt), sample_offsets)
+
+    def run(self, batch: RaggedBatch, samples: torch.Tensor, spec_out: torch.Tensor | None = None,
+            energy_out: torch.Tensor | None = None, want_energy=True):
+        """One asynchronous launch on the current stream.  ``samples`` is the packed device
+        buffer the batch's offsets index (float32, or int16 if the batch was made for it)."""
+        plan = batch.plan
+        want = torch.int16 if plan.sample_format == _lib.SAMPLES_S16 else torch.float32
+        if not samples.is_cuda or samples.device != plan.device:
+            raise ValueError(f"samples must live on {plan.device}")
+        if samples.dtype != want or not samples.is_contiguous():
+            raise ValueError(f"samples must be a contiguous {want} tensor")
+        if samples.numel() < int(batch.sample_offsets[-1]):
+            raise ValueError("samples buffer is shorter than the last sample offset")
+        if spec_out is None:
+            spec_out = torch.empty((batch.total_frames, plan.row_floats), dtype=torch.float32, device=plan.device)
+        elif (spec_out.dtype != torch.float32 or not spec_out.is_contiguous()
+              or spec_out.numel() < batch.total_frames * plan.row_floats or spec_out.device != plan.device):
+            raise ValueError("spec_out must be a contiguous float32 device tensor of total_frames * row_floats")
+        if self.is_complex:
+            want_energy = False
+        if want_energy and energy_out is None:
+            energy_out = torch.empty((batch.total_frames,), dtype=torch.float32, device=plan.device)
+        with torch.cuda.device(plan.device):
+            _lib.check(plan._lib.evf_features_run(plan.handle, batch.handle, _ptr(samples), _ptr(spec_out),
+                                                  _ptr(energy_out if want_energy else None),
+                                                  _stream_ptr(plan.device)))
+        return spec_out, (energy_out if want_energy else None)
+
+    def features_ragged(self, samples: torch.Tensor, sample_offsets, apply_log=True, keep_last=False,
+                        want_energy=True) -> RaggedFeatures:
+        """Log-spectrogram (+ energy) of a packed ragged batch: for every utterance what
+        ``process_spec`` (preprocessor.py:917-928) + ``extract_energy`` (:302-309) produce."""
+        device = self._resolve_device(samples)
+        if not samples.is_cuda:
+            samples = samples.to(device, non_blocking=True)
+        if samples.dtype not in (torch.float32, torch.int16):
+            samples = samples.float()
+        batch = self.make_batch(sample_offsets, device, apply_log, keep_last, samples.dtype)
+        spec, energy = self.run(batch, samples.contiguous(), want_energy=want_energy)
+        return RaggedFeatures(spec, energy, batch.frame_offsets, self.n_rows, self.is_complex)
+
+    # -- dense [..., L] entry points ------------------------------------------------------------
+    def features(self, x: torch.Tensor, normalize=True, keep_last=True) -> torch.Tensor:
+        """``x[..., L] -> [..., F, T]`` with ``T = L//hop (+1)``; ``normalize`` applies the
+        fused ``log(clamp(., 1e-5))``.  Result lives on ``x``'s device."""
+        if x.dim() < 1:
+            raise ValueError("expected a tensor with a trailing time dimension")
+        src_device = x.device
+        device = self._resolve_device(x)
+        xd = x.to(device=device, dtype=torch.float32).contiguous()
+        L = x.shape[-1]
+        lead = tuple(x.shape[:-1])
+        B = int(np.prod(lead)) if lead else 1
+        offsets = np.arange(B + 1, dtype=np.int64) * L
+        batch = self.make_batch(offsets, device, apply_log=normalize and not self.is_complex, keep_last=keep_last)
+        spec, _ = self.run(batch, xd.view(-1), want_energy=False)
+        T = self.num_frames(L, keep_last)
+        if self.is_complex:
+            out = torch.view_as_complex(spec.view(*lead, T, self.n_freqs, 2))
+        else:
+            out = spec.view(*lead, T, self.n_rows)
+        out = out.transpose(-1, -2)
+        return out if src_device == device else out.to(src_device)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """The bare transform of the reference: linear-domain, ``1 + L//hop`` frames
+        (``T.MelSpectrogram`` / ``T.Spectrogram`` / the mel-librosa closure)."""
+        return self.features(x, normalize=False, keep_last=True)
+
+
+def get_spectral_transform(
+    spec_type,
+    n_fft,
+    win_length,
+    hop_length,
+    sample_rate=None,
+    n_mels=None,
+    f_min=0,
+    f_max=8000,
+):
+    """Reference: ``everyvoice/utils/heavy.py:47-119``.  ``"istft"`` (synthesis-side inverse
+    transform) is outside this path and, like any unknown type, yields ``None``."""
+    st = getattr(spec_type, "value", spec_type)
+    if st in (AudioSpecTypeEnum.mel.value, AudioSpecTypeEnum.mel_librosa.value,
+              AudioSpecTypeEnum.linear.value, AudioSpecTypeEnum.raw.value):
+        return SpectralTransform(st, n_fft, win_length, hop_length, sample_rate, n_mels, f_min, f_max)
+    return None
+
+
+def dynamic_range_compression_torch(x: torch.Tensor, C=1, clip_val=1e-5) -> torch.Tensor:
+    """Reference: ``everyvoice/utils/heavy.py:39-40`` -- ``log(clamp(x, min=clip_val) * C)``
+    as a stand-alone operator (the fused kernels do this in their epilogue)."""
+    device = x.device if x.is_cuda else _require_cuda(None)
+    xd = x.to(device=device, dtype=torch.float32).contiguous()
+    out = torch.empty_like(xd)
+    lib = _lib.load()
+    with torch.cuda.device(device):
+        _lib.check(lib.evf_log_compress(_ptr(xd), _ptr(out), xd.numel(), float(C), float(clip_val), _stream_ptr(device)))
+    return out if x.is_cuda else out.to(x.device)

@@ -1,0 +1,226 @@
+"""Drop-in for the numeric methods of ``everyvoice/preprocessor/preprocessor.py`` on a B200.
+
+Mirrors, with the reference's names and argument meaning:
+
+* ``Preprocessor.__init__``'s transform construction            (preprocessor.py:94-129)
+* ``Preprocessor.extract_spectral_features(audio, transform, normalize=True)``  (:220-233)
+* ``Preprocessor.extract_energy(spec[F, T]) -> [T]``                            (:302-309)
+* ``Preprocessor.average_data_by_durations(data[T], durations[P]) -> [P]``      (:287-300)
+* the in-memory cores of ``process_spec`` (:917-928) and ``process_energy`` (:641-650) as
+  batched, ragged calls (one kernel launch for a whole list of utterances), and
+  ``compute_stats`` / ``normalize_stats`` (:378-490) over in-memory shards.
+
+File I/O, text processing, audio ingest, config locks and the CLI are out of scope (they
+stay with the reference; see INTEGRATION.md for where these calls slot in).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import AudioConfig, ConfigError
+from .heavy import (RaggedFeatures, SpectralTransform, _ptr, _require_cuda, _stream_ptr,
+                    get_spectral_transform)
+from .helpers import Scaler
+
+
+def _as_i64_dev(x, device) -> torch.Tensor:
+    if torch.is_tensor(x):
+        return x.to(device=device, dtype=torch.int64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.int64))).to(device)
+
+
+class Preprocessor:
+    def __init__(self, config=None, device=None):
+        """``config``: an ``AudioConfig`` (ours or the reference's) or any object exposing
+        ``.preprocessing.audio`` like the reference's FeaturePrediction/Vocoder configs."""
+        if config is None:
+            config = AudioConfig()
+        self.config = config
+        self.audio_config = getattr(getattr(config, "preprocessing", None), "audio", config)
+        self.device = device
+        self.pitch_scaler = Scaler(device)
+        self.energy_scaler = Scaler(device)
+        self.sep = "--"
+        ac = self.audio_config
+        self.input_sampling_rate = ac.input_sampling_rate
+        self.output_sampling_rate = ac.output_sampling_rate
+        self.sampling_rate_change = self.output_sampling_rate // self.input_sampling_rate
+        self.output_hop_size = ac.fft_hop_size * self.sampling_rate_change
+        spec_type = getattr(ac.spec_type, "value", ac.spec_type)
+        # preprocessor.py:102-121 (note: the output transform's mel basis also uses the
+        # *input* sampling rate, exactly as the reference does)
+        self.input_spectral_transform = get_spectral_transform(
+            spec_type, ac.n_fft, ac.fft_window_size, ac.fft_hop_size,
+            sample_rate=self.input_sampling_rate, n_mels=ac.n_mels, f_min=ac.f_min, f_max=ac.f_max,
+        )
+        self.output_spectral_transform = get_spectral_transform(
+            spec_type, ac.n_fft * self.sampling_rate_change, ac.fft_window_size * self.sampling_rate_change,
+            self.output_hop_size,
+            sample_rate=self.input_sampling_rate, n_mels=ac.n_mels, f_min=ac.f_min, f_max=ac.f_max,
+        )
+        if self.input_spectral_transform is None or self.output_spectral_transform is None:
+            raise ConfigError(
+                f"Spectral feature specification '{spec_type}' is not supported. Please edit your config file."
+            )
+        if device is not None:
+            self.input_spectral_transform.to(device)
+            self.output_spectral_transform.to(device)
+
+    # ------------------------------------------------------------------------------------------
+    # The reference's per-utterance operators
+    # ------------------------------------------------------------------------------------------
+    def extract_spectral_features(self, audio_tensor: torch.Tensor, transform, normalize=True):
+        """Reference: preprocessor.py:220-233.  ``transform`` must be one returned by
+        ``everyvoice_b200.get_spectral_transform`` (window, FFT, mel and the log run as one
+        fused kernel); there is no fallback for foreign callables."""
+        if not isinstance(transform, SpectralTransform):
+            raise TypeError(
+                "transform must come from everyvoice_b200.get_spectral_transform; "
+                "everyvoice_b200 has no CPU / torchaudio fallback"
+            )
+        return transform.features(audio_tensor, normalize=normalize, keep_last=True)
+
+    def extract_energy(self, spectral_feature_tensor: torch.Tensor):
+        """Reference: preprocessor.py:302-309 -- ``torch.linalg.norm(spec, dim=0)`` of a
+        ``[F, T]`` (log-)spectrogram."""
+        spec = spectral_feature_tensor
+        if spec.dim() != 2:
+            raise ValueError("extract_energy expects a [F, T] spectrogram")
+        device = spec.device if spec.is_cuda else _require_cuda(self.device)
+        tm = spec.to(device=device, dtype=torch.float32).transpose(0, 1).contiguous()  # [T, F]; free for our views
+        T, F = tm.shape
+        out = torch.empty(T, dtype=torch.float32, device=device)
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            _lib.check(lib.evf_energy_from_spec(_ptr(tm), T, F, _ptr(out), _stream_ptr(device)))
+        return out if spec.is_cuda else out.to(spec.device)
+
+    def average_data_by_durations(self, data: torch.Tensor, durations: torch.Tensor):
+        """Reference: preprocessor.py:287-300 (one utterance)."""
+        device = data.device if data.is_cuda else _require_cuda(self.device)
+        vals = data.to(device=device, dtype=torch.float32).contiguous().view(-1)
+        durs = _as_i64_dev(durations, device).view(-1)
+        out = self.average_data_by_durations_ragged(
+            vals, np.array([0, vals.numel()], dtype=np.int64), durs, np.array([0, durs.numel()], dtype=np.int64)
+        )
+        return out if data.is_cuda else out.to(data.device)
+
+    # ------------------------------------------------------------------------------------------
+    # Batched / ragged drivers (one launch per batch instead of one Python call per file)
+    # ------------------------------------------------------------------------------------------
+    def average_data_by_durations_ragged(self, values: torch.Tensor, value_offsets, durations, phone_offsets):
+        """``average_data_by_durations`` for a packed batch: utterance ``b`` owns
+        ``values[value_offsets[b]:value_offsets[b+1]]`` and
+        ``durations[phone_offsets[b]:phone_offsets[b+1]]``.  Returns packed ``[sum P_b]`` float32."""
+        device = values.device if values.is_cuda else _require_cuda(self.device)
+        vals = values.to(device=device, dtype=torch.float32).contiguous()
+        v_off = _as_i64_dev(value_offsets, device)
+        durs = _as_i64_dev(durations, device)
+        p_off = _as_i64_dev(phone_offsets, device)
+        n_utts = v_off.numel() - 1
+        if p_off.numel() != n_utts + 1:
+            raise ValueError("value_offsets and phone_offsets must describe the same number of utterances")
+        out = torch.empty(durs.numel(), dtype=torch.float32, device=device)
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            _lib.check(lib.evf_segment_mean(_ptr(vals), _ptr(v_off), _ptr(durs), _ptr(p_off), n_utts, _ptr(out),
+                                            _stream_ptr(device)))
+        return out
+
+    def process_spec_batch(self, audios, sample_offsets=None, output=False, want_energy=True) -> RaggedFeatures:
+        """The in-memory core of ``process_spec`` (preprocessor.py:917-928) for many items at
+        once: ``extract_spectral_features(audio, transform)[:, :L // hop]`` for each utterance
+        (+ ``extract_energy`` of it, fused).  ``audios`` is a list of 1-D tensors, or a packed
+        1-D tensor (float32 / int16 PCM) together with ``sample_offsets``."""
+        transform = self.output_spectral_transform if output else self.input_spectral_transform
+        device = _require_cuda(self.device)
+        if sample_offsets is None:
+            lens = np.array([a.numel() for a in audios], dtype=np.int64)
+            sample_offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+            dt = torch.int16 if all(a.dtype == torch.int16 for a in audios) else torch.float32
+            packed = torch.cat([a.reshape(-1).to(dt) for a in audios]) if len(audios) else torch.zeros(0, dtype=dt)
+        else:
+            packed = audios
+        if not packed.is_cuda:
+            packed = packed.pin_memory().to(device, non_blocking=True) if packed.numel() else packed.to(device)
+        return transform.features_ragged(packed, sample_offsets, apply_log=True, keep_last=False,
+                                         want_energy=want_energy)
+
+    def process_energy_batch(self, feats: RaggedFeatures, durations=None, phone_offsets=None):
+        """The in-memory core of ``process_energy`` (preprocessor.py:641-650): frame energy, and
+        phone-level averages when ``durations`` (packed int64 + ``phone_offsets``, or a list of
+        per-utterance tensors) is given.  Returns ``(values_packed, offsets)``."""
+        energy = feats.energy
+        if durations is None:
+            return energy, feats.frame_offsets
+        if phone_offsets is None:
+            lens = np.array([int(d.numel()) for d in durations], dtype=np.int64)
+            phone_offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+            durations = torch.cat([d.reshape(-1).to(torch.int64) for d in durations])
+        out = self.average_data_by_durations_ragged(energy, feats.frame_offsets, durations, phone_offsets)
+        return out, np.asarray(phone_offsets, dtype=np.int64)
+
+    # ------------------------------------------------------------------------------------------
+    # Corpus statistics (preprocessor.py:378-490 driven by fs2/cli/preprocess.py:44-77)
+    # ------------------------------------------------------------------------------------------
+    def compute_stats(self, energy=None, pitch=None, n_energy_files=None, n_pitch_files=None):
+        """``energy`` / ``pitch``: a list of per-utterance tensors, or one packed device tensor
+        holding this rank's shard (then ``n_*_files`` gives the number of utterances, the
+        reference's ``sample_size``).  Returns ``(energy_scaler, pitch_scaler)``."""
+        scalers = []
+        for data, n_files in ((energy, n_energy_files), (pitch, n_pitch_files)):
+            if data is None:
+                scalers.append(None)
+                continue
+            s = Scaler(self.device)
+            if torch.is_tensor(data):
+                s.append(data)
+                s._n_files = int(n_files) if n_files is not None else 1
+            else:
+                for t in data:
+                    s.append(t)
+            scalers.append(s)
+        self.energy_scaler, self.pitch_scaler = scalers[0] or self.energy_scaler, scalers[1] or self.pitch_scaler
+        return scalers[0], scalers[1]
+
+    def normalize_stats(self, energy_scaler: Scaler | None, pitch_scaler: Scaler | None, group=None,
+                        distributed=None) -> dict:
+        """Reference: preprocessor.py:453-490 -- statistics, then ``(x - mean) / std`` over every
+        stored value (here: in place over the scaler's device tensors, one launch each)."""
+        stats = {}
+        for name, scaler in (("energy", energy_scaler), ("pitch", pitch_scaler)):
+            if not scaler:
+                continue
+            n_files = getattr(scaler, "_n_files", None)
+            if n_files is not None:
+                st = _packed_stats(scaler, n_files, group, distributed)
+            else:
+                st = scaler.calculate_stats(group=group, distributed=distributed)
+            for i, t in enumerate(scaler.data):
+                if t.is_cuda and t.dtype == torch.float32 and t.is_contiguous():
+                    scaler.normalize_(t)
+                else:
+                    scaler.data[i] = scaler.normalize(t)
+            stats[name] = st
+        return stats
+
+
+def _packed_stats(scaler: Scaler, n_files: int, group, distributed):
+    """calculate_stats for a scaler that holds one packed shard: ``sample_size`` must count
+    utterances (files), not tensors."""
+    import torch.distributed as dist
+
+    from .distributed import allreduce_stats, finalize_stats
+
+    if distributed is None:
+        distributed = dist.is_available() and dist.is_initialized()
+    stats5, sample_size = scaler.partial_stats(), n_files
+    if distributed:
+        stats5, sample_size = allreduce_stats(stats5, sample_size, group)
+    st = finalize_stats(stats5.cpu().tolist(), sample_size)
+    for k in ("min", "max", "mean", "std", "norm_min", "norm_max"):
+        setattr(scaler, k, torch.tensor(st[k], dtype=torch.float32, device=stats5.device))
+    return st

@@ -1,0 +1,169 @@
+/*
+ * evfeat.h -- C ABI of libevfeat.so: the B200 (sm_100a) implementation of EveryVoice's
+ * preprocessing feature-extraction hot path.
+ *
+ * The reference has no FFI for this path: it is a Python operator surface over
+ * torchaudio.  Each entry point below names the reference
+ * operator it replaces (paths relative to the EveryVoice repository root); the Python
+ * shim `everyvoice_b200` keeps the reference's names on top of these calls through
+ * ctypes (INTEGRATION.md shows the binding a maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; every `*_dev` pointer is a CUDA device pointer owned by the
+ *     caller (e.g. torch.Tensor.data_ptr()); every `*_host` pointer is host memory that
+ *     is only read during the call;
+ *   - every function returns an evf_status (0 == EVF_OK); evf_last_error() returns a
+ *     thread-local, human readable description of the last failure;
+ *   - no exception crosses the ABI; nothing is computed on the CPU; there is no fallback;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  All
+ *     compute entry points are asynchronous with respect to the host;
+ *   - a plan / batch is immutable after creation and may be used from several host
+ *     threads on distinct streams.
+ */
+#ifndef EVFEAT_H_
+#define EVFEAT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define EVF_API __attribute__((visibility("default")))
+#else
+#define EVF_API
+#endif
+
+typedef enum evf_status {
+  EVF_OK = 0,
+  EVF_ERR_INVALID_ARGUMENT = 1,
+  EVF_ERR_UNSUPPORTED = 2,   /* e.g. n_fft not in {1024, 2048}, spec_type unknown */
+  EVF_ERR_SHORT_INPUT = 3,   /* an utterance has L <= n_fft/2: reflect padding undefined
+                                (torch.stft raises RuntimeError for the same input)       */
+  EVF_ERR_FILTERBANK = 4,    /* mel filterbank is not a bank of adjacent triangular filters */
+  EVF_ERR_CUDA = 5,          /* a CUDA runtime call failed; see evf_last_error()          */
+  EVF_ERR_NO_DEVICE = 6,     /* no sm_100 device: this library has no other code path     */
+  EVF_ERR_OUT_OF_MEMORY = 7
+} evf_status;
+
+/* everyvoice/config/preprocessing_config.py:18-22  AudioSpecTypeEnum */
+typedef enum evf_spec_type {
+  EVF_SPEC_MEL = 0,          /* "mel"          utils/heavy.py:57-68   (htk scale, slaney norm, power) */
+  EVF_SPEC_MEL_LIBROSA = 1,  /* "mel-librosa"  utils/heavy.py:69-100  (basis @ sqrt(power + 1e-9))   */
+  EVF_SPEC_LINEAR = 2,       /* "linear"       utils/heavy.py:101-106 (power spectrogram)             */
+  EVF_SPEC_RAW = 3           /* "raw"          utils/heavy.py:107-113 (complex STFT, no log/energy)   */
+} evf_spec_type;
+
+typedef enum evf_sample_format {
+  EVF_SAMPLES_F32 = 0,       /* float32 in [-1, 1] (what torchaudio.load returns)                   */
+  EVF_SAMPLES_S16 = 1        /* PCM16 as stored by process_audio; converted as s / 32768.0f on load */
+} evf_sample_format;
+
+/* The parameter contract of everyvoice/config/preprocessing_config.py:25-91 (AudioConfig)
+ * as consumed by get_spectral_transform (utils/heavy.py:47-56). */
+typedef struct evf_config {
+  int32_t spec_type;      /* evf_spec_type                                                     */
+  int32_t sample_rate;    /* informational (the mel basis is passed in explicitly)             */
+  int32_t n_fft;          /* 1024 or 2048 (n_fft 2048 needs an even hop)                                      */
+  int32_t win_length;     /* <= n_fft; informational (window is passed in explicitly)          */
+  int32_t hop_length;     /* fft_hop_size                                                      */
+  int32_t n_mels;         /* rows of the mel basis; ignored for linear / raw                   */
+  int32_t apply_log;      /* 1: log(max(x, log_clip))  == dynamic_range_compression_torch,
+                                utils/heavy.py:39-40 (Preprocessor.extract_spectral_features,
+                                preprocessor/preprocessor.py:230-233, normalize=True)          */
+  int32_t keep_last_frame;/* 0: T = L // hop frames (process_spec drops the last frame,
+                                preprocessor/preprocessor.py:921-927);
+                             1: T = L // hop + 1 (what the bare transform returns)             */
+  int32_t sample_format;  /* evf_sample_format                                                 */
+  float   log_clip;       /* 1e-5f                                                             */
+} evf_config;
+
+typedef struct evf_plan evf_plan;
+typedef struct evf_batch evf_batch;
+
+EVF_API int         evf_abi_version(void);
+EVF_API const char* evf_last_error(void);
+
+/* Replaces the construction done by get_spectral_transform (utils/heavy.py:47-119).
+ *   window_host : n_fft floats -- torch.hann_window(win_length) centre-padded to n_fft,
+ *                 exactly the window torch.stft applies;
+ *   mel_fb_host : [n_fft/2+1][n_mels] floats, row-major (frequency-major), the matrix
+ *                 torchaudio.functional.melscale_fbanks returns / librosa.filters.mel
+ *                 transposed; NULL for linear / raw.
+ * Uploads window, FFT twiddles (computed in fp64) and the compressed mel table. */
+EVF_API int evf_plan_create(const evf_config* cfg, const float* window_host, const float* mel_fb_host,
+                    int device, evf_plan** plan_out);
+EVF_API int evf_plan_destroy(evf_plan* plan);
+/* floats written per frame: n_mels (mel types), n_fft/2+1 (linear), 2*(n_fft/2+1) (raw) */
+EVF_API int evf_plan_row_floats(const evf_plan* plan, int32_t* row_floats_out);
+/* frames produced for an utterance of n_samples (bit-exact with L // hop [+ 1]) */
+EVF_API int64_t evf_plan_num_frames(const evf_plan* plan, int64_t n_samples);
+
+/* A ragged batch descriptor: utterance b occupies samples [sample_offsets[b],
+ * sample_offsets[b+1]) of the packed sample buffer.  Computes per-utterance frame
+ * counts / offsets and the frame-tile work list and uploads them. */
+EVF_API int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, int32_t n_utts,
+                     evf_batch** batch_out);
+EVF_API int evf_batch_destroy(evf_batch* batch);
+EVF_API int evf_batch_total_frames(const evf_batch* batch, int64_t* total_frames_out);
+/* copies frame_offsets[n_utts + 1] to host memory */
+EVF_API int evf_batch_frame_offsets(const evf_batch* batch, int64_t* frame_offsets_host_out);
+/* device copy of the same array (int64[n_utts + 1]); owned by the batch */
+EVF_API int evf_batch_frame_offsets_dev(const evf_batch* batch, const int64_t** frame_offsets_dev_out);
+
+/* Replaces, for every utterance of the batch at once,
+ *   Preprocessor.extract_spectral_features(audio, transform)[:, :L // hop]
+ *     (preprocessor/preprocessor.py:220-233, 921-927; utils/heavy.py:39-113) and
+ *   Preprocessor.extract_energy(spec)  (preprocessor/preprocessor.py:302-309).
+ *   samples_dev : packed float32 or int16 samples (cfg.sample_format)
+ *   spec_out_dev: packed, time-major [total_frames][row_floats] float32
+ *   energy_out_dev: [total_frames] float32, or NULL (must be NULL-able; ignored for raw) */
+EVF_API int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* samples_dev,
+                     float* spec_out_dev, float* energy_out_dev, void* stream);
+
+/* Convenience wrapper: batch_create + features_run + batch_destroy.
+ * frame_offsets_host_out may be NULL. */
+EVF_API int evf_features_ragged(const evf_plan* plan, const void* samples_dev,
+                        const int64_t* sample_offsets_host, int32_t n_utts, float* spec_out_dev,
+                        float* energy_out_dev, int64_t* frame_offsets_host_out, void* stream);
+
+/* Replaces Preprocessor.extract_energy (preprocessor/preprocessor.py:302-309) on an
+ * already computed time-major spectrogram [n_frames][row_floats]. */
+EVF_API int evf_energy_from_spec(const float* spec_dev, int64_t n_frames, int32_t row_floats,
+                         float* energy_out_dev, void* stream);
+
+/* Replaces dynamic_range_compression_torch (utils/heavy.py:39-40) as a stand-alone
+ * operator: out = log(max(in, clip_val) * c).  in_dev may equal out_dev. */
+EVF_API int evf_log_compress(const float* in_dev, float* out_dev, int64_t n, float c, float clip_val,
+                     void* stream);
+
+/* Replaces Preprocessor.average_data_by_durations (preprocessor/preprocessor.py:287-300)
+ * for a ragged batch: utterance b has values [value_offsets[b], value_offsets[b+1]) and
+ * durations [phone_offsets[b], phone_offsets[b+1]); out has one float per duration.
+ * Python slice semantics are reproduced exactly (clipping, d <= 0 -> 1e-7f, empty -> NaN). */
+EVF_API int evf_segment_mean(const float* values_dev, const int64_t* value_offsets_dev,
+                     const int64_t* durations_dev, const int64_t* phone_offsets_dev,
+                     int32_t n_utts, float* out_dev, void* stream);
+
+/* Replaces the reductions of Scaler.calculate_stats (preprocessor/helpers.py:86-106):
+ * out5_dev = {count, sum, sum of squares, min, max} over the non-NaN values, float64.
+ * With accumulate != 0 the result is merged into what out5_dev already holds (so several
+ * buffers, and -- after an all-reduce -- several GPUs, can be combined). */
+EVF_API int evf_stats_partial(const float* values_dev, int64_t n, double* out5_dev, int32_t accumulate,
+                      void* stream);
+
+/* Replaces Scaler.normalize (preprocessor/helpers.py:78-80) over a whole shard, in place. */
+EVF_API int evf_normalize_inplace(float* values_dev, int64_t n, float mean, float std, void* stream);
+
+/* Same, with mean = sum/n and std = sqrt((sumsq - sum^2/n)/(n-1)) derived on the device from
+ * the (possibly all-reduced) five numbers of evf_stats_partial: no host round trip between
+ * the reduction and the normalisation. */
+EVF_API int evf_normalize_by_stats(float* values_dev, int64_t n, const double* stats5_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVFEAT_H_ */
