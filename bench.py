@@ -69,53 +69,76 @@ def make_durations(lengths, hop, seed):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region from a background thread
+    (NVML through pynvml, ~every 5 ms; the timed region can be a few tens of ms long, far
+    shorter than nvidia-smi's start-up)."""
 
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
-        self.proc = None
-        self.path = None
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = None
+        self._thread = None
+        self.source = None
+
+    def _resolve_nvml_index(self, pynvml):
+        # CUDA_VISIBLE_DEVICES may remap ordinals; match by PCI bus id through torch
+        try:
+            import torch
+
+            bus = torch.cuda.get_device_properties(self.gpu_index).pci_bus_id
+            dom = torch.cuda.get_device_properties(self.gpu_index).pci_domain_id
+            dev = torch.cuda.get_device_properties(self.gpu_index).pci_device_id
+            return pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0".encode())
+        except Exception:
+            return pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
 
     def start(self):
+        import threading
+
         try:
-            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
-            self.path = f.name
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = self._resolve_nvml_index(pynvml)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = {
+                "hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            }
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
         except Exception:
-            self.proc = None
+            return
+        self.source = "nvml"
+        self._stop = threading.Event()
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    mask = int(get_reasons(h))
+                    for n, bit in names.items():
+                        if mask & bit:
+                            self.reasons.add(n)
+                except Exception:
+                    pass
+                self._stop.wait(0.005)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
 
     def stop(self) -> dict:
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, reasons, mx = [], set(), None
-        try:
-            for line in open(self.path):
-                parts = [p.strip() for p in line.split(",")]
-                if len(parts) < 9:
-                    continue
-                try:
-                    sm.append(float(parts[1]))
-                    mx = float(parts[2])
-                except ValueError:
-                    continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+               "samples": len(self.samples), "source": self.source}
+        if self.samples:
+            out["sm_mhz"] = float(np.median(self.samples))
         return out
 
 
