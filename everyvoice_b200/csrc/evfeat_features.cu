@@ -93,6 +93,61 @@ __device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32],
   }
 }
 
+// ---- mbarrier / bulk-copy (TMA 1-D) primitives ----------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (SASS: UBLKCP); completion is signalled on the mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct TileInfo {
+  long long s_off;       // first sample of the utterance in the packed buffer
+  long long out_frame0;  // first output frame of the tile in the packed output
+  int L;                 // samples in the utterance
+  int start;             // utterance-relative sample index of tile word 0 (may be negative)
+  int span;              // words of the tile that are consumed
+  int nvalid;            // frames of the tile that exist
+};
+
+// The manual (non-bulk) part of a tile: tile words [0, a_lo) and [a_hi, span).
+struct ManualRange {
+  int a_lo, a_hi, total;
+};
+
+__device__ __forceinline__ int reflect_index(int j, int L) {
+  j = (j < 0) ? -j : j;
+  j = (j >= L) ? 2 * (L - 1) - j : j;
+  return (j < 0) ? 0 : j;  // only reachable for frames beyond the last valid one
+}
+
 template <int MODE, int SPEC, typename SampleT>
 __global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams p) {
   using MT = ModeTraits<MODE>;
@@ -102,9 +157,9 @@ __global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams 
   constexpr int FS = FR + 1;              // padded frame stride of the P tile
   constexpr int PARTS = 32 / FR;          // projection workers per warp
   constexpr bool kMel = (SPEC == EVF_SPEC_MEL || SPEC == EVF_SPEC_MEL_LIBROSA);
+  constexpr bool kBulk = sizeof(SampleT) == 4;  // float samples can be bulk-copied as they are
 
   extern __shared__ __align__(16) float smem[];
-  float* s_in = smem + p.off_in;
   float* s_win = smem + p.off_win;
   float2* s_tw = reinterpret_cast<float2*>(smem + p.off_tw);
   float2* s_wpost = reinterpret_cast<float2*>(smem + p.off_wpost);
@@ -113,13 +168,20 @@ __global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams 
   int* s_vwm = reinterpret_cast<int*>(smem + p.off_vwm);
   float* s_p = smem + p.off_p;
   float* s_out = smem + p.off_sout;
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
   float* scr = smem + p.off_scr + warp * (32 * kScrStride);
+  const int nbuf = p.nbuf;
 
-  // ---- one-time table copy ------------------------------------------------------------
+  // ---- one-time setup: mbarriers + table copy --------------------------------------------
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_mbar_init();
+  }
   for (int i = tid; i < NFFT; i += kThreads) s_win[i] = p.window[i];
   for (int i = tid; i < kFftSize; i += kThreads) s_tw[i] = p.tw[i];
   if constexpr (MODE == MODE_HALF) {
@@ -130,35 +192,95 @@ __global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams 
     for (int i = tid; i < p.n_mels + 2; i += kThreads) s_kstart[i] = p.kstart[i];
     for (int i = tid; i < kWarps * PARTS + 1; i += kThreads) s_vwm[i] = p.vw_m[i];
   }
+  __syncthreads();
 
   const int hop = p.hop;
   const SampleT* __restrict__ samples = static_cast<const SampleT*>(p.samples);
 
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+  auto tile_info = [&](int tile) {
+    TileInfo ti;
     const int2 tl = p.tiles[tile];
-    const int utt = tl.x, f0 = tl.y;
-    const long long s_off = p.sample_off[utt];
-    const long long L = p.sample_off[utt + 1] - s_off;
-    const long long fr_off = p.frame_off[utt];
-    const int T = (int)(p.frame_off[utt + 1] - fr_off);
-    const int nvalid = min(FR, T - f0);
-    const long long out_frame0 = fr_off + f0;
+    ti.s_off = p.sample_off[tl.x];
+    ti.L = (int)(p.sample_off[tl.x + 1] - ti.s_off);
+    const long long fr_off = p.frame_off[tl.x];
+    const int T = (int)(p.frame_off[tl.x + 1] - fr_off);
+    ti.nvalid = min(FR, T - tl.y);
+    ti.out_frame0 = fr_off + tl.y;
+    ti.start = tl.y * hop - NFFT / 2;
+    const int njobs = (ti.nvalid + FPJ - 1) / FPJ;
+    ti.span = (njobs * FPJ - 1) * hop + NFFT;
+    return ti;
+  };
 
-    // ---- phase 0: stage the sample span, reflect padding by index mirroring ------------
-    {
-      const int njobs = (nvalid + FPJ - 1) / FPJ;
-      const int span = (njobs * FPJ - 1) * hop + NFFT;
-      const long long start = (long long)f0 * hop - NFFT / 2;
-      const SampleT* src = samples + s_off;
-      for (int i = tid; i < span; i += kThreads) {
-        long long j = start + i;
-        j = (j < 0) ? -j : j;
-        j = (j >= L) ? 2 * (L - 1) - j : j;
-        j = (j < 0) ? 0 : j;  // only reachable for frames beyond the last valid one
-        s_in[i] = load_sample(src, j);
+  // Issue the staging of a tile into `buf`: one bulk copy for the 16-byte aligned in-range part
+  // (thread 0), the rest (reflected margins, unaligned / int16 input) is left to the caller.
+  auto stage_issue = [&](const TileInfo& ti, float* buf, uint64_t* bar) {
+    ManualRange mr;
+    const int lo = max(0, -ti.start);                 // first tile word inside the utterance
+    const int hi = min(ti.span, ti.L - ti.start);     // one past the last
+    mr.a_lo = lo;
+    mr.a_hi = lo;
+    if constexpr (kBulk) {
+      // tile word i <-> packed sample s_off + start + i ; both sides must be 16-byte aligned
+      if ((((ti.s_off + ti.start + lo) | lo) & 3) == 0 && hi > lo) mr.a_hi = lo + ((hi - lo) & ~3);
+    }
+    mr.total = mr.a_lo + (ti.span - mr.a_hi);
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)(mr.a_hi - mr.a_lo) * 4u;
+      mbar_arrive_expect_tx(bar, bytes);
+      if (bytes) bulk_g2s(buf + mr.a_lo, reinterpret_cast<const float*>(samples) + ti.s_off + ti.start + mr.a_lo, bytes, bar);
+    }
+    return mr;
+  };
+  auto manual_word = [&](const ManualRange& mr, int e) { return (e < mr.a_lo) ? e : mr.a_hi + (e - mr.a_lo); };
+  auto manual_load = [&](const TileInfo& ti, int word) {
+    return load_sample(samples + ti.s_off, (long long)reflect_index(ti.start + word, ti.L));
+  };
+  auto manual_fill_now = [&](const TileInfo& ti, const ManualRange& mr, float* buf) {
+    for (int e = tid; e < mr.total; e += kThreads) {
+      const int w = manual_word(mr, e);
+      buf[w] = manual_load(ti, w);
+    }
+  };
+
+  int tile = blockIdx.x;
+  if (tile >= p.n_tiles) return;
+  TileInfo cur = tile_info(tile);
+  {
+    const ManualRange mr = stage_issue(cur, smem + p.off_in, &s_bar[0]);
+    manual_fill_now(cur, mr, smem + p.off_in);
+  }
+  __syncthreads();
+
+  for (int it = 0; tile < p.n_tiles; ++it, tile += gridDim.x) {
+    const int b = (nbuf == 2) ? (it & 1) : 0;
+    float* s_in = smem + (b ? p.off_in2 : p.off_in);
+    const uint32_t parity = (nbuf == 2) ? ((it >> 1) & 1) : (it & 1);
+    const int next_tile = tile + gridDim.x;
+    const bool has_next = next_tile < p.n_tiles;
+    TileInfo nxt = cur;
+    ManualRange nmr{0, 0, 0};
+    float* s_next = smem + ((nbuf == 2 && !b) ? p.off_in2 : p.off_in);
+    uint64_t* bar_next = &s_bar[(nbuf == 2) ? (b ^ 1) : 0];
+    float mv0 = 0.f, mv1 = 0.f;
+    bool deferred = false;
+    if (has_next) nxt = tile_info(next_tile);
+    if (has_next && nbuf == 2) {
+      // prefetch the next tile into the other buffer; its few manual words ride in registers
+      // across phase A (loads issued now, stores after the FFT)
+      nmr = stage_issue(nxt, s_next, bar_next);
+      if (nmr.total <= 2 * kThreads) {
+        deferred = true;
+        if (tid < nmr.total) mv0 = manual_load(nxt, manual_word(nmr, tid));
+        if (tid + kThreads < nmr.total) mv1 = manual_load(nxt, manual_word(nmr, tid + kThreads));
+      } else {
+        manual_fill_now(nxt, nmr, s_next);
       }
     }
-    __syncthreads();
+    const int nvalid = cur.nvalid;
+    const long long out_frame0 = cur.out_frame0;
+
+    mbar_wait(&s_bar[b], parity);
 
     // ---- phase A: one FFT job per warp ------------------------------------------------
     if (warp * FPJ < nvalid) {
@@ -198,92 +320,89 @@ __global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams 
 #pragma unroll
       for (int j = 0; j <= 16; ++j) {
         const int k = lane + 32 * j;
-        {  // warp-uniform: does any lane of this row own a bin that is consumed?
-          bool need = 32 * j < kcap;
-          if constexpr (MODE == MODE_HALF) need = need || (1024 - 32 * j - 31 < kcap);
-          if (!need) continue;
-        }
-        float zr, zi, pr, pi;
-        if (j < 16) {
-          zr = re[bitrev5(j)];
-          zi = im[bitrev5(j)];
-          pr = __shfl_sync(0xffffffffu, re[bitrev5(31 - j)], src_lane);
-          pi = __shfl_sync(0xffffffffu, im[bitrev5(31 - j)], src_lane);
-          if (lane == 0) {
-            pr = re[bitrev5((32 - j) & 31)];
-            pi = im[bitrev5((32 - j) & 31)];
+        // warp-uniform: does any lane of this row own a bin that is consumed?
+        bool need = 32 * j < kcap;
+        if constexpr (MODE == MODE_HALF) need = need || (1024 - 32 * j - 31 < kcap);
+        if (need) {
+          float zr, zi, pr, pi;
+          if (j < 16) {
+            zr = re[bitrev5(j)];
+            zi = im[bitrev5(j)];
+            // lane 0 is its own partner, with a different register (bin 32*(32-j) instead of 32*(31-j)+32-lane)
+            const float sr = (lane == 0) ? re[bitrev5((32 - j) & 31)] : re[bitrev5(31 - j)];
+            const float si = (lane == 0) ? im[bitrev5((32 - j) & 31)] : im[bitrev5(31 - j)];
+            pr = __shfl_sync(0xffffffffu, sr, src_lane);
+            pi = __shfl_sync(0xffffffffu, si, src_lane);
+          } else {  // bin 512 (lane 0 only): its own mirror
+            zr = pr = re[bitrev5(16)];
+            zi = pi = im[bitrev5(16)];
           }
-        } else {  // bin 512 (lane 0 only): its own mirror
-          zr = pr = re[bitrev5(16)];
-          zi = pi = im[bitrev5(16)];
-          if (lane != 0) continue;
-        }
-        if constexpr (MODE == MODE_PACK2) {
-          // window was pre-scaled by 1/2: X_a = Z[k] + conj(Z[N-k]), X_b = (Z[k] - conj(Z[N-k])) / i
-          const float ar = zr + pr, ai = zi - pi;
-          const float br = zi + pi, bi = pr - zr;
-          if constexpr (SPEC == EVF_SPEC_RAW) {
-            if (k <= 512) {
-              reinterpret_cast<float2*>(ga)[k] = make_float2(ar, ai);
-              if (b_valid) reinterpret_cast<float2*>(gb)[k] = make_float2(br, bi);
-            }
-          } else {
-            float pa = fmaf(ar, ar, ai * ai);
-            float pb = fmaf(br, br, bi * bi);
-            if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
-              pa = sqrtf(pa + 1e-9f);
-              pb = sqrtf(pb + 1e-9f);
-            }
-            if constexpr (kMel) {
-              if (k < kcap) {
-                s_p[k * FS + fa] = pa;
-                s_p[k * FS + fa + 1] = pb;
-              }
-            } else {
-              if (k <= 512) {
-                const float va = compress(pa, p.apply_log, p.log_clip);
-                const float vb = compress(pb, p.apply_log, p.log_clip);
-                ga[k] = va;
-                esum_a = fmaf(va, va, esum_a);
-                if (b_valid) {
-                  gb[k] = vb;
-                  esum_b = fmaf(vb, vb, esum_b);
+          if (j < 16 || lane == 0) {
+            if constexpr (MODE == MODE_PACK2) {
+              // window was pre-scaled by 1/2: X_a = Z[k] + conj(Z[N-k]), X_b = (Z[k] - conj(Z[N-k])) / i
+              const float ar = zr + pr, ai = zi - pi;
+              const float br = zi + pi, bi = pr - zr;
+              if constexpr (SPEC == EVF_SPEC_RAW) {
+                reinterpret_cast<float2*>(ga)[k] = make_float2(ar, ai);
+                if (b_valid) reinterpret_cast<float2*>(gb)[k] = make_float2(br, bi);
+              } else {
+                float pa = fmaf(ar, ar, ai * ai);
+                float pb = fmaf(br, br, bi * bi);
+                if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
+                  pa = sqrtf(pa + 1e-9f);
+                  pb = sqrtf(pb + 1e-9f);
+                }
+                if constexpr (kMel) {
+                  if (k < kcap) {
+                    s_p[k * FS + fa] = pa;
+                    s_p[k * FS + fa + 1] = pb;
+                  }
+                } else {
+                  const float va = compress(pa, p.apply_log, p.log_clip);
+                  const float vb = compress(pb, p.apply_log, p.log_clip);
+                  ga[k] = va;
+                  esum_a = fmaf(va, va, esum_a);
+                  if (b_valid) {
+                    gb[k] = vb;
+                    esum_b = fmaf(vb, vb, esum_b);
+                  }
                 }
               }
-            }
-          }
-        } else {
-          // X[k] = E - T, X[M-k] = conj(E + T), E = Z[k] + conj(Z[M-k]), T = i * w_k * (Z[k] - conj(Z[M-k]))
-          const float er = zr + pr, ei = zi - pi;
-          const float orr = zr - pr, oi = zi + pi;
-          const float2 w = s_wpost[k];  // (cos, -sin)(2 pi k / 2048)
-          const float tr = -fmaf(w.x, oi, w.y * orr);
-          const float ti = fmaf(w.x, orr, -w.y * oi);
-          const float x0r = er - tr, x0i = ei - ti;      // bin k
-          const float x1r = er + tr, x1i = -(ei + ti);   // bin 1024 - k
-          const int km = 1024 - k;
-          const bool has_mirror = (j < 16);              // k == 512 is its own mirror
-          if constexpr (SPEC == EVF_SPEC_RAW) {
-            reinterpret_cast<float2*>(ga)[k] = make_float2(x0r, x0i);
-            if (has_mirror) reinterpret_cast<float2*>(ga)[km] = make_float2(x1r, x1i);
-          } else {
-            float p0 = fmaf(x0r, x0r, x0i * x0i);
-            float p1 = fmaf(x1r, x1r, x1i * x1i);
-            if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
-              p0 = sqrtf(p0 + 1e-9f);
-              p1 = sqrtf(p1 + 1e-9f);
-            }
-            if constexpr (kMel) {
-              if (k < kcap) s_p[k * FS + fa] = p0;
-              if (has_mirror && km < kcap) s_p[km * FS + fa] = p1;
             } else {
-              const float v0 = compress(p0, p.apply_log, p.log_clip);
-              ga[k] = v0;
-              esum_a = fmaf(v0, v0, esum_a);
-              if (has_mirror) {
-                const float v1 = compress(p1, p.apply_log, p.log_clip);
-                ga[km] = v1;
-                esum_a = fmaf(v1, v1, esum_a);
+              // X[k] = E - T, X[M-k] = conj(E + T), E = Z[k] + conj(Z[M-k]), T = i * w_k * (Z[k] - conj(Z[M-k]))
+              const float er = zr + pr, ei = zi - pi;
+              const float orr = zr - pr, oi = zi + pi;
+              const float2 w = s_wpost[k];  // (cos, -sin)(2 pi k / 2048)
+              const float tr = -fmaf(w.x, oi, w.y * orr);
+              const float ti = fmaf(w.x, orr, -w.y * oi);
+              const float x0r = er - tr, x0i = ei - ti;      // bin k
+              const float x1r = er + tr, x1i = -(ei + ti);   // bin 1024 - k
+              const int km = 1024 - k;
+              constexpr bool kHasMirrorRow = true;
+              const bool has_mirror = kHasMirrorRow && (j < 16);  // k == 512 is its own mirror
+              if constexpr (SPEC == EVF_SPEC_RAW) {
+                reinterpret_cast<float2*>(ga)[k] = make_float2(x0r, x0i);
+                if (has_mirror) reinterpret_cast<float2*>(ga)[km] = make_float2(x1r, x1i);
+              } else {
+                float p0 = fmaf(x0r, x0r, x0i * x0i);
+                float p1 = fmaf(x1r, x1r, x1i * x1i);
+                if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
+                  p0 = sqrtf(p0 + 1e-9f);
+                  p1 = sqrtf(p1 + 1e-9f);
+                }
+                if constexpr (kMel) {
+                  if (k < kcap) s_p[k * FS + fa] = p0;
+                  if (has_mirror && km < kcap) s_p[km * FS + fa] = p1;
+                } else {
+                  const float v0 = compress(p0, p.apply_log, p.log_clip);
+                  ga[k] = v0;
+                  esum_a = fmaf(v0, v0, esum_a);
+                  if (has_mirror) {
+                    const float v1 = compress(p1, p.apply_log, p.log_clip);
+                    ga[km] = v1;
+                    esum_a = fmaf(v1, v1, esum_a);
+                  }
+                }
               }
             }
           }
@@ -304,8 +423,19 @@ __global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams 
       }
     }
 
+    // the next tile's manual words (reflected margins) were loaded before the FFT: store them now
+    if (deferred) {
+      if (tid < nmr.total) s_next[manual_word(nmr, tid)] = mv0;
+      if (tid + kThreads < nmr.total) s_next[manual_word(nmr, tid + kThreads)] = mv1;
+    }
+    __syncthreads();  // (1) input tile consumed, P tile complete, next tile's manual words visible
+    if (has_next && nbuf == 1) {
+      // single input buffer (large-footprint plans): restage now, overlapping phases B and C
+      const ManualRange mr = stage_issue(nxt, s_in, &s_bar[0]);
+      manual_fill_now(nxt, mr, s_in);
+    }
+
     if constexpr (kMel) {
-      __syncthreads();
       // ---- phase B: mel projection, lane = frame ---------------------------------------
       {
         const int fr = lane % FR;
@@ -317,6 +447,7 @@ __global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams 
           for (int j = m0; j <= m1; ++j) {
             const int kb = s_kstart[j], ke = s_kstart[j + 1];
             float sa = 0.f, sb = 0.f;
+#pragma unroll 4
             for (int k = kb; k < ke; ++k) {
               const float pv = pcol[k * FS];
               const float2 w = s_melw[k];
@@ -328,7 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams 
           }
         }
       }
-      __syncthreads();
+      __syncthreads();  // (2)
       // ---- phase C: coalesced store of the log-mel rows + per-frame energy --------------
 #pragma unroll
       for (int q = 0; q < FPJ; ++q) {
@@ -350,8 +481,9 @@ __global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams 
         }
       }
     } else {
-      __syncthreads();  // the input tile is about to be overwritten
+      if (nbuf == 1) __syncthreads();  // the restaged manual words must be visible to the next FFT
     }
+    cur = nxt;
   }
 }
 
@@ -403,39 +535,51 @@ int features_smem_bytes(int mode, int spec_type, int hop, int n_fft, int n_mels,
   const int fr = kWarps * fpj;
   const int parts = 32 / fr;
   auto up4 = [](int w) { return (w + 3) & ~3; };
-  int w = 0;
-  c->off_in = w;
-  c->in_words = up4((fr - 1) * hop + n_fft);
-  w += c->in_words;
-  c->off_win = w;
-  w += up4(n_fft);
-  c->off_tw = w;
-  w += 2 * kFftSize;
-  c->off_wpost = w;
-  if (mode == MODE_HALF) w += up4(2 * 513);
-  c->off_melw = w;
-  c->off_kstart = w;
-  c->off_vwm = w;
-  c->off_p = w;
-  c->off_sout = w;
-  c->sout_stride = 1;
-  if (mel) {
-    w += up4(2 * k_used);
+  // Prefer two input buffers (the next tile's bulk copy overlaps this tile's FFTs); fall back
+  // to one when the plan's tables do not leave room for it.
+  for (int nbuf = 2; nbuf >= 1; --nbuf) {
+    int w = 0;
+    c->nbuf = nbuf;
+    c->off_bar = w;
+    w += 4;  // two 8-byte mbarriers
+    c->off_in = w;
+    c->in_words = up4((fr - 1) * hop + n_fft);
+    w += c->in_words;
+    c->off_in2 = c->off_in;
+    if (nbuf == 2) {
+      c->off_in2 = w;
+      w += c->in_words;
+    }
+    c->off_win = w;
+    w += up4(n_fft);
+    c->off_tw = w;
+    w += 2 * kFftSize;
+    c->off_wpost = w;
+    if (mode == MODE_HALF) w += up4(2 * 513);
+    c->off_melw = w;
     c->off_kstart = w;
-    w += up4(n_mels + 2);
     c->off_vwm = w;
-    w += up4(kWarps * parts + 1);
     c->off_p = w;
-    w += up4(k_used * (fr + 1));
     c->off_sout = w;
-    c->sout_stride = n_mels | 1;
-    w += up4(fr * c->sout_stride);
+    c->sout_stride = 1;
+    if (mel) {
+      w += up4(2 * k_used);
+      c->off_kstart = w;
+      w += up4(n_mels + 2);
+      c->off_vwm = w;
+      w += up4(kWarps * parts + 1);
+      c->off_p = w;
+      w += up4(k_used * (fr + 1));
+      c->off_sout = w;
+      c->sout_stride = n_mels | 1;
+      w += up4(fr * c->sout_stride);
+    }
+    c->off_scr = w;
+    w += kWarps * 32 * kScrStride;
+    const long long bytes = 4ll * w;
+    if (bytes <= 227 * 1024) return (int)bytes;
   }
-  c->off_scr = w;
-  w += kWarps * 32 * kScrStride;
-  const long long bytes = 4ll * w;
-  if (bytes > 227 * 1024) return -1;
-  return (int)bytes;
+  return -1;
 }
 
 int features_configure(int mode, int spec_type, int sample_format, int smem_bytes) {

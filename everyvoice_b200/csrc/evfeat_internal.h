@@ -44,7 +44,9 @@ struct FeatParams {
   int apply_log;
   float log_clip;
   // shared-memory carve-up, in 4-byte words from the start of dynamic shared memory
-  int off_in, off_win, off_tw, off_wpost, off_melw, off_kstart, off_vwm, off_p, off_scr, off_sout;
+  int off_bar, off_in, off_in2, off_win, off_tw, off_wpost, off_melw, off_kstart, off_vwm, off_p, off_scr,
+      off_sout;
+  int nbuf;              // input tile buffers: 2 = bulk-copy prefetch of the next tile, 1 = restage in place
   int in_words;          // capacity of the input tile
   int sout_stride;       // odd row stride of the output staging tile
 };
