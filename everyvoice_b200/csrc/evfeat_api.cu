@@ -1,6 +1,7 @@
 // C ABI of libevfeat.so (see include/evfeat.h): plan / batch management and entry points.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -14,6 +15,7 @@ struct evf_plan {
   int n_freq = 0;
   int row_floats = 0;
   int frames_per_tile = 0;
+  int warps = 16;
   int num_sms = 0;
   int smem_bytes = 0;
   int k_used = 0;
@@ -24,7 +26,8 @@ struct evf_plan {
   float2* d_wpost = nullptr;
   float2* d_melw = nullptr;
   int* d_kstart = nullptr;
-  int* d_vwm = nullptr;
+  int* d_vwk = nullptr;
+  int* d_jk = nullptr;
 };
 
 struct evf_batch {
@@ -130,19 +133,33 @@ int compress_filterbank(const float* fb, int n_freq, int n_mels, int n_vw, PlanT
     }
     t->kstart[n_mels + 1] = k_used;
   }
-  // Split the mels over the projection workers, balanced by the bins each has to walk.
-  std::vector<long long> prefix(n_mels + 1, 0);
-  for (int m = 0; m < n_mels; ++m)
-    prefix[m + 1] = prefix[m] + (t->kstart[m + 1] - t->kstart[m]) + 2;
-  t->vw_m.assign(n_vw + 1, n_mels);
-  t->vw_m[0] = 0;
-  int m = 0;
-  for (int v = 1; v < n_vw; ++v) {
-    const long long target = prefix[n_mels] * v / n_vw;
-    while (m < n_mels && prefix[m] < target) ++m;
-    t->vw_m[v] = m;
+  t->jk.assign(jk.begin(), jk.begin() + k_used);
+  t->jk.push_back(-1);  // sentinel: the last bin always ends its interval
+  // Split the bins over the projection workers: contiguous runs of whole intervals with the
+  // largest run as small as possible (binary search on the cap, greedy feasibility check).
+  // Interval j owns bins [kstart[j], kstart[j + 1]), j = 0 .. n_mels.
+  const int n_int = n_mels + 1;
+  auto feasible = [&](int cap, std::vector<int>* cuts) {
+    int j = 0;
+    if (cuts) cuts->assign(n_vw + 1, k_used);
+    if (cuts) (*cuts)[0] = 0;
+    for (int v = 0; v < n_vw && j < n_int; ++v) {
+      const int k0 = t->kstart[j];
+      int e = j + 1;
+      if (t->kstart[e] - k0 > cap) return false;
+      while (e < n_int && t->kstart[e + 1] - k0 <= cap) ++e;
+      j = e;
+      if (cuts) (*cuts)[v + 1] = t->kstart[j];
+    }
+    return j >= n_int;
+  };
+  int lo = 1, hi = k_used;
+  while (lo < hi) {
+    const int mid = (lo + hi) / 2;
+    if (feasible(mid, nullptr)) hi = mid; else lo = mid + 1;
   }
-  t->vw_m[n_vw] = n_mels;
+  feasible(lo, &t->vw_k);
+  t->vw_k[n_vw] = k_used;
   return EVF_OK;
 }
 
@@ -152,7 +169,8 @@ void free_plan_tables(evf_plan* p) {
   cudaFree(p->d_wpost);
   cudaFree(p->d_melw);
   cudaFree(p->d_kstart);
-  cudaFree(p->d_vwm);
+  cudaFree(p->d_vwk);
+  cudaFree(p->d_jk);
 }
 
 }  // namespace
@@ -220,7 +238,12 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   p->device = device;
   p->mode = (cfg->n_fft == 1024) ? MODE_PACK2 : MODE_HALF;
   p->n_freq = cfg->n_fft / 2 + 1;
-  p->frames_per_tile = kWarps * (p->mode == MODE_PACK2 ? 2 : 1);
+  {
+    // CTA shape: 8 warps x 2 CTAs/SM (default) or 16 warps x 1 CTA/SM (EVF_WARPS=16)
+    const char* e = getenv("EVF_WARPS");
+    p->warps = (e && atoi(e) == 16) ? 16 : 8;
+  }
+  p->frames_per_tile = p->warps * (p->mode == MODE_PACK2 ? 2 : 1);
   p->num_sms = prop.multiProcessorCount;
   p->row_floats = mel ? cfg->n_mels : (cfg->spec_type == EVF_SPEC_RAW ? 2 * p->n_freq : p->n_freq);
 
@@ -245,25 +268,32 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   }
   int rc = EVF_OK;
   if (mel) {
-    const int n_vw = kWarps * (32 / p->frames_per_tile);
+    const int n_vw = p->warps * (32 / p->frames_per_tile);
     rc = compress_filterbank(mel_fb_host, p->n_freq, cfg->n_mels, n_vw, &t);
     if (rc != EVF_OK) { delete p; return rc; }
     p->k_used = t.k_used;
   }
-  p->smem_bytes = features_smem_bytes(p->mode, cfg->spec_type, cfg->hop_length, cfg->n_fft,
+  p->smem_bytes = features_smem_bytes(p->mode, cfg->spec_type, p->warps, cfg->hop_length, cfg->n_fft,
                                       cfg->n_mels, p->k_used, &p->carve);
+  if (p->smem_bytes < 0 && p->warps == 8) {  // does not fit twice per SM: one 16-warp CTA per SM
+    p->warps = 16;
+    p->frames_per_tile = p->warps * (p->mode == MODE_PACK2 ? 2 : 1);
+    p->smem_bytes = features_smem_bytes(p->mode, cfg->spec_type, p->warps, cfg->hop_length, cfg->n_fft,
+                                        cfg->n_mels, p->k_used, &p->carve);
+  }
   if (p->smem_bytes < 0) {
     delete p;
     set_error("evf_plan_create: this n_fft / hop_length / n_mels combination needs more than 227 KB of shared memory per CTA");
     return EVF_ERR_UNSUPPORTED;
   }
-  rc = features_configure(p->mode, cfg->spec_type, cfg->sample_format, p->smem_bytes);
+  rc = features_configure(p->mode, cfg->spec_type, cfg->sample_format, p->warps, p->smem_bytes);
   if (rc == EVF_OK) rc = upload(t.window, &p->d_window);
   if (rc == EVF_OK) rc = upload(t.tw, &p->d_tw);
   if (rc == EVF_OK) rc = upload(t.wpost, &p->d_wpost);
   if (rc == EVF_OK) rc = upload(t.melw, &p->d_melw);
   if (rc == EVF_OK) rc = upload(t.kstart, &p->d_kstart);
-  if (rc == EVF_OK) rc = upload(t.vw_m, &p->d_vwm);
+  if (rc == EVF_OK) rc = upload(t.vw_k, &p->d_vwk);
+  if (rc == EVF_OK) rc = upload(t.jk, &p->d_jk);
   if (rc != EVF_OK) {
     free_plan_tables(p);
     delete p;
@@ -410,7 +440,8 @@ int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* s
   p.wpost = plan->d_wpost;
   p.melw = plan->d_melw;
   p.kstart = plan->d_kstart;
-  p.vw_m = plan->d_vwm;
+  p.vw_k = plan->d_vwk;
+  p.jk = plan->d_jk;
   p.hop = plan->cfg.hop_length;
   p.n_mels = plan->cfg.n_mels;
   p.n_freq = plan->n_freq;
@@ -418,8 +449,9 @@ int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* s
   p.row_floats = plan->row_floats;
   p.apply_log = (plan->cfg.spec_type == EVF_SPEC_RAW) ? 0 : plan->cfg.apply_log;
   p.log_clip = plan->cfg.log_clip;
-  const int grid = batch->n_tiles < plan->num_sms ? batch->n_tiles : plan->num_sms;
-  return features_launch(plan->mode, plan->cfg.spec_type, plan->cfg.sample_format, p, grid,
+  const int max_ctas = plan->num_sms * (16 / plan->warps);
+  const int grid = batch->n_tiles < max_ctas ? batch->n_tiles : max_ctas;
+  return features_launch(plan->mode, plan->cfg.spec_type, plan->cfg.sample_format, plan->warps, p, grid,
                          plan->smem_bytes, static_cast<cudaStream_t>(stream));
 }
 

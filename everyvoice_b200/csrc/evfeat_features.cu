@@ -148,12 +148,13 @@ __device__ __forceinline__ int reflect_index(int j, int L) {
   return (j < 0) ? 0 : j;  // only reachable for frames beyond the last valid one
 }
 
-template <int MODE, int SPEC, typename SampleT>
-__global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams p) {
+template <int MODE, int SPEC, typename SampleT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const FeatParams p) {
   using MT = ModeTraits<MODE>;
+  constexpr int kThreads = WARPS * 32;
   constexpr int NFFT = MT::kNfft;
   constexpr int FPJ = MT::kFramesPerJob;
-  constexpr int FR = kWarps * FPJ;        // frames per tile
+  constexpr int FR = WARPS * FPJ;         // frames per tile
   constexpr int FS = FR + 1;              // padded frame stride of the P tile
   constexpr int PARTS = 32 / FR;          // projection workers per warp
   constexpr bool kMel = (SPEC == EVF_SPEC_MEL || SPEC == EVF_SPEC_MEL_LIBROSA);
@@ -165,9 +166,11 @@ __global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams 
   float2* s_wpost = reinterpret_cast<float2*>(smem + p.off_wpost);
   float2* s_melw = reinterpret_cast<float2*>(smem + p.off_melw);
   int* s_kstart = reinterpret_cast<int*>(smem + p.off_kstart);
-  int* s_vwm = reinterpret_cast<int*>(smem + p.off_vwm);
+  int* s_vwk = reinterpret_cast<int*>(smem + p.off_vwk);
+  int* s_jk = reinterpret_cast<int*>(smem + p.off_jk);
   float* s_p = smem + p.off_p;
-  float* s_out = smem + p.off_sout;
+  float* s_sa = smem + p.off_sa;
+  float* s_sb = smem + p.off_sb;
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
 
   const int tid = threadIdx.x;
@@ -190,7 +193,8 @@ __global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams 
   if constexpr (kMel) {
     for (int i = tid; i < p.k_used; i += kThreads) s_melw[i] = p.melw[i];
     for (int i = tid; i < p.n_mels + 2; i += kThreads) s_kstart[i] = p.kstart[i];
-    for (int i = tid; i < kWarps * PARTS + 1; i += kThreads) s_vwm[i] = p.vw_m[i];
+    for (int i = tid; i < WARPS * PARTS + 1; i += kThreads) s_vwk[i] = p.vw_k[i];
+    for (int i = tid; i < p.k_used + 1; i += kThreads) s_jk[i] = p.jk[i];
   }
   __syncthreads();
 
@@ -437,39 +441,64 @@ __global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams 
 
     if constexpr (kMel) {
       // ---- phase B: mel projection, lane = frame ---------------------------------------
+      // Each worker (a warp, or a half / quarter warp when the tile has fewer than 32 frames)
+      // walks a contiguous run of bins that starts and ends on interval boundaries.  Two running
+      // FMAs per bin; when the interval index changes the two sums are flushed (fire-and-forget
+      // stores, linear domain): SA[j] = sum of rising-slope weights * P over interval j,
+      // SB[j] = the same for the falling slopes.  mel[m] = SA[m] + SB[m + 1] (phase C).
       {
         const int fr = lane % FR;
         const int vw = warp * PARTS + lane / FR;
-        const int m0 = s_vwm[vw], m1 = s_vwm[vw + 1];
-        if (m0 < m1) {
-          const float* pcol = s_p + fr;
-          float sa_prev = 0.f;
-          for (int j = m0; j <= m1; ++j) {
-            const int kb = s_kstart[j], ke = s_kstart[j + 1];
-            float sa = 0.f, sb = 0.f;
-#pragma unroll 4
-            for (int k = kb; k < ke; ++k) {
-              const float pv = pcol[k * FS];
-              const float2 w = s_melw[k];
-              sa = fmaf(w.x, pv, sa);
-              sb = fmaf(w.y, pv, sb);
-            }
-            if (j > m0) s_out[fr * p.sout_stride + (j - 1)] = compress(sa_prev + sb, p.apply_log, p.log_clip);
-            sa_prev = sa;
-          }
+        int k = s_vwk[vw];
+        const int k1 = s_vwk[vw + 1];
+        const float* pcol = s_p + fr;
+        float* sa_col = s_sa + fr;
+        float* sb_col = s_sb + fr;
+        float sa = 0.f, sb = 0.f;
+        int jc = (k < k1) ? s_jk[k] : 0;
+        for (; k + 4 <= k1; k += 4) {
+          const float p0 = pcol[(k + 0) * FS], p1 = pcol[(k + 1) * FS];
+          const float p2 = pcol[(k + 2) * FS], p3 = pcol[(k + 3) * FS];
+          const float2 w0 = s_melw[k + 0], w1 = s_melw[k + 1], w2 = s_melw[k + 2], w3 = s_melw[k + 3];
+          const int j1 = s_jk[k + 1], j2 = s_jk[k + 2], j3 = s_jk[k + 3], j4 = s_jk[k + 4];
+          sa = fmaf(w0.x, p0, sa);
+          sb = fmaf(w0.y, p0, sb);
+          if (j1 != jc) { sa_col[jc * FS] = sa; sb_col[jc * FS] = sb; sa = 0.f; sb = 0.f; }
+          sa = fmaf(w1.x, p1, sa);
+          sb = fmaf(w1.y, p1, sb);
+          if (j2 != j1) { sa_col[j1 * FS] = sa; sb_col[j1 * FS] = sb; sa = 0.f; sb = 0.f; }
+          sa = fmaf(w2.x, p2, sa);
+          sb = fmaf(w2.y, p2, sb);
+          if (j3 != j2) { sa_col[j2 * FS] = sa; sb_col[j2 * FS] = sb; sa = 0.f; sb = 0.f; }
+          sa = fmaf(w3.x, p3, sa);
+          sb = fmaf(w3.y, p3, sb);
+          if (j4 != j3) { sa_col[j3 * FS] = sa; sb_col[j3 * FS] = sb; sa = 0.f; sb = 0.f; }
+          jc = j4;
+        }
+        for (; k < k1; ++k) {
+          const float pv = pcol[k * FS];
+          const float2 w = s_melw[k];
+          const int jn = s_jk[k + 1];
+          sa = fmaf(w.x, pv, sa);
+          sb = fmaf(w.y, pv, sb);
+          if (jn != jc) { sa_col[jc * FS] = sa; sb_col[jc * FS] = sb; sa = 0.f; sb = 0.f; }
+          jc = jn;
         }
       }
       __syncthreads();  // (2)
-      // ---- phase C: coalesced store of the log-mel rows + per-frame energy --------------
+      // ---- phase C: combine, log, coalesced store of the log-mel rows + per-frame energy ---
 #pragma unroll
       for (int q = 0; q < FPJ; ++q) {
         const int f = warp * FPJ + q;
         if (f < nvalid) {
-          const float* row = s_out + f * p.sout_stride;
           float* dst = p.spec_out + (out_frame0 + f) * (long long)p.row_floats;
           float acc = 0.f;
           for (int m = lane; m < p.n_mels; m += 32) {
-            const float v = row[m];
+            const int ks0 = s_kstart[m], ks1 = s_kstart[m + 1], ks2 = s_kstart[m + 2];
+            float v = 0.f;
+            if (ks1 > ks0) v = s_sa[m * FS + f];            // interval m has bins
+            if (ks2 > ks1) v += s_sb[(m + 1) * FS + f];     // interval m + 1 has bins
+            v = compress(v, p.apply_log, p.log_clip);
             dst[m] = v;
             acc = fmaf(v, v, acc);
           }
@@ -487,40 +516,46 @@ __global__ void __launch_bounds__(kThreads, 1) features_kernel(const FeatParams 
   }
 }
 
-template <int MODE, int SPEC, typename SampleT>
-int launch_t(const FeatParams& p, int grid, int smem, cudaStream_t stream, bool configure_only) {
-  auto kern = features_kernel<MODE, SPEC, SampleT>;
+template <int MODE, int SPEC, typename SampleT, int WARPS>
+int launch_w(const FeatParams& p, int grid, int smem, cudaStream_t stream, bool configure_only) {
+  auto kern = features_kernel<MODE, SPEC, SampleT, WARPS>;
   if (configure_only) {
     EVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return EVF_OK;
   }
-  kern<<<grid, kThreads, smem, stream>>>(p);
+  kern<<<grid, WARPS * 32, smem, stream>>>(p);
   EVF_CUDA(cudaGetLastError());
   return EVF_OK;
 }
 
+template <int MODE, int SPEC, typename SampleT>
+int launch_t(int warps, const FeatParams& p, int grid, int smem, cudaStream_t stream, bool cfg) {
+  if (warps == 8) return launch_w<MODE, SPEC, SampleT, 8>(p, grid, smem, stream, cfg);
+  return launch_w<MODE, SPEC, SampleT, 16>(p, grid, smem, stream, cfg);
+}
+
 template <int MODE, int SPEC>
-int launch_s(int fmt, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
-  if (fmt == EVF_SAMPLES_S16) return launch_t<MODE, SPEC, short>(p, grid, smem, st, cfg);
-  return launch_t<MODE, SPEC, float>(p, grid, smem, st, cfg);
+int launch_s(int fmt, int warps, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
+  if (fmt == EVF_SAMPLES_S16) return launch_t<MODE, SPEC, short>(warps, p, grid, smem, st, cfg);
+  return launch_t<MODE, SPEC, float>(warps, p, grid, smem, st, cfg);
 }
 
 template <int MODE>
-int launch_m(int spec, int fmt, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
+int launch_m(int spec, int fmt, int warps, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
   switch (spec) {
-    case EVF_SPEC_MEL: return launch_s<MODE, EVF_SPEC_MEL>(fmt, p, grid, smem, st, cfg);
-    case EVF_SPEC_MEL_LIBROSA: return launch_s<MODE, EVF_SPEC_MEL_LIBROSA>(fmt, p, grid, smem, st, cfg);
-    case EVF_SPEC_LINEAR: return launch_s<MODE, EVF_SPEC_LINEAR>(fmt, p, grid, smem, st, cfg);
-    case EVF_SPEC_RAW: return launch_s<MODE, EVF_SPEC_RAW>(fmt, p, grid, smem, st, cfg);
+    case EVF_SPEC_MEL: return launch_s<MODE, EVF_SPEC_MEL>(fmt, warps, p, grid, smem, st, cfg);
+    case EVF_SPEC_MEL_LIBROSA: return launch_s<MODE, EVF_SPEC_MEL_LIBROSA>(fmt, warps, p, grid, smem, st, cfg);
+    case EVF_SPEC_LINEAR: return launch_s<MODE, EVF_SPEC_LINEAR>(fmt, warps, p, grid, smem, st, cfg);
+    case EVF_SPEC_RAW: return launch_s<MODE, EVF_SPEC_RAW>(fmt, warps, p, grid, smem, st, cfg);
   }
   set_error("unknown spec_type");
   return EVF_ERR_UNSUPPORTED;
 }
 
-int dispatch(int mode, int spec, int fmt, const FeatParams& p, int grid, int smem, cudaStream_t st,
+int dispatch(int mode, int spec, int fmt, int warps, const FeatParams& p, int grid, int smem, cudaStream_t st,
              bool cfg) {
-  if (mode == MODE_PACK2) return launch_m<MODE_PACK2>(spec, fmt, p, grid, smem, st, cfg);
-  if (mode == MODE_HALF) return launch_m<MODE_HALF>(spec, fmt, p, grid, smem, st, cfg);
+  if (mode == MODE_PACK2) return launch_m<MODE_PACK2>(spec, fmt, warps, p, grid, smem, st, cfg);
+  if (mode == MODE_HALF) return launch_m<MODE_HALF>(spec, fmt, warps, p, grid, smem, st, cfg);
   set_error("unknown FFT mode");
   return EVF_ERR_UNSUPPORTED;
 }
@@ -528,12 +563,14 @@ int dispatch(int mode, int spec, int fmt, const FeatParams& p, int grid, int sme
 }  // namespace
 
 // Computes the shared-memory carve-up for a plan; returns bytes (or -1 if it cannot fit).
-int features_smem_bytes(int mode, int spec_type, int hop, int n_fft, int n_mels, int k_used,
+int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, int n_mels, int k_used,
                         FeatParams* c) {
   const bool mel = (spec_type == EVF_SPEC_MEL || spec_type == EVF_SPEC_MEL_LIBROSA);
   const int fpj = (mode == MODE_PACK2) ? 2 : 1;
-  const int fr = kWarps * fpj;
+  const int fr = warps * fpj;
   const int parts = 32 / fr;
+  // 16 warps: one CTA per SM (227 KB); 8 warps: two CTAs per SM (228 KB - 2 x 1 KB reserved, halved)
+  const long long limit = (warps == 16) ? 227 * 1024 : 113 * 1024;
   auto up4 = [](int w) { return (w + 3) & ~3; };
   // Prefer two input buffers (the next tile's bulk copy overlaps this tile's FFTs); fall back
   // to one when the plan's tables do not leave room for it.
@@ -558,38 +595,42 @@ int features_smem_bytes(int mode, int spec_type, int hop, int n_fft, int n_mels,
     if (mode == MODE_HALF) w += up4(2 * 513);
     c->off_melw = w;
     c->off_kstart = w;
-    c->off_vwm = w;
+    c->off_vwk = w;
+    c->off_jk = w;
     c->off_p = w;
-    c->off_sout = w;
-    c->sout_stride = 1;
+    c->off_sa = w;
+    c->off_sb = w;
     if (mel) {
       w += up4(2 * k_used);
       c->off_kstart = w;
       w += up4(n_mels + 2);
-      c->off_vwm = w;
-      w += up4(kWarps * parts + 1);
+      c->off_vwk = w;
+      w += up4(warps * parts + 1);
+      c->off_jk = w;
+      w += up4(k_used + 1);
       c->off_p = w;
       w += up4(k_used * (fr + 1));
-      c->off_sout = w;
-      c->sout_stride = n_mels | 1;
-      w += up4(fr * c->sout_stride);
+      c->off_sa = w;
+      w += up4((n_mels + 1) * (fr + 1));
+      c->off_sb = w;
+      w += up4((n_mels + 1) * (fr + 1));
     }
     c->off_scr = w;
-    w += kWarps * 32 * kScrStride;
+    w += warps * 32 * kScrStride;
     const long long bytes = 4ll * w;
-    if (bytes <= 227 * 1024) return (int)bytes;
+    if (bytes <= limit) return (int)bytes;
   }
   return -1;
 }
 
-int features_configure(int mode, int spec_type, int sample_format, int smem_bytes) {
+int features_configure(int mode, int spec_type, int sample_format, int warps, int smem_bytes) {
   FeatParams dummy{};
-  return dispatch(mode, spec_type, sample_format, dummy, 1, smem_bytes, nullptr, true);
+  return dispatch(mode, spec_type, sample_format, warps, dummy, 1, smem_bytes, nullptr, true);
 }
 
-int features_launch(int mode, int spec_type, int sample_format, const FeatParams& p, int grid,
+int features_launch(int mode, int spec_type, int sample_format, int warps, const FeatParams& p, int grid,
                     int smem_bytes, cudaStream_t stream) {
-  return dispatch(mode, spec_type, sample_format, p, grid, smem_bytes, stream, false);
+  return dispatch(mode, spec_type, sample_format, warps, p, grid, smem_bytes, stream, false);
 }
 
 }  // namespace evf

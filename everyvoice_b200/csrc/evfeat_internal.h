@@ -10,8 +10,7 @@
 
 namespace evf {
 
-constexpr int kWarps = 16;           // warps per CTA; one 1024-point complex FFT per warp per tile
-constexpr int kThreads = kWarps * 32;
+constexpr int kMaxWarps = 16;        // warps per CTA (16 x 1 CTA/SM or 8 x 2 CTAs/SM); one FFT job per warp per tile
 constexpr int kFftSize = 1024;       // complex points per warp-level FFT
 constexpr int kScrStride = 33;       // padded row stride of the per-warp transpose scratch
 
@@ -35,7 +34,8 @@ struct FeatParams {
   const float2* wpost;   // MODE_HALF: exp(-2 pi i k / n_fft), k = 0..512
   const float2* melw;    // [k_used] (rising weight -> mel j(k), falling weight -> mel j(k)-1)
   const int* kstart;     // [n_mels + 2] first bin of every inter-centre interval
-  const int* vw_m;       // [n_vw + 1] mel range of every virtual worker of the projection phase
+  const int* vw_k;       // [n_vw + 1] bin range of every worker of the projection phase (interval aligned)
+  const int* jk;         // [k_used + 1] interval index of every bin (+ sentinel)
   int hop;
   int n_mels;
   int n_freq;
@@ -44,11 +44,10 @@ struct FeatParams {
   int apply_log;
   float log_clip;
   // shared-memory carve-up, in 4-byte words from the start of dynamic shared memory
-  int off_bar, off_in, off_in2, off_win, off_tw, off_wpost, off_melw, off_kstart, off_vwm, off_p, off_scr,
-      off_sout;
+  int off_bar, off_in, off_in2, off_win, off_tw, off_wpost, off_melw, off_kstart, off_vwk, off_jk, off_p,
+      off_sa, off_sb, off_scr;
   int nbuf;              // input tile buffers: 2 = bulk-copy prefetch of the next tile, 1 = restage in place
   int in_words;          // capacity of the input tile
-  int sout_stride;       // odd row stride of the output staging tile
 };
 
 struct PlanTables {
@@ -57,7 +56,8 @@ struct PlanTables {
   std::vector<float2> wpost;      // 513 (MODE_HALF) or empty
   std::vector<float2> melw;       // k_used
   std::vector<int> kstart;        // n_mels + 2
-  std::vector<int> vw_m;          // n_vw + 1
+  std::vector<int> vw_k;          // n_vw + 1
+  std::vector<int> jk;            // k_used + 1
   int k_used = 0;
 };
 
@@ -70,10 +70,10 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 // evfeat_features.cu
-int features_smem_bytes(int mode, int spec_type, int hop, int n_fft, int n_mels, int k_used,
+int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, int n_mels, int k_used,
                         FeatParams* carve);
-int features_configure(int mode, int spec_type, int sample_format, int smem_bytes);
-int features_launch(int mode, int spec_type, int sample_format, const FeatParams& p, int grid,
+int features_configure(int mode, int spec_type, int sample_format, int warps, int smem_bytes);
+int features_launch(int mode, int spec_type, int sample_format, int warps, const FeatParams& p, int grid,
                     int smem_bytes, cudaStream_t stream);
 
 // evfeat_aux.cu
