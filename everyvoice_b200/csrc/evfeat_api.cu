@@ -24,10 +24,8 @@ struct evf_plan {
   float* d_window = nullptr;
   float2* d_tw = nullptr;
   float2* d_wpost = nullptr;
-  float2* d_melw = nullptr;
-  int* d_kstart = nullptr;
+  float4* d_melw4 = nullptr;
   int* d_vwk = nullptr;
-  int* d_jk = nullptr;
 };
 
 struct evf_batch {
@@ -38,7 +36,7 @@ struct evf_batch {
   std::vector<int64_t> frame_off;  // host copy
   long long* d_sample_off = nullptr;
   long long* d_frame_off = nullptr;
-  int2* d_tiles = nullptr;
+  evf::TileDesc* d_tiles = nullptr;
 };
 
 namespace evf {
@@ -135,6 +133,14 @@ int compress_filterbank(const float* fb, int n_freq, int n_mels, int n_vw, PlanT
   }
   t->jk.assign(jk.begin(), jk.begin() + k_used);
   t->jk.push_back(-1);  // sentinel: the last bin always ends its interval
+  t->melw4.resize(k_used);
+  for (int k = 0; k < k_used; ++k) {
+    float jz, jw;
+    const int j0 = t->jk[k], j1 = t->jk[k + 1];
+    memcpy(&jz, &j0, 4);
+    memcpy(&jw, &j1, 4);
+    t->melw4[k] = make_float4(w[k].x, w[k].y, jz, jw);
+  }
   // Split the bins over the projection workers: contiguous runs of whole intervals with the
   // largest run as small as possible (binary search on the cap, greedy feasibility check).
   // Interval j owns bins [kstart[j], kstart[j + 1]), j = 0 .. n_mels.
@@ -167,10 +173,8 @@ void free_plan_tables(evf_plan* p) {
   cudaFree(p->d_window);
   cudaFree(p->d_tw);
   cudaFree(p->d_wpost);
-  cudaFree(p->d_melw);
-  cudaFree(p->d_kstart);
+  cudaFree(p->d_melw4);
   cudaFree(p->d_vwk);
-  cudaFree(p->d_jk);
 }
 
 }  // namespace
@@ -239,9 +243,9 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   p->mode = (cfg->n_fft == 1024) ? MODE_PACK2 : MODE_HALF;
   p->n_freq = cfg->n_fft / 2 + 1;
   {
-    // CTA shape: 8 warps x 2 CTAs/SM (default) or 16 warps x 1 CTA/SM (EVF_WARPS=16)
+    // CTA shape: 16 warps x 1 CTA/SM (default, measured faster) or 8 warps x 2 CTAs/SM (EVF_WARPS=8)
     const char* e = getenv("EVF_WARPS");
-    p->warps = (e && atoi(e) == 16) ? 16 : 8;
+    p->warps = (e && atoi(e) == 8) ? 8 : 16;
   }
   p->frames_per_tile = p->warps * (p->mode == MODE_PACK2 ? 2 : 1);
   p->num_sms = prop.multiProcessorCount;
@@ -290,10 +294,8 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   if (rc == EVF_OK) rc = upload(t.window, &p->d_window);
   if (rc == EVF_OK) rc = upload(t.tw, &p->d_tw);
   if (rc == EVF_OK) rc = upload(t.wpost, &p->d_wpost);
-  if (rc == EVF_OK) rc = upload(t.melw, &p->d_melw);
-  if (rc == EVF_OK) rc = upload(t.kstart, &p->d_kstart);
+  if (rc == EVF_OK) rc = upload(t.melw4, &p->d_melw4);
   if (rc == EVF_OK) rc = upload(t.vw_k, &p->d_vwk);
-  if (rc == EVF_OK) rc = upload(t.jk, &p->d_jk);
   if (rc != EVF_OK) {
     free_plan_tables(p);
     delete p;
@@ -334,7 +336,8 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
   }
   const int hop = plan->cfg.hop_length, n_fft = plan->cfg.n_fft, fr = plan->frames_per_tile;
   std::vector<long long> s_off(n_utts + 1, 0), f_off(n_utts + 1, 0);
-  std::vector<int2> tiles;
+  std::vector<TileDesc> tiles;
+  const int fpj = (plan->mode == MODE_PACK2) ? 2 : 1;
   for (int b = 0; b < n_utts; ++b) {
     const int64_t L = sample_offsets_host[b + 1] - sample_offsets_host[b];
     if (L <= n_fft / 2) {
@@ -350,8 +353,22 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
       set_error("evf_batch_create: utterance too long");
       return EVF_ERR_INVALID_ARGUMENT;
     }
+    if (L > 0x7fffffff - 4 * n_fft) {
+      set_error("evf_batch_create: utterance too long");
+      return EVF_ERR_INVALID_ARGUMENT;
+    }
     f_off[b + 1] = f_off[b] + T;
-    for (int64_t f0 = 0; f0 < T; f0 += fr) tiles.push_back(make_int2(b, (int)f0));
+    for (int64_t f0 = 0; f0 < T; f0 += fr) {
+      TileDesc d;
+      d.s_off = sample_offsets_host[b];
+      d.out_frame0 = f_off[b] + f0;
+      d.L = (int)L;
+      d.start = (int)(f0 * hop) - n_fft / 2;
+      d.nvalid = (int)((T - f0 < fr) ? (T - f0) : fr);
+      const int njobs = (d.nvalid + fpj - 1) / fpj;
+      d.span = (njobs * fpj - 1) * hop + n_fft;
+      tiles.push_back(d);
+    }
   }
   for (int b = 0; b <= n_utts; ++b) s_off[b] = n_utts ? sample_offsets_host[b] : 0;
 
@@ -429,8 +446,6 @@ int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* s
   DeviceGuard guard(plan->device);
   FeatParams p = plan->carve;
   p.samples = samples_dev;
-  p.sample_off = batch->d_sample_off;
-  p.frame_off = batch->d_frame_off;
   p.tiles = batch->d_tiles;
   p.n_tiles = batch->n_tiles;
   p.spec_out = spec_out_dev;
@@ -438,10 +453,8 @@ int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* s
   p.window = plan->d_window;
   p.tw = plan->d_tw;
   p.wpost = plan->d_wpost;
-  p.melw = plan->d_melw;
-  p.kstart = plan->d_kstart;
+  p.melw4 = plan->d_melw4;
   p.vw_k = plan->d_vwk;
-  p.jk = plan->d_jk;
   p.hop = plan->cfg.hop_length;
   p.n_mels = plan->cfg.n_mels;
   p.n_freq = plan->n_freq;

@@ -128,14 +128,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
-struct TileInfo {
-  long long s_off;       // first sample of the utterance in the packed buffer
-  long long out_frame0;  // first output frame of the tile in the packed output
-  int L;                 // samples in the utterance
-  int start;             // utterance-relative sample index of tile word 0 (may be negative)
-  int span;              // words of the tile that are consumed
-  int nvalid;            // frames of the tile that exist
-};
+using TileInfo = TileDesc;  // host-built, 32 bytes, one per tile (evfeat_internal.h)
 
 // The manual (non-bulk) part of a tile: tile words [0, a_lo) and [a_hi, span).
 struct ManualRange {
@@ -164,10 +157,8 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
   float* s_win = smem + p.off_win;
   float2* s_tw = reinterpret_cast<float2*>(smem + p.off_tw);
   float2* s_wpost = reinterpret_cast<float2*>(smem + p.off_wpost);
-  float2* s_melw = reinterpret_cast<float2*>(smem + p.off_melw);
-  int* s_kstart = reinterpret_cast<int*>(smem + p.off_kstart);
+  float4* s_mw4 = reinterpret_cast<float4*>(smem + p.off_melw);
   int* s_vwk = reinterpret_cast<int*>(smem + p.off_vwk);
-  int* s_jk = reinterpret_cast<int*>(smem + p.off_jk);
   float* s_p = smem + p.off_p;
   float* s_sa = smem + p.off_sa;
   float* s_sb = smem + p.off_sb;
@@ -191,28 +182,26 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
     for (int i = tid; i <= 512; i += kThreads) s_wpost[i] = p.wpost[i];
   }
   if constexpr (kMel) {
-    for (int i = tid; i < p.k_used; i += kThreads) s_melw[i] = p.melw[i];
-    for (int i = tid; i < p.n_mels + 2; i += kThreads) s_kstart[i] = p.kstart[i];
+    for (int i = tid; i < p.k_used; i += kThreads) s_mw4[i] = p.melw4[i];
     for (int i = tid; i < WARPS * PARTS + 1; i += kThreads) s_vwk[i] = p.vw_k[i];
-    for (int i = tid; i < p.k_used + 1; i += kThreads) s_jk[i] = p.jk[i];
+    for (int i = tid; i < 2 * (p.n_mels + 1) * FS; i += kThreads) s_sa[i] = 0.f;  // SA and SB are adjacent
   }
   __syncthreads();
 
   const int hop = p.hop;
   const SampleT* __restrict__ samples = static_cast<const SampleT*>(p.samples);
 
+  // Tile descriptors are host-built (no dependent loads) and fetched one iteration ahead.
   auto tile_info = [&](int tile) {
+    const int4* q = reinterpret_cast<const int4*>(p.tiles + tile);
+    const int4 a = __ldg(q), b = __ldg(q + 1);
     TileInfo ti;
-    const int2 tl = p.tiles[tile];
-    ti.s_off = p.sample_off[tl.x];
-    ti.L = (int)(p.sample_off[tl.x + 1] - ti.s_off);
-    const long long fr_off = p.frame_off[tl.x];
-    const int T = (int)(p.frame_off[tl.x + 1] - fr_off);
-    ti.nvalid = min(FR, T - tl.y);
-    ti.out_frame0 = fr_off + tl.y;
-    ti.start = tl.y * hop - NFFT / 2;
-    const int njobs = (ti.nvalid + FPJ - 1) / FPJ;
-    ti.span = (njobs * FPJ - 1) * hop + NFFT;
+    ti.s_off = ((long long)(unsigned)a.x) | ((long long)a.y << 32);
+    ti.out_frame0 = ((long long)(unsigned)a.z) | ((long long)a.w << 32);
+    ti.L = b.x;
+    ti.start = b.y;
+    ti.nvalid = b.z;
+    ti.span = b.w;
     return ti;
   };
 
@@ -250,6 +239,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
   int tile = blockIdx.x;
   if (tile >= p.n_tiles) return;
   TileInfo cur = tile_info(tile);
+  TileInfo nxt = (tile + (int)gridDim.x < p.n_tiles) ? tile_info(tile + gridDim.x) : cur;
   {
     const ManualRange mr = stage_issue(cur, smem + p.off_in, &s_bar[0]);
     manual_fill_now(cur, mr, smem + p.off_in);
@@ -262,13 +252,12 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
     const uint32_t parity = (nbuf == 2) ? ((it >> 1) & 1) : (it & 1);
     const int next_tile = tile + gridDim.x;
     const bool has_next = next_tile < p.n_tiles;
-    TileInfo nxt = cur;
+    const TileInfo fut = (next_tile + (int)gridDim.x < p.n_tiles) ? tile_info(next_tile + gridDim.x) : nxt;
     ManualRange nmr{0, 0, 0};
     float* s_next = smem + ((nbuf == 2 && !b) ? p.off_in2 : p.off_in);
     uint64_t* bar_next = &s_bar[(nbuf == 2) ? (b ^ 1) : 0];
     float mv0 = 0.f, mv1 = 0.f;
     bool deferred = false;
-    if (has_next) nxt = tile_info(next_tile);
     if (has_next && nbuf == 2) {
       // prefetch the next tile into the other buffer; its few manual words ride in registers
       // across phase A (loads issued now, stores after the FFT)
@@ -447,43 +436,61 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
       // stores, linear domain): SA[j] = sum of rising-slope weights * P over interval j,
       // SB[j] = the same for the falling slopes.  mel[m] = SA[m] + SB[m + 1] (phase C).
       {
-        const int fr = lane % FR;
-        const int vw = warp * PARTS + lane / FR;
-        int k = s_vwk[vw];
-        const int k1 = s_vwk[vw + 1];
-        const float* pcol = s_p + fr;
-        float* sa_col = s_sa + fr;
-        float* sb_col = s_sb + fr;
-        float sa = 0.f, sb = 0.f;
-        int jc = (k < k1) ? s_jk[k] : 0;
-        for (; k + 4 <= k1; k += 4) {
-          const float p0 = pcol[(k + 0) * FS], p1 = pcol[(k + 1) * FS];
-          const float p2 = pcol[(k + 2) * FS], p3 = pcol[(k + 3) * FS];
-          const float2 w0 = s_melw[k + 0], w1 = s_melw[k + 1], w2 = s_melw[k + 2], w3 = s_melw[k + 3];
-          const int j1 = s_jk[k + 1], j2 = s_jk[k + 2], j3 = s_jk[k + 3], j4 = s_jk[k + 4];
-          sa = fmaf(w0.x, p0, sa);
-          sb = fmaf(w0.y, p0, sb);
-          if (j1 != jc) { sa_col[jc * FS] = sa; sb_col[jc * FS] = sb; sa = 0.f; sb = 0.f; }
-          sa = fmaf(w1.x, p1, sa);
-          sb = fmaf(w1.y, p1, sb);
-          if (j2 != j1) { sa_col[j1 * FS] = sa; sb_col[j1 * FS] = sb; sa = 0.f; sb = 0.f; }
-          sa = fmaf(w2.x, p2, sa);
-          sb = fmaf(w2.y, p2, sb);
-          if (j3 != j2) { sa_col[j2 * FS] = sa; sb_col[j2 * FS] = sb; sa = 0.f; sb = 0.f; }
-          sa = fmaf(w3.x, p3, sa);
-          sb = fmaf(w3.y, p3, sb);
-          if (j4 != j3) { sa_col[j3 * FS] = sa; sb_col[j3 * FS] = sb; sa = 0.f; sb = 0.f; }
-          jc = j4;
+        const float* __restrict__ sp = s_p;
+        float* __restrict__ sa_out = s_sa;
+        float* __restrict__ sb_out = s_sb;
+        const float4* __restrict__ mw = s_mw4;  // per bin: {rising w, falling w, interval, interval of next bin}
+        if constexpr (PARTS == 1) {
+          // lane = frame, warp = worker: everything but the P value is warp-uniform
+          const int wu = __shfl_sync(0xffffffffu, warp, 0);
+          int k = s_vwk[wu];
+          const int k1 = s_vwk[wu + 1];
+          const float* pp = sp + k * FS + lane;
+          const float4* wp = mw + k;
+          float sa = 0.f, sb = 0.f;
+          for (; k + 4 <= k1; k += 4, pp += 4 * FS, wp += 4) {
+            const float p0 = pp[0], p1 = pp[FS], p2 = pp[2 * FS], p3 = pp[3 * FS];
+            const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+#define EVF_BIN_STEP(W, P)                                                     \
+  sa = fmaf(W.x, P, sa);                                                       \
+  sb = fmaf(W.y, P, sb);                                                       \
+  if (__float_as_int(W.z) != __float_as_int(W.w)) {                            \
+    sa_out[__float_as_int(W.z) * FS + lane] = sa;                              \
+    sb_out[__float_as_int(W.z) * FS + lane] = sb;                              \
+    sa = 0.f;                                                                  \
+    sb = 0.f;                                                                  \
+  }
+            EVF_BIN_STEP(w0, p0)
+            EVF_BIN_STEP(w1, p1)
+            EVF_BIN_STEP(w2, p2)
+            EVF_BIN_STEP(w3, p3)
+          }
+          for (; k < k1; ++k, pp += FS, ++wp) {
+            const float p0 = pp[0];
+            const float4 w0 = wp[0];
+            EVF_BIN_STEP(w0, p0)
+          }
+        } else {
+          // several workers per warp (tiles of 16 or 8 frames): same walk, per-lane bin ranges
+          const int fr = lane % FR;
+          const int vw = warp * PARTS + lane / FR;
+          int k = s_vwk[vw];
+          const int k1 = s_vwk[vw + 1];
+          float sa = 0.f, sb = 0.f;
+          for (; k < k1; ++k) {
+            const float pv = sp[k * FS + fr];
+            const float4 w = mw[k];
+            sa = fmaf(w.x, pv, sa);
+            sb = fmaf(w.y, pv, sb);
+            if (__float_as_int(w.z) != __float_as_int(w.w)) {
+              sa_out[__float_as_int(w.z) * FS + fr] = sa;
+              sb_out[__float_as_int(w.z) * FS + fr] = sb;
+              sa = 0.f;
+              sb = 0.f;
+            }
+          }
         }
-        for (; k < k1; ++k) {
-          const float pv = pcol[k * FS];
-          const float2 w = s_melw[k];
-          const int jn = s_jk[k + 1];
-          sa = fmaf(w.x, pv, sa);
-          sb = fmaf(w.y, pv, sb);
-          if (jn != jc) { sa_col[jc * FS] = sa; sb_col[jc * FS] = sb; sa = 0.f; sb = 0.f; }
-          jc = jn;
-        }
+#undef EVF_BIN_STEP
       }
       __syncthreads();  // (2)
       // ---- phase C: combine, log, coalesced store of the log-mel rows + per-frame energy ---
@@ -493,11 +500,11 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
         if (f < nvalid) {
           float* dst = p.spec_out + (out_frame0 + f) * (long long)p.row_floats;
           float acc = 0.f;
+          const float* sa_f = s_sa + f;
+          const float* sb_f = s_sb + FS + f;
           for (int m = lane; m < p.n_mels; m += 32) {
-            const int ks0 = s_kstart[m], ks1 = s_kstart[m + 1], ks2 = s_kstart[m + 2];
-            float v = 0.f;
-            if (ks1 > ks0) v = s_sa[m * FS + f];            // interval m has bins
-            if (ks2 > ks1) v += s_sb[(m + 1) * FS + f];     // interval m + 1 has bins
+            // rows of intervals without bins are never flushed and stay zero (cleared at start)
+            float v = sa_f[m * FS] + sb_f[m * FS];
             v = compress(v, p.apply_log, p.log_clip);
             dst[m] = v;
             acc = fmaf(v, v, acc);
@@ -513,6 +520,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
       if (nbuf == 1) __syncthreads();  // the restaged manual words must be visible to the next FFT
     }
     cur = nxt;
+    nxt = fut;
   }
 }
 
@@ -594,26 +602,21 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
     c->off_wpost = w;
     if (mode == MODE_HALF) w += up4(2 * 513);
     c->off_melw = w;
-    c->off_kstart = w;
     c->off_vwk = w;
-    c->off_jk = w;
     c->off_p = w;
     c->off_sa = w;
     c->off_sb = w;
     if (mel) {
-      w += up4(2 * k_used);
-      c->off_kstart = w;
-      w += up4(n_mels + 2);
+      w += 4 * k_used;
       c->off_vwk = w;
       w += up4(warps * parts + 1);
-      c->off_jk = w;
-      w += up4(k_used + 1);
       c->off_p = w;
       w += up4(k_used * (fr + 1));
       c->off_sa = w;
-      w += up4((n_mels + 1) * (fr + 1));
-      c->off_sb = w;
-      w += up4((n_mels + 1) * (fr + 1));
+      w += (n_mels + 1) * (fr + 1);
+      c->off_sb = w;  // directly after SA (cleared together)
+      w += (n_mels + 1) * (fr + 1);
+      w = up4(w);
     }
     c->off_scr = w;
     w += warps * 32 * kScrStride;

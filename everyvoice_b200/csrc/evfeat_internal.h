@@ -19,12 +19,22 @@ enum FftMode : int {
   MODE_HALF = 1,   // n_fft == 2048: one real frame as a 1024-point complex FFT + split
 };
 
+// One frame tile of one utterance; built on the host by evf_batch_create so that the kernel
+// needs no dependent loads (tile -> utterance -> offsets) to start staging a tile.
+struct alignas(16) TileDesc {
+  long long s_off;       // first sample of the utterance in the packed sample buffer
+  long long out_frame0;  // first output frame of the tile in the packed output
+  int L;                 // samples in the utterance
+  int start;             // utterance-relative sample index of tile word 0 (may be negative)
+  int nvalid;            // frames of the tile that exist
+  int span;              // words of the input tile that are consumed
+};
+static_assert(sizeof(TileDesc) == 32, "TileDesc is loaded as two 16-byte words");
+
 // Kernel parameters (passed by value; lives in the constant bank).
 struct FeatParams {
   const void* samples;
-  const long long* sample_off;  // [B+1]
-  const long long* frame_off;   // [B+1]
-  const int2* tiles;            // (utterance, first frame)
+  const TileDesc* tiles;
   int n_tiles;
   float* spec_out;
   float* energy_out;
@@ -32,10 +42,8 @@ struct FeatParams {
   const float* window;   // [n_fft], pre-scaled by 0.5
   const float2* tw;      // [32][32] inter-pass twiddles, indexed [register position][lane]
   const float2* wpost;   // MODE_HALF: exp(-2 pi i k / n_fft), k = 0..512
-  const float2* melw;    // [k_used] (rising weight -> mel j(k), falling weight -> mel j(k)-1)
-  const int* kstart;     // [n_mels + 2] first bin of every inter-centre interval
+  const float4* melw4;   // [k_used] {rising weight -> mel j(k), falling weight -> mel j(k)-1, j(k), j(k+1)} (ints as bits)
   const int* vw_k;       // [n_vw + 1] bin range of every worker of the projection phase (interval aligned)
-  const int* jk;         // [k_used + 1] interval index of every bin (+ sentinel)
   int hop;
   int n_mels;
   int n_freq;
@@ -44,8 +52,7 @@ struct FeatParams {
   int apply_log;
   float log_clip;
   // shared-memory carve-up, in 4-byte words from the start of dynamic shared memory
-  int off_bar, off_in, off_in2, off_win, off_tw, off_wpost, off_melw, off_kstart, off_vwk, off_jk, off_p,
-      off_sa, off_sb, off_scr;
+  int off_bar, off_in, off_in2, off_win, off_tw, off_wpost, off_melw, off_vwk, off_p, off_sa, off_sb, off_scr;
   int nbuf;              // input tile buffers: 2 = bulk-copy prefetch of the next tile, 1 = restage in place
   int in_words;          // capacity of the input tile
 };
@@ -55,6 +62,7 @@ struct PlanTables {
   std::vector<float2> tw;         // 1024
   std::vector<float2> wpost;      // 513 (MODE_HALF) or empty
   std::vector<float2> melw;       // k_used
+  std::vector<float4> melw4;      // k_used
   std::vector<int> kstart;        // n_mels + 2
   std::vector<int> vw_k;          // n_vw + 1
   std::vector<int> jk;            // k_used + 1
