@@ -70,7 +70,8 @@ def librosa_mel_basis(sr: int, n_fft: int, n_mels: int, fmin: float, fmax: float
     log_t = mels >= min_log_mel
     mel_f[log_t] = min_log_hz * np.exp(logstep * (mels[log_t] - min_log_mel))
 
-    fftfreqs = np.fft.rfftfreq(n=n_fft, d=1.0 / sr)
+    # == numpy's rfftfreq(n_fft, 1 / sr), operation for operation (a frequency grid, not a transform)
+    fftfreqs = np.arange(0, n_fft // 2 + 1, dtype=int) * (1.0 / (n_fft * (1.0 / sr)))
     fdiff = np.diff(mel_f)
     ramps = np.subtract.outer(mel_f, fftfreqs)
     lower = -ramps[:-2] / fdiff[:-1, None]
