@@ -7,6 +7,8 @@ hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
 ix = {h: i for i, h in enumerate(hdr)}
 data = rows[hdr_i + 1:]
+end = next((i for i, r in enumerate(data) if not r or r[0] == "Kernel Name"), len(data))  # first launch only
+data = data[:end]
 tot_inst = sum(int(r[ix["Instructions Executed"]]) for r in data)
 tot_samp = sum(int(r[ix["# Samples"]]) for r in data)
 print(f"SASS instructions: {len(data)}, executed warp-instr: {tot_inst}, samples: {tot_samp}")
