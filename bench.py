@@ -6,7 +6,7 @@ audio-seconds per second, log-mel + energy + phone-level averaging, at N B200s).
 
 One "step" = one pass of the hot path over one batch of synthetic utterances per rank:
 fused log-spectrogram + energy kernel -> phone-level averaging of energy by durations ->
-{count,sum,sumsq,min,max} reduction -> (N>1: NCCL all-reduce of those five numbers) ->
+{count,sum,sumsq,min,max} reduction -> (N>1: one NCCL all-gather of those five numbers) ->
 in-place normalisation.  Ranks hold independent shards (weak scaling); `value` is the
 whole-job audio-seconds processed per second, timed on the device, max over ranks.
 
@@ -329,9 +329,12 @@ def run_ours(args, w, wname):
     spec = torch.empty((total_frames, batch.plan.row_floats), dtype=torch.float32, device=device)
     energy = torch.empty(total_frames, dtype=torch.float32, device=device)
     scaler = ev.Scaler(device)
+    from everyvoice_b200.distributed import allgather_stats
+    gathered = torch.empty((world, 5), dtype=torch.float64, device=device) if world > 1 else None
     stream = torch.cuda.current_stream(device)
     launches = 0
     feat_events = []
+    dbg_events = []
 
     def step(timed: bool):
         nonlocal launches
@@ -346,10 +349,16 @@ def run_ours(args, w, wname):
         scaler.clear_data()
         scaler.append(phone)
         stats5 = scaler.partial_stats()                                                # 2 (init + reduce)
+        if timed and args.debug_timing:
+            e2 = torch.cuda.Event(enable_timing=True); e2.record(stream)
         if world > 1:
-            from everyvoice_b200.distributed import allreduce_stats
-            stats5, _ = allreduce_stats(stats5, len(lengths))
-        scaler.normalize_by_device_stats_(phone, stats5)                               # 1 (mean/std derived on device)
+            stats5 = allgather_stats(stats5, out=gathered)                             # ONE NCCL collective, no host sync
+        if timed and args.debug_timing:
+            e3 = torch.cuda.Event(enable_timing=True); e3.record(stream)
+        scaler.normalize_by_device_stats_(phone, stats5)                               # 1 (ranks merged + mean/std on device)
+        if timed and args.debug_timing:
+            e4 = torch.cuda.Event(enable_timing=True); e4.record(stream)
+            dbg_events.append((e0, e1, e2, e3, e4))
         launches += 5
         return phone
 
@@ -362,10 +371,14 @@ def run_ours(args, w, wname):
     for _ in range(args.warmup):
         step(False)
     launches = 0
-    sync_all()
+    # NVML init takes tens of ms: start the sampler BEFORE the barrier, or rank 0 enters the timed
+    # region late and every other rank waits for it in the first exchange
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    sync_all()
+    if rank == 0:
+        clocks.samples.clear()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record(stream)
     for _ in range(args.steps):
@@ -375,6 +388,12 @@ def run_ours(args, w, wname):
     clock_info = clocks.stop() if rank == 0 else None
     elapsed_ms = t_start.elapsed_time(t_end)
     feat_ms = float(np.mean([a.elapsed_time(b) for a, b in feat_events]))
+    if args.debug_timing:
+        seg = np.array([[ev[i].elapsed_time(ev[i + 1]) for i in range(4)] for ev in dbg_events])
+        gaps = np.array([dbg_events[i][4].elapsed_time(dbg_events[i + 1][0]) for i in range(len(dbg_events) - 1)])
+        print(f"[rank {rank}] ms: features {seg[:, 0].mean():.3f} segmean+stats {seg[:, 1].mean():.3f} "
+              f"exchange {seg[:, 2].mean():.3f} normalise {seg[:, 3].mean():.3f} inter-step gap {gaps.mean():.3f} "
+              f"total {elapsed_ms / args.steps:.3f}", file=sys.stderr)
     if world > 1:
         t = torch.tensor([elapsed_ms, feat_ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -443,9 +462,9 @@ def run_ours(args, w, wname):
                 "workload": wname, "spec_type": spec_type, "sample_rate": sr, "n_fft": n_fft, "win": win, "hop": hop,
                 "n_mels": n_mels, "utterances_per_gpu": int(len(lengths)), "audio_s_per_gpu": audio_s_rank,
                 "frames_per_gpu": int(total_frames), "sample_dtype": "f32",
-                "step": "features(log-spec+energy) -> phone averaging -> stats -> allreduce(N>1) -> normalise",
+                "step": "features(log-spec+energy) -> phone averaging -> stats -> all-gather of the 5-number summaries (N>1) -> normalise",
                 "l2_policy": f"inputs larger than L2 ({total_samples * 4 / 1e6:.0f} MB read + {spec.numel() * 4 / 1e6:.0f} MB written per step)",
-                "parallelism": f"utterance shards x{world}, stats all-reduce only",
+                "parallelism": f"utterance shards x{world}, stats all-gather only",
             },
             "realtime_factor_per_gpu": value / world,
             "roofline": {
@@ -475,6 +494,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=list(WORKLOADS), default=DEFAULT_WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--debug-timing", action="store_true", help="per-segment CUDA-event breakdown on stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]

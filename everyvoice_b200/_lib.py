@@ -7,10 +7,12 @@ everything here raises.  The library is built in-tree by ``everyvoice_b200.build
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libevfeat.so"
+# EVF_LIB selects an experimental build of the same library (kernel A/B runs); never a fallback
+LIB_PATH = Path(os.environ.get("EVF_LIB") or Path(__file__).resolve().parent / "libevfeat.so")
 
 # evf_status
 EVF_OK = 0
@@ -26,7 +28,7 @@ EVF_ERR_OUT_OF_MEMORY = 7
 SPEC_TYPES = {"mel": 0, "mel-librosa": 1, "linear": 2, "raw": 3}
 SAMPLES_F32, SAMPLES_S16 = 0, 1
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class evf_config(C.Structure):
@@ -67,6 +69,8 @@ PROTOTYPES = {
     "evf_stats_partial": (C.c_int, [_P, C.c_int64, _P, C.c_int32, _P]),
     "evf_normalize_inplace": (C.c_int, [_P, C.c_int64, C.c_float, C.c_float, _P]),
     "evf_normalize_by_stats": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "evf_stats_merge": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
+    "evf_normalize_by_gathered_stats": (C.c_int, [_P, C.c_int64, _P, C.c_int32, C.c_int32, _P]),
 }
 
 

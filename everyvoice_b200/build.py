@@ -39,17 +39,22 @@ def is_stale() -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, defines: list[str] | None = None, out: Path | None = None) -> Path:
+    """``defines`` / ``out`` build an experimental variant next to the product library
+    (kernel A/B runs: ``EVF_LIB=<path>`` makes ``_lib.load`` pick it up)."""
+    global LIB
+    if out is None and not force and not is_stale():
         return LIB
     nvcc = find_nvcc()
     objs = []
-    build_dir = PKG / "build"
+    build_dir = PKG / ("build" if out is None else "build_" + Path(out).stem)
     build_dir.mkdir(exist_ok=True)
+    lib_out = LIB if out is None else Path(out)
+    extra = [f"-D{d}" for d in (defines or [])]
     procs = []
     for s in SOURCES:
         obj = build_dir / (Path(s).stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(ROOT / "include"), "-I", str(CSRC), "-c", str(CSRC / s), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", str(ROOT / "include"), "-I", str(CSRC), "-c", str(CSRC / s), "-o", str(obj)]
         procs.append((s, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(str(obj))
     log = []
@@ -60,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {s}")
     cmd = [nvcc, "-shared", "--cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-o", str(LIB), *objs]
+           "-o", str(lib_out), *objs]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log.append(f"$ {' '.join(cmd)}\n{r.stdout}")
     (build_dir / "build.log").write_text("\n".join(log))
@@ -69,9 +74,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("link of libevfeat.so failed")
     if verbose:
         print("\n".join(log))
-    return LIB
+    return lib_out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv or True, verbose=True)
-    print(f"built {LIB} ({os.path.getsize(LIB)} bytes)")
+    # python -m everyvoice_b200.build [-DNAME[=V] ...] [-o path/to/libvariant.so]
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outp = Path(sys.argv[sys.argv.index("-o") + 1]).resolve() if "-o" in sys.argv else None
+    lib = build(force=True, verbose="-q" not in sys.argv, defines=defs, out=outp)
+    print(f"built {lib} ({os.path.getsize(lib)} bytes)")

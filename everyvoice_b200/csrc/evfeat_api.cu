@@ -22,7 +22,7 @@ struct evf_plan {
   evf::FeatParams carve{};
   // device tables
   float* d_window = nullptr;
-  float2* d_tw = nullptr;
+  float4* d_tw4 = nullptr;
   float2* d_wpost = nullptr;
   float4* d_melw4 = nullptr;
   int* d_vwk = nullptr;
@@ -171,7 +171,7 @@ int compress_filterbank(const float* fb, int n_freq, int n_mels, int n_vw, PlanT
 
 void free_plan_tables(evf_plan* p) {
   cudaFree(p->d_window);
-  cudaFree(p->d_tw);
+  cudaFree(p->d_tw4);
   cudaFree(p->d_wpost);
   cudaFree(p->d_melw4);
   cudaFree(p->d_vwk);
@@ -253,14 +253,28 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
 
   PlanTables t;
   t.window.resize(cfg->n_fft);
-  for (int i = 0; i < cfg->n_fft; ++i) t.window[i] = 0.5f * window_host[i];  // exact scaling
-  t.tw.resize(kFftSize);
+  if (p->mode == MODE_PACK2) {
+    // pair layout for LDS.64: [q][lane] = {w[32 * 2q + lane], w[32 * (2q + 1) + lane]}; 0.5 is exact
+    for (int q = 0; q < 16; ++q)
+      for (int lane = 0; lane < 32; ++lane) {
+        t.window[(q * 32 + lane) * 2 + 0] = 0.5f * window_host[32 * (2 * q) + lane];
+        t.window[(q * 32 + lane) * 2 + 1] = 0.5f * window_host[32 * (2 * q + 1) + lane];
+      }
+  } else {
+    for (int i = 0; i < cfg->n_fft; ++i) t.window[i] = 0.5f * window_host[i];  // exact scaling
+  }
+  t.tw4.resize(kFftSize / 2);
   const double two_pi = 6.283185307179586476925286766559;
-  for (int pos = 0; pos < 32; ++pos) {
-    const int k1 = bitrev5(pos);
+  for (int q = 0; q < 16; ++q) {
     for (int lane = 0; lane < 32; ++lane) {
-      const double ang = -two_pi * (double)((lane * k1) % kFftSize) / (double)kFftSize;
-      t.tw[pos * 32 + lane] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+      float c[2], sn[2];
+      for (int h = 0; h < 2; ++h) {
+        const int k1 = bitrev5(2 * q + h);
+        const double ang = -two_pi * (double)((lane * k1) % kFftSize) / (double)kFftSize;
+        c[h] = (float)std::cos(ang);
+        sn[h] = (float)std::sin(ang);
+      }
+      t.tw4[q * 32 + lane] = make_float4(c[0], sn[0], c[1], sn[1]);
     }
   }
   if (p->mode == MODE_HALF) {
@@ -279,6 +293,17 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   }
   p->smem_bytes = features_smem_bytes(p->mode, cfg->spec_type, p->warps, cfg->hop_length, cfg->n_fft,
                                       cfg->n_mels, p->k_used, &p->carve);
+  if (p->mode == MODE_HALF && (p->smem_bytes < 0 || p->carve.nbuf < 2)) {
+    // no room to stage the post-twiddles next to two input buffers: read them through L1 instead
+    evf::FeatParams alt{};
+    const int b = features_smem_bytes(MODE_HALF_L1, cfg->spec_type, p->warps, cfg->hop_length, cfg->n_fft,
+                                      cfg->n_mels, p->k_used, &alt);
+    if (b >= 0 && (p->smem_bytes < 0 || alt.nbuf > p->carve.nbuf)) {
+      p->mode = MODE_HALF_L1;
+      p->smem_bytes = b;
+      p->carve = alt;
+    }
+  }
   if (p->smem_bytes < 0 && p->warps == 8) {  // does not fit twice per SM: one 16-warp CTA per SM
     p->warps = 16;
     p->frames_per_tile = p->warps * (p->mode == MODE_PACK2 ? 2 : 1);
@@ -292,7 +317,7 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   }
   rc = features_configure(p->mode, cfg->spec_type, cfg->sample_format, p->warps, p->smem_bytes);
   if (rc == EVF_OK) rc = upload(t.window, &p->d_window);
-  if (rc == EVF_OK) rc = upload(t.tw, &p->d_tw);
+  if (rc == EVF_OK) rc = upload(t.tw4, &p->d_tw4);
   if (rc == EVF_OK) rc = upload(t.wpost, &p->d_wpost);
   if (rc == EVF_OK) rc = upload(t.melw4, &p->d_melw4);
   if (rc == EVF_OK) rc = upload(t.vw_k, &p->d_vwk);
@@ -451,7 +476,7 @@ int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* s
   p.spec_out = spec_out_dev;
   p.energy_out = (plan->cfg.spec_type == EVF_SPEC_RAW) ? nullptr : energy_out_dev;
   p.window = plan->d_window;
-  p.tw = plan->d_tw;
+  p.tw4 = plan->d_tw4;
   p.wpost = plan->d_wpost;
   p.melw4 = plan->d_melw4;
   p.vw_k = plan->d_vwk;
@@ -539,6 +564,25 @@ int evf_normalize_by_stats(float* values_dev, int64_t n, const double* stats5_de
     return EVF_ERR_INVALID_ARGUMENT;
   }
   return launch_normalize_by_stats(values_dev, n, stats5_dev, static_cast<cudaStream_t>(stream));
+}
+
+int evf_stats_merge(const double* parts_dev, int32_t n_parts, int32_t stride_doubles, double* out5_dev,
+                    void* stream) {
+  if (n_parts < 1 || stride_doubles < 5 || !parts_dev || !out5_dev) {
+    set_error("evf_stats_merge: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_stats_merge(parts_dev, n_parts, stride_doubles, out5_dev, static_cast<cudaStream_t>(stream));
+}
+
+int evf_normalize_by_gathered_stats(float* values_dev, int64_t n, const double* parts_dev, int32_t n_parts,
+                                    int32_t stride_doubles, void* stream) {
+  if (n < 0 || n_parts < 1 || stride_doubles < 5 || !parts_dev || (n > 0 && !values_dev)) {
+    set_error("evf_normalize_by_gathered_stats: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_normalize_by_gathered(values_dev, n, parts_dev, n_parts, stride_doubles,
+                                      static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -178,6 +178,46 @@ __global__ void __launch_bounds__(256) normalize_by_stats_kernel(float* __restri
     x[i] = (x[i] - mean) / std;
 }
 
+// Same, from the all-gathered summaries of n_parts ranks (parts[r * stride + 0..4]): every block
+// merges the <= a few dozen numbers itself (SUM of count/sum/sumsq; min/max are not needed for
+// the normalisation), so the all-gather's output feeds the normalisation with no kernel between.
+__global__ void __launch_bounds__(256) normalize_by_gathered_kernel(float* __restrict__ x, long long n,
+                                                                    const double* __restrict__ parts,
+                                                                    int n_parts, int stride) {
+  double cnt = 0.0, sum = 0.0, sq = 0.0;
+  for (int r = 0; r < n_parts; ++r) {  // fixed order: every rank derives bit-identical mean / std
+    cnt += parts[(long long)r * stride + 0];
+    sum += parts[(long long)r * stride + 1];
+    sq += parts[(long long)r * stride + 2];
+  }
+  const double mean_d = sum / cnt;
+  const double var_d = (sq - sum * sum / cnt) / (cnt - 1.0);
+  const float mean = (float)mean_d;
+  const float std = (float)sqrt(var_d > 0.0 ? var_d : 0.0);
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
+    x[i] = (x[i] - mean) / std;
+}
+
+// out5 = merge of n_parts five-number summaries (what an all-reduce with SUM/SUM/SUM/MIN/MAX gives).
+__global__ void stats_merge_kernel(const double* __restrict__ parts, int n_parts, int stride,
+                                   double* __restrict__ out5) {
+  double cnt = 0.0, sum = 0.0, sq = 0.0, mn = CUDART_INF, mx = -CUDART_INF;
+  for (int r = 0; r < n_parts; ++r) {
+    const double* p = parts + (long long)r * stride;
+    cnt += p[0];
+    sum += p[1];
+    sq += p[2];
+    mn = fmin(mn, p[3]);
+    mx = fmax(mx, p[4]);
+  }
+  out5[0] = cnt;
+  out5[1] = sum;
+  out5[2] = sq;
+  out5[3] = mn;
+  out5[4] = mx;
+}
+
 __global__ void __launch_bounds__(256) log_compress_kernel(const float* __restrict__ in,
                                                            float* __restrict__ out, long long n,
                                                            float c, float clip) {
@@ -250,6 +290,20 @@ int launch_stats_partial(const float* values, int64_t n, double* out5, int accum
 int launch_normalize_by_stats(float* values, int64_t n, const double* stats5, cudaStream_t s) {
   if (n == 0) return EVF_OK;
   normalize_by_stats_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, s>>>(values, n, stats5);
+  EVF_CUDA(cudaGetLastError());
+  return EVF_OK;
+}
+
+int launch_normalize_by_gathered(float* values, int64_t n, const double* parts, int n_parts, int stride,
+                                 cudaStream_t s) {
+  if (n == 0) return EVF_OK;
+  normalize_by_gathered_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, s>>>(values, n, parts, n_parts, stride);
+  EVF_CUDA(cudaGetLastError());
+  return EVF_OK;
+}
+
+int launch_stats_merge(const double* parts, int n_parts, int stride, double* out5, cudaStream_t s) {
+  stats_merge_kernel<<<1, 1, 0, s>>>(parts, n_parts, stride, out5);
   EVF_CUDA(cudaGetLastError());
   return EVF_OK;
 }

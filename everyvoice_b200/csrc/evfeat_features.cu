@@ -43,6 +43,8 @@ struct ModeTraits<MODE_HALF> {
   static constexpr int kNfft = 2048;
   static constexpr int kFramesPerJob = 1;
 };
+template <>
+struct ModeTraits<MODE_HALF_L1> : ModeTraits<MODE_HALF> {};
 
 __device__ __forceinline__ float load_sample(const float* p, long long i) { return __ldg(p + i); }
 __device__ __forceinline__ float load_sample(const short* p, long long i) {
@@ -60,37 +62,65 @@ __device__ __forceinline__ float compress(float v, int apply_log, float clip) {
 // 1024-point complex FFT of the 32x32 values held by one warp.
 // In : lane n2 holds z[32*n1 + n2] at index n1.
 // Out: lane k1 holds Z[k1 + 32*k2] at index bitrev5(k2).
+// Shared-memory instruction diet: the inter-pass twiddles come as 16 LDS.128 (two per load), the
+// transposed reads as 2 x 16 LDS.64 (row stride 34 words keeps them 8-byte aligned and
+// conflict-free: half-warp lanes hit banks 2*lane, 2*lane + 1).
 __device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32],
-                                             const float2* __restrict__ s_tw,
+                                             const float4* __restrict__ s_tw4,
                                              float* __restrict__ scr, int lane) {
 #pragma unroll 1
   for (int pass = 0; pass < 2; ++pass) {
     dft32_dif(re, im);
     if (pass == 0) {
-      // index p now holds k1 = bitrev5(p); multiply by W_1024^(n2*k1) (table is stored
-      // by register position) and hand element k1 to lane k1.
+      {
+        // index p now holds k1 = bitrev5(p); multiply by W_1024^(n2*k1) (table is stored
+        // by register position, two positions per entry) and hand element k1 to lane k1.
 #pragma unroll
-      for (int p = 1; p < 32; ++p) {
-        float2 t = s_tw[p * 32 + lane];
-        float a = fmaf(-im[p], t.y, re[p] * t.x);
-        float b = fmaf(re[p], t.y, im[p] * t.x);
-        re[p] = a;
-        im[p] = b;
+        for (int q = 0; q < 16; ++q) {
+          const float4 t = s_tw4[q * 32 + lane];
+          if (q > 0) {  // position 0 is k1 = 0: twiddle 1
+            const float a = fmaf(-im[2 * q], t.y, re[2 * q] * t.x);
+            const float b = fmaf(re[2 * q], t.y, im[2 * q] * t.x);
+            re[2 * q] = a;
+            im[2 * q] = b;
+          }
+          const float c = fmaf(-im[2 * q + 1], t.w, re[2 * q + 1] * t.z);
+          const float d = fmaf(re[2 * q + 1], t.w, im[2 * q + 1] * t.z);
+          re[2 * q + 1] = c;
+          im[2 * q + 1] = d;
+        }
+        const float2* row = reinterpret_cast<const float2*>(scr + lane * kScrStride);
+#pragma unroll
+        for (int p = 0; p < 32; ++p) scr[bitrev5(p) * kScrStride + lane] = re[p];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const float2 v = row[m];
+          re[2 * m] = v.x;
+          re[2 * m + 1] = v.y;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 32; ++p) scr[bitrev5(p) * kScrStride + lane] = im[p];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const float2 v = row[m];
+          im[2 * m] = v.x;
+          im[2 * m + 1] = v.y;
+        }
+        __syncwarp();
       }
-#pragma unroll
-      for (int p = 0; p < 32; ++p) scr[bitrev5(p) * kScrStride + lane] = re[p];
-      __syncwarp();
-#pragma unroll
-      for (int n = 0; n < 32; ++n) re[n] = scr[lane * kScrStride + n];
-      __syncwarp();
-#pragma unroll
-      for (int p = 0; p < 32; ++p) scr[bitrev5(p) * kScrStride + lane] = im[p];
-      __syncwarp();
-#pragma unroll
-      for (int n = 0; n < 32; ++n) im[n] = scr[lane * kScrStride + n];
-      __syncwarp();
     }
   }
+}
+
+// sqrt for the mel-librosa magnitude: one MUFU (relative error <= 2^-22, far inside the 1e-3
+// log-domain budget) instead of the ~8-instruction correctly rounded sequence.
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
 // ---- mbarrier / bulk-copy (TMA 1-D) primitives ----------------------------------------------
@@ -152,11 +182,13 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
   constexpr int PARTS = 32 / FR;          // projection workers per warp
   constexpr bool kMel = (SPEC == EVF_SPEC_MEL || SPEC == EVF_SPEC_MEL_LIBROSA);
   constexpr bool kBulk = sizeof(SampleT) == 4;  // float samples can be bulk-copied as they are
+  constexpr bool kHalf = (MODE != MODE_PACK2);          // n_fft 2048: one frame per FFT + real-FFT split
+  constexpr bool kStageWpost = (MODE == MODE_HALF);     // MODE_HALF_L1: post-twiddles read through L1
 
   extern __shared__ __align__(16) float smem[];
   float* s_win = smem + p.off_win;
-  float2* s_tw = reinterpret_cast<float2*>(smem + p.off_tw);
-  float2* s_wpost = reinterpret_cast<float2*>(smem + p.off_wpost);
+  float4* s_tw4 = reinterpret_cast<float4*>(smem + p.off_tw);
+  const float2* s_wpost = reinterpret_cast<const float2*>(smem + p.off_wpost);
   float4* s_mw4 = reinterpret_cast<float4*>(smem + p.off_melw);
   int* s_vwk = reinterpret_cast<int*>(smem + p.off_vwk);
   float* s_p = smem + p.off_p;
@@ -177,9 +209,9 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
     fence_mbar_init();
   }
   for (int i = tid; i < NFFT; i += kThreads) s_win[i] = p.window[i];
-  for (int i = tid; i < kFftSize; i += kThreads) s_tw[i] = p.tw[i];
-  if constexpr (MODE == MODE_HALF) {
-    for (int i = tid; i <= 512; i += kThreads) s_wpost[i] = p.wpost[i];
+  for (int i = tid; i < kFftSize / 2; i += kThreads) s_tw4[i] = p.tw4[i];
+  if constexpr (kStageWpost) {
+    for (int i = tid; i <= 512; i += kThreads) reinterpret_cast<float2*>(smem + p.off_wpost)[i] = p.wpost[i];
   }
   if constexpr (kMel) {
     for (int i = tid; i < p.k_used; i += kThreads) s_mw4[i] = p.melw4[i];
@@ -279,14 +311,33 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
     if (warp * FPJ < nvalid) {
       float re[32], im[32];
       if constexpr (MODE == MODE_PACK2) {
+        // window pairs: s_win holds {w[32*(2q) + lane], w[32*(2q+1) + lane]} at [q][lane] (16 LDS.64)
         const float* xa = s_in + (2 * warp) * hop + lane;
-        const float* xb = xa + hop;
-        const float* wv = s_win + lane;
+        const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
+        if (hop == 256) {
+          // the two frames of the job overlap by 768 samples: sample rows 8..31 of frame a ARE rows
+          // 0..23 of frame b, so 40 row loads feed both frames (instead of 64)
+          float v[40];
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-          float w = wv[32 * n1];
-          re[n1] = w * xa[32 * n1];
-          im[n1] = w * xb[32 * n1];
+          for (int r = 0; r < 40; ++r) v[r] = xa[32 * r];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float2 w = wv[32 * q];
+            re[2 * q] = w.x * v[2 * q];
+            im[2 * q] = w.x * v[2 * q + 8];
+            re[2 * q + 1] = w.y * v[2 * q + 1];
+            im[2 * q + 1] = w.y * v[2 * q + 9];
+          }
+        } else {
+          const float* xb = xa + hop;
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float2 w = wv[32 * q];
+            re[2 * q] = w.x * xa[32 * (2 * q)];
+            im[2 * q] = w.x * xb[32 * (2 * q)];
+            re[2 * q + 1] = w.y * xa[32 * (2 * q + 1)];
+            im[2 * q + 1] = w.y * xb[32 * (2 * q + 1)];
+          }
         }
       } else {
         const float2* x2 = reinterpret_cast<const float2*>(s_in + warp * hop) + lane;
@@ -299,7 +350,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
           im[n1] = w.y * x.y;
         }
       }
-      warp_fft1024(re, im, s_tw, scr, lane);
+      warp_fft1024(re, im, s_tw4, scr, lane);
 
       // ---- real-FFT separation; the mirrored bin lives in lane (32 - lane) % 32 -------
       const int src_lane = (32 - lane) & 31;
@@ -315,7 +366,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
         const int k = lane + 32 * j;
         // warp-uniform: does any lane of this row own a bin that is consumed?
         bool need = 32 * j < kcap;
-        if constexpr (MODE == MODE_HALF) need = need || (1024 - 32 * j - 31 < kcap);
+        if constexpr (kHalf) need = need || (1024 - 32 * j - 31 < kcap);
         if (need) {
           float zr, zi, pr, pi;
           if (j < 16) {
@@ -342,8 +393,8 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
                 float pa = fmaf(ar, ar, ai * ai);
                 float pb = fmaf(br, br, bi * bi);
                 if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
-                  pa = sqrtf(pa + 1e-9f);
-                  pb = sqrtf(pb + 1e-9f);
+                  pa = fast_sqrt(pa + 1e-9f);
+                  pb = fast_sqrt(pb + 1e-9f);
                 }
                 if constexpr (kMel) {
                   if (k < kcap) {
@@ -365,7 +416,8 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
               // X[k] = E - T, X[M-k] = conj(E + T), E = Z[k] + conj(Z[M-k]), T = i * w_k * (Z[k] - conj(Z[M-k]))
               const float er = zr + pr, ei = zi - pi;
               const float orr = zr - pr, oi = zi + pi;
-              const float2 w = s_wpost[k];  // (cos, -sin)(2 pi k / 2048)
+              // (cos, -sin)(2 pi k / 2048): from shared memory, or through L1 when the plan has no room to stage it
+              const float2 w = kStageWpost ? s_wpost[k] : __ldg(p.wpost + k);
               const float tr = -fmaf(w.x, oi, w.y * orr);
               const float ti = fmaf(w.x, orr, -w.y * oi);
               const float x0r = er - tr, x0i = ei - ti;      // bin k
@@ -380,8 +432,8 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
                 float p0 = fmaf(x0r, x0r, x0i * x0i);
                 float p1 = fmaf(x1r, x1r, x1i * x1i);
                 if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
-                  p0 = sqrtf(p0 + 1e-9f);
-                  p1 = sqrtf(p1 + 1e-9f);
+                  p0 = fast_sqrt(p0 + 1e-9f);
+                  p1 = fast_sqrt(p1 + 1e-9f);
                 }
                 if constexpr (kMel) {
                   if (k < kcap) s_p[k * FS + fa] = p0;
@@ -564,6 +616,7 @@ int dispatch(int mode, int spec, int fmt, int warps, const FeatParams& p, int gr
              bool cfg) {
   if (mode == MODE_PACK2) return launch_m<MODE_PACK2>(spec, fmt, warps, p, grid, smem, st, cfg);
   if (mode == MODE_HALF) return launch_m<MODE_HALF>(spec, fmt, warps, p, grid, smem, st, cfg);
+  if (mode == MODE_HALF_L1) return launch_m<MODE_HALF_L1>(spec, fmt, warps, p, grid, smem, st, cfg);
   set_error("unknown FFT mode");
   return EVF_ERR_UNSUPPORTED;
 }
@@ -581,7 +634,9 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
   const long long limit = (warps == 16) ? 227 * 1024 : 113 * 1024;
   auto up4 = [](int w) { return (w + 3) & ~3; };
   // Prefer two input buffers (the next tile's bulk copy overlaps this tile's FFTs); fall back
-  // to one when the plan's tables do not leave room for it.
+  // to one when the plan's tables do not leave room for it.  (The caller retries with
+  // MODE_HALF_L1 -- post-twiddles read through L1 instead of staged -- when MODE_HALF cannot fit.)
+  const int stage_wpost = (mode == MODE_HALF) ? 1 : 0;
   for (int nbuf = 2; nbuf >= 1; --nbuf) {
     int w = 0;
     c->nbuf = nbuf;
@@ -600,7 +655,7 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
     c->off_tw = w;
     w += 2 * kFftSize;
     c->off_wpost = w;
-    if (mode == MODE_HALF) w += up4(2 * 513);
+    if (stage_wpost) w += up4(2 * 513);
     c->off_melw = w;
     c->off_vwk = w;
     c->off_p = w;

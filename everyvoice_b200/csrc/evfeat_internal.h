@@ -12,11 +12,12 @@ namespace evf {
 
 constexpr int kMaxWarps = 16;        // warps per CTA (16 x 1 CTA/SM or 8 x 2 CTAs/SM); one FFT job per warp per tile
 constexpr int kFftSize = 1024;       // complex points per warp-level FFT
-constexpr int kScrStride = 33;       // padded row stride of the per-warp transpose scratch
+constexpr int kScrStride = 34;       // padded row stride of the per-warp transpose scratch (even: LDS.64 rows)
 
 enum FftMode : int {
   MODE_PACK2 = 0,  // n_fft == 1024: two real frames packed as re/im of one complex FFT
   MODE_HALF = 1,   // n_fft == 2048: one real frame as a 1024-point complex FFT + split
+  MODE_HALF_L1 = 2,  // same, post-twiddle table read through L1 (plans whose tables fill shared memory)
 };
 
 // One frame tile of one utterance; built on the host by evf_batch_create so that the kernel
@@ -39,8 +40,8 @@ struct FeatParams {
   float* spec_out;
   float* energy_out;
   // plan tables (global memory; copied to shared memory once per CTA)
-  const float* window;   // [n_fft], pre-scaled by 0.5
-  const float2* tw;      // [32][32] inter-pass twiddles, indexed [register position][lane]
+  const float* window;   // [n_fft], pre-scaled by 0.5; n_fft 1024: stored as pairs {w[64q + lane], w[64q + 32 + lane]} at [q][lane]
+  const float4* tw4;     // [16][32] inter-pass twiddles {t[2q][lane], t[2q+1][lane]}, t indexed by register position
   const float2* wpost;   // MODE_HALF: exp(-2 pi i k / n_fft), k = 0..512
   const float4* melw4;   // [k_used] {rising weight -> mel j(k), falling weight -> mel j(k)-1, j(k), j(k+1)} (ints as bits)
   const int* vw_k;       // [n_vw + 1] bin range of every worker of the projection phase (interval aligned)
@@ -59,7 +60,7 @@ struct FeatParams {
 
 struct PlanTables {
   std::vector<float> window;      // n_fft, pre-scaled
-  std::vector<float2> tw;         // 1024
+  std::vector<float4> tw4;        // 512
   std::vector<float2> wpost;      // 513 (MODE_HALF) or empty
   std::vector<float2> melw;       // k_used
   std::vector<float4> melw4;      // k_used
@@ -91,6 +92,9 @@ int launch_segment_mean(const float* values, const int64_t* value_off, const int
 int launch_stats_partial(const float* values, int64_t n, double* out5, int accumulate, cudaStream_t s);
 int launch_normalize(float* values, int64_t n, float mean, float std, cudaStream_t s);
 int launch_normalize_by_stats(float* values, int64_t n, const double* stats5, cudaStream_t s);
+int launch_normalize_by_gathered(float* values, int64_t n, const double* parts, int n_parts, int stride,
+                                 cudaStream_t s);
+int launch_stats_merge(const double* parts, int n_parts, int stride, double* out5, cudaStream_t s);
 int launch_log_compress(const float* in, float* out, int64_t n, float c, float clip, cudaStream_t s);
 
 }  // namespace evf

@@ -2,8 +2,9 @@
 
 The corpus is sharded by utterance, one process per GPU; nothing crosses GPUs except the
 five-number summaries ``{count, sum, sumsq, min, max}`` (float64) per feature, which are
-all-reduced (NCCL over NVLink / NVSwitch on the GPU box, gloo in the CPU tests) and then
-turned into the reference's ``Scaler`` statistics (preprocessor/helpers.py:86-106).
+all-gathered in ONE collective (NCCL over NVLink / NVSwitch on the GPU box, gloo in the CPU
+tests; 40 bytes per rank) and merged where they are needed: on the device by the normalisation
+kernel, on the host for the reference's ``Scaler`` statistics (preprocessor/helpers.py:86-106).
 """
 
 from __future__ import annotations
@@ -32,22 +33,41 @@ def shard_utterances(lengths, world_size: int) -> list[list[int]]:
     return shards
 
 
+def allgather_stats(stats5: torch.Tensor, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """ONE collective for the exchange step: all-gather every rank's five-number summary
+    ``{count, sum, sumsq, min, max}`` (float64) into ``[world, 5]``.  Asynchronous on the current
+    stream for NCCL (no host synchronisation); ``evf_normalize_by_gathered_stats`` /
+    ``evf_stats_merge`` consume the result directly on the device.  Without a process group the
+    result is ``stats5[None]``."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return stats5.reshape(1, -1)
+    world = dist.get_world_size(group)
+    src = stats5.detach().reshape(-1)[:5].contiguous()
+    if dist.get_backend(group) == "gloo" and src.is_cuda:
+        src = src.cpu()
+    if out is None or out.numel() != world * 5 or out.device != src.device or not out.is_contiguous():
+        out = torch.empty((world, 5), dtype=torch.float64, device=src.device)
+    dist.all_gather_into_tensor(out.view(-1), src, group=group)  # flat output: accepted by nccl and gloo
+    return out.view(world, 5)
+
+
+def merge_stats(parts: torch.Tensor) -> torch.Tensor:
+    """``[world, 5]`` -> ``[5]`` (SUM, SUM, SUM, MIN, MAX) with torch ops on whatever device the
+    parts live on; the host-side twin of ``evf_stats_merge`` used when the statistics are needed
+    as Python numbers anyway (``Scaler.calculate_stats`` -> stats.json)."""
+    parts = parts.reshape(-1, 5)
+    return torch.cat([parts[:, :3].sum(dim=0), parts[:, 3].min().reshape(1), parts[:, 4].max().reshape(1)])
+
+
 def allreduce_stats(stats5: torch.Tensor, sample_size: int, group=None) -> tuple[torch.Tensor, int]:
-    """All-reduce ``{count, sum, sumsq}`` with SUM and ``{min, max}`` with MIN / MAX, and the
-    number of files with SUM.  ``stats5`` is a float64 tensor of 5 values on the device the
-    process group's backend expects (CUDA for nccl, CPU for gloo)."""
+    """Corpus-wide ``{count, sum, sumsq, min, max}`` and number of files on every rank.  Returns
+    Python-side values (synchronises); the hot loop uses ``allgather_stats`` instead."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return stats5, sample_size
-    backend = dist.get_backend(group)
-    work = stats5.detach().clone()
-    if backend == "gloo" and work.is_cuda:
-        work = work.cpu()
-    sums = torch.cat([work[:3], work.new_tensor([float(sample_size)])])
-    ext = torch.stack([-work[3], work[4]])  # one MAX all-reduce covers min and max
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=group)
-    out = torch.stack([sums[0], sums[1], sums[2], -ext[0], ext[1]]).to(stats5.device)
-    return out, int(round(float(sums[3])))
+    parts = allgather_stats(stats5, group)
+    n = torch.tensor([float(sample_size)], dtype=torch.float64, device=parts.device)
+    dist.all_reduce(n, op=dist.ReduceOp.SUM, group=group)
+    return merge_stats(parts).to(stats5.device), int(round(float(n[0])))
 
 
 def finalize_stats(stats5, sample_size: int) -> dict:

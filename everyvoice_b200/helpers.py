@@ -113,15 +113,20 @@ class Scaler:
         return data
 
     def normalize_by_device_stats_(self, data: torch.Tensor, stats5: torch.Tensor) -> torch.Tensor:
-        """In place, with mean / std derived on the device from the (all-reduced) float64[5]
-        summary: the reduction, the all-reduce and the normalisation stay on the stream."""
+        """In place, with mean / std derived on the device from the float64 summary -- either one
+        ``[5]`` summary or the ``[world, 5]`` output of ``distributed.allgather_stats``: the
+        reduction, the collective and the normalisation stay on the stream."""
         if not (data.is_cuda and data.dtype == torch.float32 and data.is_contiguous()):
             raise ValueError("normalize_by_device_stats_ needs a contiguous float32 CUDA tensor")
-        if not (stats5.is_cuda and stats5.dtype == torch.float64 and stats5.numel() >= 5):
-            raise ValueError("stats5 must be a float64[5] CUDA tensor")
+        if not (stats5.is_cuda and stats5.dtype == torch.float64 and stats5.is_contiguous() and stats5.numel() >= 5):
+            raise ValueError("stats5 must be a contiguous float64 CUDA tensor of [5] or [world, 5]")
         lib = _lib.load()
         with torch.cuda.device(data.device):
-            _lib.check(lib.evf_normalize_by_stats(_ptr(data), data.numel(), _ptr(stats5), _stream_ptr(data.device)))
+            if stats5.dim() == 2:
+                _lib.check(lib.evf_normalize_by_gathered_stats(_ptr(data), data.numel(), _ptr(stats5), stats5.shape[0],
+                                                               stats5.shape[1], _stream_ptr(data.device)))
+            else:
+                _lib.check(lib.evf_normalize_by_stats(_ptr(data), data.numel(), _ptr(stats5), _stream_ptr(data.device)))
         return data
 
     def denormalize(self, data):

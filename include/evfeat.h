@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define EVF_ABI_VERSION 1
+#define EVF_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define EVF_API __attribute__((visibility("default")))
@@ -162,6 +162,17 @@ EVF_API int evf_normalize_inplace(float* values_dev, int64_t n, float mean, floa
  * the (possibly all-reduced) five numbers of evf_stats_partial: no host round trip between
  * the reduction and the normalisation. */
 EVF_API int evf_normalize_by_stats(float* values_dev, int64_t n, const double* stats5_dev, void* stream);
+
+/* The multi-GPU exchange step (replaces gathering every file into one Scaler,
+ * preprocessor/preprocessor.py:378-451): parts_dev holds n_parts five-number summaries, one per
+ * rank, `stride_doubles` apart -- the output of ONE all-gather of evf_stats_partial results.
+ * evf_stats_merge reduces them to one summary (SUM, SUM, SUM, MIN, MAX);
+ * evf_normalize_by_gathered_stats normalises a shard in place straight from the gathered buffer
+ * (ranks are merged in index order, so every rank derives bit-identical mean / std). */
+EVF_API int evf_stats_merge(const double* parts_dev, int32_t n_parts, int32_t stride_doubles, double* out5_dev,
+                    void* stream);
+EVF_API int evf_normalize_by_gathered_stats(float* values_dev, int64_t n, const double* parts_dev, int32_t n_parts,
+                                    int32_t stride_doubles, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,7 +46,8 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from everyvoice_b200.distributed import allreduce_stats, finalize_stats, shard_utterances
+        from everyvoice_b200.distributed import (allgather_stats, allreduce_stats, finalize_stats, merge_stats,
+                                                 shard_utterances)
 
         utts = _corpus()
         mine = shard_utterances([len(u) for u in utts], world)[rank]
@@ -55,6 +56,10 @@ def _worker(rank, world, port, q):
         st = finalize_stats(stats5.tolist(), n_files)
         # a rank whose shard is empty still takes part and gets the same answer
         empty5, n2 = allreduce_stats(_five(local if rank == 0 else np.zeros(0, np.float32)), len(mine) if rank == 0 else 0)
+        # the hot-loop form: ONE all-gather, merged later (on the GPU: evf_normalize_by_gathered_stats)
+        parts = allgather_stats(_five(local))
+        assert tuple(parts.shape) == (world, 5) and torch.equal(parts[rank], _five(local))
+        assert torch.equal(merge_stats(parts), stats5)
         q.put((rank, st, len(mine), empty5.tolist(), n2))
     finally:
         dist.destroy_process_group()
@@ -98,3 +103,9 @@ def test_allreduce_is_identity_without_a_process_group():
     t = torch.tensor([3.0, 6.0, 14.0, 1.0, 3.0], dtype=torch.float64)
     out, n = allreduce_stats(t, 5)
     assert out is t and n == 5
+    from everyvoice_b200.distributed import allgather_stats, merge_stats
+
+    parts = allgather_stats(t)
+    assert tuple(parts.shape) == (1, 5) and torch.equal(merge_stats(parts), t)
+    two = torch.stack([t, torch.tensor([2.0, 10.0, 52.0, 4.0, 6.0], dtype=torch.float64)])
+    assert merge_stats(two).tolist() == [5.0, 16.0, 66.0, 1.0, 6.0]

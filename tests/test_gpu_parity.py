@@ -332,6 +332,46 @@ def test_scaler_matches_oracle_on_device_shard(cuda_device):
     _same_with_nans(xd.cpu(), o.normalize(torch.from_numpy(x)), atol=1e-4)  # normalised in place
 
 
+def test_gathered_stats_merge_and_normalise_on_device(cuda_device):
+    """The N > 1 exchange step as the ranks see it after the all-gather: [world, 5] summaries are
+    merged and applied on the device; result == the reference's Scaler over the whole corpus."""
+    import ctypes as C
+
+    import everyvoice_b200 as ev
+    from everyvoice_b200 import _lib
+    from everyvoice_b200.distributed import finalize_stats, merge_stats
+    from oracle import ev_oracle as O
+
+    rng = np.random.default_rng(21)
+    shards = [rng.normal(25.0, 6.0, size=n).astype(np.float32) for n in (5003, 7001, 1, 2999)]
+    shards[1][10] = np.nan
+    parts = []
+    for sh in shards:
+        s = ev.Scaler(cuda_device)
+        s.append(torch.from_numpy(sh).to(cuda_device))
+        parts.append(s.partial_stats().clone())
+    gathered = torch.stack(parts).contiguous()  # what allgather_stats returns on every rank
+    merged = torch.empty(5, dtype=torch.float64, device=cuda_device)
+    lib = _lib.load()
+    _lib.check(lib.evf_stats_merge(C.c_void_p(gathered.data_ptr()), 4, 5, C.c_void_p(merged.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert torch.allclose(merged.cpu(), merge_stats(gathered).cpu(), rtol=1e-15, atol=0)
+    o = O.Scaler()
+    for sh in shards:
+        o.append(torch.from_numpy(sh))
+    ref = o.calculate_stats()
+    st = finalize_stats(merged.cpu().tolist(), len(shards))
+    assert st["min"] == ref["min"] and st["max"] == ref["max"] and st["sample_size"] == 4
+    for k in ("mean", "std", "norm_min", "norm_max"):
+        assert st[k] == pytest.approx(ref[k], rel=5e-6)
+    mine = torch.from_numpy(shards[0]).to(cuda_device)
+    ev.Scaler(cuda_device).normalize_by_device_stats_(mine, gathered)
+    _same_with_nans(mine.cpu(), o.normalize(torch.from_numpy(shards[0])), atol=1e-5)
+    single = torch.from_numpy(shards[0]).to(cuda_device)
+    ev.Scaler(cuda_device).normalize_by_device_stats_(single, merged)
+    assert torch.equal(single, mine)  # [5] and [world, 5] forms agree bit for bit
+
+
 # ------------------------------------------------------------------------------------------
 # reference test-suite invariants (everyvoice/tests/test_preprocessing.py:385-435, 496-568)
 # ------------------------------------------------------------------------------------------
