@@ -16,10 +16,11 @@ from .heavy import (  # noqa: F401
     get_spectral_transform,
 )
 from .helpers import Scaler  # noqa: F401
+from .pipeline import CorpusPipeline  # noqa: F401
 from .preprocessor import Preprocessor  # noqa: F401
 
 __all__ = [
     "AudioConfig", "AudioSpecTypeEnum", "ConfigError", "RaggedBatch", "RaggedFeatures",
     "SpectralTransform", "dynamic_range_compression_torch", "get_spectral_transform",
-    "Scaler", "Preprocessor",
+    "Scaler", "Preprocessor", "CorpusPipeline",
 ]

@@ -28,7 +28,7 @@ EVF_ERR_OUT_OF_MEMORY = 7
 SPEC_TYPES = {"mel": 0, "mel-librosa": 1, "linear": 2, "raw": 3}
 SAMPLES_F32, SAMPLES_S16 = 0, 1
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class evf_config(C.Structure):
@@ -62,6 +62,7 @@ PROTOTYPES = {
     "evf_batch_frame_offsets": (C.c_int, [_P, _P]),
     "evf_batch_frame_offsets_dev": (C.c_int, [_P, C.POINTER(_P)]),
     "evf_features_run": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "evf_features_run_range": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "evf_features_ragged": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "evf_energy_from_spec": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
     "evf_log_compress": (C.c_int, [_P, _P, C.c_int64, C.c_float, C.c_float, _P]),

@@ -34,6 +34,7 @@ struct evf_batch {
   int n_tiles = 0;
   int64_t total_frames = 0;
   std::vector<int64_t> frame_off;  // host copy
+  std::vector<int> tile_start;     // [n_utts + 1] first tile of every utterance
   long long* d_sample_off = nullptr;
   long long* d_frame_off = nullptr;
   evf::TileDesc* d_tiles = nullptr;
@@ -362,8 +363,10 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
   const int hop = plan->cfg.hop_length, n_fft = plan->cfg.n_fft, fr = plan->frames_per_tile;
   std::vector<long long> s_off(n_utts + 1, 0), f_off(n_utts + 1, 0);
   std::vector<TileDesc> tiles;
+  std::vector<int> tile_start(n_utts + 1, 0);
   const int fpj = (plan->mode == MODE_PACK2) ? 2 : 1;
   for (int b = 0; b < n_utts; ++b) {
+    tile_start[b] = (int)tiles.size();
     const int64_t L = sample_offsets_host[b + 1] - sample_offsets_host[b];
     if (L <= n_fft / 2) {
       char buf[256];
@@ -395,6 +398,7 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
       tiles.push_back(d);
     }
   }
+  tile_start[n_utts] = (int)tiles.size();
   for (int b = 0; b <= n_utts; ++b) s_off[b] = n_utts ? sample_offsets_host[b] : 0;
 
   DeviceGuard guard(plan->device);
@@ -405,13 +409,23 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
   bt->n_tiles = (int)tiles.size();
   bt->total_frames = f_off[n_utts];
   bt->frame_off.assign(f_off.begin(), f_off.end());
-  int rc = upload(s_off, &bt->d_sample_off);
-  if (rc == EVF_OK) rc = upload(f_off, &bt->d_frame_off);
-  if (rc == EVF_OK) rc = upload(tiles, &bt->d_tiles);
+  bt->tile_start.swap(tile_start);
+  // one device block, one copy: [sample offsets | frame offsets | tile descriptors]
+  const size_t off_bytes = (size_t)(n_utts + 1) * sizeof(long long);
+  const size_t tile_bytes = tiles.size() * sizeof(TileDesc);
+  std::vector<unsigned char> blob(2 * off_bytes + tile_bytes);
+  memcpy(blob.data(), s_off.data(), off_bytes);
+  memcpy(blob.data() + off_bytes, f_off.data(), off_bytes);
+  if (tile_bytes) memcpy(blob.data() + 2 * off_bytes, tiles.data(), tile_bytes);
+  unsigned char* d_blob = nullptr;
+  int rc = upload(blob, &d_blob);
   if (rc != EVF_OK) {
     evf_batch_destroy(bt);
     return rc;
   }
+  bt->d_sample_off = reinterpret_cast<long long*>(d_blob);  // owns the block
+  bt->d_frame_off = reinterpret_cast<long long*>(d_blob + off_bytes);
+  bt->d_tiles = reinterpret_cast<evf::TileDesc*>(d_blob + 2 * off_bytes);  // 16 * (n_utts + 1) bytes in: 16-byte aligned
   *batch_out = bt;
   return EVF_OK;
 }
@@ -419,9 +433,7 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
 int evf_batch_destroy(evf_batch* batch) {
   if (!batch) return EVF_OK;
   DeviceGuard guard(batch->device);
-  cudaFree(batch->d_sample_off);
-  cudaFree(batch->d_frame_off);
-  cudaFree(batch->d_tiles);
+  cudaFree(batch->d_sample_off);  // the single block
   delete batch;
   return EVF_OK;
 }
@@ -453,26 +465,14 @@ int evf_batch_frame_offsets_dev(const evf_batch* batch, const int64_t** frame_of
   return EVF_OK;
 }
 
-int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* samples_dev,
-                     float* spec_out_dev, float* energy_out_dev, void* stream) {
-  if (!plan || !batch) {
-    set_error("evf_features_run: null plan or batch");
-    return EVF_ERR_INVALID_ARGUMENT;
-  }
-  if (batch->device != plan->device) {
-    set_error("evf_features_run: plan and batch live on different devices");
-    return EVF_ERR_INVALID_ARGUMENT;
-  }
-  if (batch->n_tiles == 0) return EVF_OK;
-  if (!samples_dev || !spec_out_dev) {
-    set_error("evf_features_run: null sample or output pointer");
-    return EVF_ERR_INVALID_ARGUMENT;
-  }
+static int features_run_tiles(const evf_plan* plan, const evf_batch* batch, int tile_begin, int tile_end,
+                              const void* samples_dev, float* spec_out_dev, float* energy_out_dev, void* stream) {
+  if (tile_end <= tile_begin) return EVF_OK;
   DeviceGuard guard(plan->device);
   FeatParams p = plan->carve;
   p.samples = samples_dev;
-  p.tiles = batch->d_tiles;
-  p.n_tiles = batch->n_tiles;
+  p.tiles = batch->d_tiles + tile_begin;
+  p.n_tiles = tile_end - tile_begin;
   p.spec_out = spec_out_dev;
   p.energy_out = (plan->cfg.spec_type == EVF_SPEC_RAW) ? nullptr : energy_out_dev;
   p.window = plan->d_window;
@@ -488,9 +488,51 @@ int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* s
   p.apply_log = (plan->cfg.spec_type == EVF_SPEC_RAW) ? 0 : plan->cfg.apply_log;
   p.log_clip = plan->cfg.log_clip;
   const int max_ctas = plan->num_sms * (16 / plan->warps);
-  const int grid = batch->n_tiles < max_ctas ? batch->n_tiles : max_ctas;
+  const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
   return features_launch(plan->mode, plan->cfg.spec_type, plan->cfg.sample_format, plan->warps, p, grid,
                          plan->smem_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* samples_dev,
+                     float* spec_out_dev, float* energy_out_dev, void* stream) {
+  if (!plan || !batch) {
+    set_error("evf_features_run: null plan or batch");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (batch->device != plan->device) {
+    set_error("evf_features_run: plan and batch live on different devices");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (batch->n_tiles == 0) return EVF_OK;
+  if (!samples_dev || !spec_out_dev) {
+    set_error("evf_features_run: null sample or output pointer");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  return features_run_tiles(plan, batch, 0, batch->n_tiles, samples_dev, spec_out_dev, energy_out_dev, stream);
+}
+
+int evf_features_run_range(const evf_plan* plan, const evf_batch* batch, int32_t utt_begin, int32_t utt_end,
+                           const void* samples_base_dev, float* spec_base_dev, float* energy_base_dev,
+                           void* stream) {
+  if (!plan || !batch) {
+    set_error("evf_features_run_range: null plan or batch");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (batch->device != plan->device) {
+    set_error("evf_features_run_range: plan and batch live on different devices");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (utt_begin < 0 || utt_end > batch->n_utts || utt_begin > utt_end) {
+    set_error("evf_features_run_range: utterance range outside the batch");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (utt_begin == utt_end) return EVF_OK;
+  if (!samples_base_dev || !spec_base_dev) {
+    set_error("evf_features_run_range: null sample or output pointer");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  return features_run_tiles(plan, batch, batch->tile_start[utt_begin], batch->tile_start[utt_end],
+                            samples_base_dev, spec_base_dev, energy_base_dev, stream);
 }
 
 int evf_features_ragged(const evf_plan* plan, const void* samples_dev,

@@ -1,0 +1,219 @@
+"""Host-buffer front door of the hot path: a chunked, triple-stream pipeline.
+
+What ``everyvoice preprocess`` does per file -- ``process_spec`` (preprocessor.py:870-929),
+``process_energy`` (:632-651) and the statistics / normalisation pass (:378-490) -- for a
+whole shard whose audio lives in (pinned) HOST memory and whose results are wanted back in
+HOST memory (to be written to disk by the caller):
+
+    copy-in stream :  H2D samples of chunk i+1 ........ overlaps
+    compute stream :  fused features kernel + phone averaging of chunk i ........ overlaps
+    copy-out stream:  D2H log-spectrogram + energy of chunk i-1
+
+PCIe is full duplex, so the step costs max(H2D, D2H) instead of their sum, and the kernels
+hide entirely behind the copies.  Phone-level values stay resident until the last chunk, are
+reduced to the five-number summary, (all-gathered across ranks,) normalised in place and
+copied out once.  int16 PCM input (what ``process_audio`` writes, preprocessor.py:196-218)
+halves the H2D bytes; it is converted on load inside the kernel, bit-identically to float input.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .distributed import allgather_stats
+from .heavy import RaggedBatch, SpectralTransform, _require_cuda
+
+
+@dataclass
+class _Chunk:
+    u0: int           # first utterance
+    u1: int           # one past the last
+    s0: int           # first sample in the packed host buffer
+    s1: int
+    f0: int           # first frame in the packed output
+    f1: int
+    pad: int          # elements of lead-in in the device sample buffer (keeps the 16-byte alignment class)
+
+
+class PipelineResources:
+    """The reusable half of a pipeline: streams, events and the double-buffered device chunks.
+    Grows on demand, never shrinks; shared by every ``CorpusPipeline`` planned on one device."""
+
+    def __init__(self, device):
+        self.device = _require_cuda(device)
+        dev = self.device
+        self.s_in = torch.cuda.Stream(dev)
+        self.s_out = torch.cuda.Stream(dev)
+        self.s_compute = torch.cuda.Stream(dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]        # H2D of buffer b done
+        self.ev_comp = [torch.cuda.Event() for _ in range(2)]      # kernels on buffer b done
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]       # D2H of buffer b done
+        self._bufs: dict = {}
+
+    def buffer(self, name: str, numel: int, dtype) -> torch.Tensor:
+        t = self._bufs.get(name)
+        if t is None or t.dtype != dtype or t.numel() < numel:
+            t = self._bufs[name] = torch.empty(max(int(numel), 1), dtype=dtype, device=self.device)
+        return t
+
+
+class CorpusPipeline:
+    """The plan for one shard layout (``sample_offsets`` [+ durations]): chunk boundaries and the
+    per-chunk batch descriptors.  Cheap to build (host index arithmetic + one small upload per
+    chunk), so a new one is planned for every new batch of files; the device buffers, streams
+    and events come from a shared ``PipelineResources``.  ``run`` may be called repeatedly."""
+
+    def __init__(self, transform: SpectralTransform, sample_offsets, device=None, sample_dtype=torch.float32,
+                 durations=None, phone_offsets=None, chunk_bytes: int = 16 << 20, want_energy: bool = True,
+                 resources: PipelineResources | None = None):
+        self.tf = transform
+        self.device = _require_cuda(device if device is not None else transform._device)
+        self.res = resources if resources is not None else PipelineResources(self.device)
+        self.sample_dtype = sample_dtype
+        self.lib = _lib.load()
+        off = np.ascontiguousarray(np.asarray(sample_offsets, dtype=np.int64))
+        self.sample_offsets = off
+        self.n_utts = int(off.size - 1)
+        hop = transform.hop_length
+        frames = (np.diff(off) // hop).astype(np.int64)
+        self.frame_offsets = np.concatenate([[0], np.cumsum(frames)]).astype(np.int64)
+        self.total_frames = int(self.frame_offsets[-1])
+        self.total_samples = int(off[-1] - off[0])
+        esize = 2 if sample_dtype == torch.int16 else 4
+        # ---- chunk plan: consecutive utterances, about chunk_bytes of samples each ---------------
+        # ONE batch descriptor for the shard; chunks are utterance ranges of it (evf_features_run_range)
+        self.batch = transform.make_batch(off - off[0], self.device, apply_log=True, keep_last=False,
+                                          sample_dtype=sample_dtype)
+        assert np.array_equal(self.batch.frame_offsets, self.frame_offsets)
+        self.chunks: list[_Chunk] = []
+        limit = max(1, chunk_bytes // esize)
+        align = 16 // esize
+        u = 0
+        while u < self.n_utts:
+            v = int(np.searchsorted(off, off[u] + limit, side="right")) - 1   # last v with off[v] - off[u] <= limit
+            v = min(max(v, u + 1), self.n_utts)
+            s0 = int(off[u] - off[0])
+            self.chunks.append(_Chunk(u, v, s0, int(off[v] - off[0]), int(self.frame_offsets[u]),
+                                      int(self.frame_offsets[v]), s0 % align))
+            u = v
+        self.row_floats = self.batch.plan.row_floats
+        max_s = max((c.s1 - c.s0 + c.pad for c in self.chunks), default=0)
+        max_f = max((c.f1 - c.f0 for c in self.chunks), default=0)
+        self.want_energy = want_energy and not transform.is_complex
+        res = self.res
+        tag = "s16" if sample_dtype == torch.int16 else "f32"
+        self._d_samples = [res.buffer(f"samples{b}_{tag}", max_s, sample_dtype) for b in range(2)]
+        self._d_spec = [res.buffer(f"spec{b}", max_f * self.row_floats, torch.float32) for b in range(2)]
+        self._d_energy = [res.buffer(f"energy{b}", max_f, torch.float32) for b in range(2)]
+        # ---- phone-level averaging (optional) ------------------------------------------------------
+        self.has_phones = durations is not None
+        self.n_phones = 0
+        if self.has_phones:
+            p_off = np.ascontiguousarray(np.asarray(phone_offsets, dtype=np.int64))
+            if p_off.size != self.n_utts + 1:
+                raise ValueError("phone_offsets must have one entry per utterance plus one")
+            self.phone_offsets = p_off
+            self.n_phones = int(p_off[-1])
+            d = durations if torch.is_tensor(durations) else torch.from_numpy(np.ascontiguousarray(durations))
+            if d.dtype != torch.int64 or d.numel() != self.n_phones:
+                raise ValueError("durations must be an int64 tensor with phone_offsets[-1] entries")
+            self._h_durations = d.contiguous()      # uploaded by run() on the copy-in stream (counted as H2D)
+            self._h_phone_off = torch.from_numpy(p_off)
+            self._d_durations = res.buffer("durations", self.n_phones, torch.int64)
+            self._d_phone_off = res.buffer("phone_off", self.n_utts + 1, torch.int64)
+            self._d_phone = res.buffer("phone", self.n_phones, torch.float32)
+            self._d_stats = res.buffer("stats5", 5, torch.float64)
+            self._d_gathered = None
+        self.h2d_bytes = self.total_samples * esize + (self.n_phones * 8 + (self.n_utts + 1) * 8 if self.has_phones else 0)
+        self.d2h_bytes = self.total_frames * self.row_floats * 4 + (self.total_frames * 4 if self.want_energy else 0) \
+            + (self.n_phones * 4 if self.has_phones else 0)
+        self.kernel_launches_per_run = len(self.chunks) * (2 if self.has_phones else 1) + (3 if self.has_phones else 0)
+        self.esize = esize
+
+    # ------------------------------------------------------------------------------------------
+    def run(self, host_samples: torch.Tensor, host_spec: torch.Tensor, host_energy: torch.Tensor | None = None,
+            host_phone: torch.Tensor | None = None, normalize_phones: bool = True, group=None):
+        """``host_samples``: packed 1-D (pinned) host tensor of the pipeline's sample dtype;
+        ``host_spec [total_frames, F]``, ``host_energy [total_frames]``, ``host_phone [n_phones]``:
+        (pinned) host outputs.  Returns the float64[5] device summary of the phone values (or None)."""
+        lib, dev = self.lib, self.device
+        if host_samples.dtype != self.sample_dtype or host_samples.numel() < int(self.sample_offsets[-1]):
+            raise ValueError("host_samples does not match the pipeline's dtype / layout")
+        if tuple(host_spec.shape) != (self.total_frames, self.row_floats) or host_spec.dtype != torch.float32:
+            raise ValueError(f"host_spec must be float32 [{self.total_frames}, {self.row_floats}]")
+        res = self.res
+        esize = 2 if self.sample_dtype == torch.int16 else 4
+        h0 = int(self.sample_offsets[0])
+        s_in, s_compute, s_out = res.s_in, res.s_compute, res.s_out
+        ev_in, ev_comp, ev_out = res.ev_in, res.ev_comp, res.ev_out
+        cur = torch.cuda.current_stream(dev)
+        for s in (s_in, s_compute, s_out):
+            s.wait_stream(cur)
+        with torch.cuda.device(dev):
+            if self.has_phones:
+                with torch.cuda.stream(s_in):
+                    self._d_durations[: self.n_phones].copy_(self._h_durations, non_blocking=True)
+                    self._d_phone_off[: self.n_utts + 1].copy_(self._h_phone_off, non_blocking=True)
+                s_compute.wait_stream(s_in)
+            for i, c in enumerate(self.chunks):
+                b = i & 1
+                ns, nf = c.s1 - c.s0, c.f1 - c.f0
+                # -- H2D (buffer b is free once the kernels of chunk i-2 have consumed it)
+                if i >= 2:
+                    s_in.wait_event(ev_comp[b])
+                with torch.cuda.stream(s_in):
+                    self._d_samples[b][c.pad : c.pad + ns].copy_(host_samples[h0 + c.s0 : h0 + c.s1], non_blocking=True)
+                    ev_in[b].record(s_in)
+                # -- kernels (output buffer b is free once chunk i-2 has been copied out)
+                s_compute.wait_event(ev_in[b])
+                if i >= 2:
+                    s_compute.wait_event(ev_out[b])
+                st = C.c_void_p(s_compute.cuda_stream)
+                # addresses sample 0 / frame 0 of the whole shard would have if the chunk sat in place
+                samples_base = self._d_samples[b].data_ptr() + (c.pad - c.s0) * esize
+                spec_base = self._d_spec[b].data_ptr() - c.f0 * self.row_floats * 4
+                energy_base = self._d_energy[b].data_ptr() - c.f0 * 4
+                need_energy = self.want_energy or self.has_phones
+                _lib.check(lib.evf_features_run_range(self.batch.plan.handle, self.batch.handle, c.u0, c.u1,
+                                                      C.c_void_p(samples_base), C.c_void_p(spec_base),
+                                                      C.c_void_p(energy_base if need_energy else 0), st))
+                if self.has_phones:
+                    _lib.check(lib.evf_segment_mean(C.c_void_p(energy_base),
+                                                    C.c_void_p(self.batch.frame_offsets_dev_ptr + 8 * c.u0),
+                                                    C.c_void_p(self._d_durations.data_ptr()),
+                                                    C.c_void_p(self._d_phone_off.data_ptr() + 8 * c.u0),
+                                                    c.u1 - c.u0, C.c_void_p(self._d_phone.data_ptr()), st))
+                ev_comp[b].record(s_compute)
+                # -- D2H
+                s_out.wait_event(ev_comp[b])
+                with torch.cuda.stream(s_out):
+                    host_spec[c.f0 : c.f1].copy_(self._d_spec[b][: nf * self.row_floats].view(nf, self.row_floats), non_blocking=True)
+                    if self.want_energy and host_energy is not None:
+                        host_energy[c.f0 : c.f1].copy_(self._d_energy[b][:nf], non_blocking=True)
+                    ev_out[b].record(s_out)
+            stats = None
+            if self.has_phones:
+                st = C.c_void_p(s_compute.cuda_stream)
+                with torch.cuda.stream(s_compute):
+                    _lib.check(lib.evf_stats_partial(C.c_void_p(self._d_phone.data_ptr()), self.n_phones,
+                                                     C.c_void_p(self._d_stats.data_ptr()), 0, st))
+                    stats = self._d_stats
+                    if normalize_phones:
+                        parts = allgather_stats(self._d_stats, group, out=self._d_gathered)
+                        if parts.dim() == 2 and parts.shape[0] > 1:
+                            self._d_gathered = parts
+                        parts = parts.contiguous()
+                        _lib.check(lib.evf_normalize_by_gathered_stats(
+                            C.c_void_p(self._d_phone.data_ptr()), self.n_phones, C.c_void_p(parts.data_ptr()),
+                            parts.shape[0], parts.shape[1], st))
+                        stats = parts
+                    if host_phone is not None:
+                        host_phone.copy_(self._d_phone[: self.n_phones], non_blocking=True)
+        for s in (s_in, s_compute, s_out):
+            cur.wait_stream(s)
+        return stats

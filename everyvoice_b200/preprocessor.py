@@ -149,6 +149,20 @@ class Preprocessor:
         return transform.features_ragged(packed, sample_offsets, apply_log=True, keep_last=False,
                                          want_energy=want_energy)
 
+    def make_corpus_pipeline(self, sample_offsets, sample_dtype=torch.float32, durations=None, phone_offsets=None,
+                             output=False, chunk_bytes: int = 16 << 20):
+        """Host-buffer front door for a whole shard (``pipeline.CorpusPipeline``): H2D of the
+        next chunk, the kernels of this one and D2H of the previous one overlap on three streams."""
+        from .pipeline import CorpusPipeline, PipelineResources
+
+        transform = self.output_spectral_transform if output else self.input_spectral_transform
+        device = _require_cuda(self.device)
+        res = getattr(self, "_pipeline_resources", None)
+        if res is None or res.device != device:
+            res = self._pipeline_resources = PipelineResources(device)   # buffers / streams live across batches
+        return CorpusPipeline(transform, sample_offsets, device, sample_dtype, durations, phone_offsets, chunk_bytes,
+                              resources=res)
+
     def process_energy_batch(self, feats: RaggedFeatures, durations=None, phone_offsets=None):
         """The in-memory core of ``process_energy`` (preprocessor.py:641-650): frame energy, and
         phone-level averages when ``durations`` (packed int64 + ``phone_offsets``, or a list of

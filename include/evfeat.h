@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define EVF_ABI_VERSION 2
+#define EVF_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define EVF_API __attribute__((visibility("default")))
@@ -123,6 +123,16 @@ EVF_API int evf_batch_frame_offsets_dev(const evf_batch* batch, const int64_t** 
  *   energy_out_dev: [total_frames] float32, or NULL (must be NULL-able; ignored for raw) */
 EVF_API int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* samples_dev,
                      float* spec_out_dev, float* energy_out_dev, void* stream);
+
+/* The same for utterances [utt_begin, utt_end) of the batch only -- the chunked host pipeline
+ * (one batch descriptor per shard, one launch per resident chunk).  The three pointers are the
+ * addresses that sample 0 / frame 0 of the WHOLE batch would have: a caller holding only the
+ * chunk [utt_begin, utt_end) in a device buffer passes `buffer - offset_of_chunk`; nothing outside
+ * the chunk is touched.  For the 16-byte bulk-copy path the chunk must sit in its buffer at the
+ * same (sample index * sample size) mod 16 as in the packed layout. */
+EVF_API int evf_features_run_range(const evf_plan* plan, const evf_batch* batch, int32_t utt_begin, int32_t utt_end,
+                           const void* samples_base_dev, float* spec_base_dev, float* energy_base_dev,
+                           void* stream);
 
 /* Convenience wrapper: batch_create + features_run + batch_destroy.
  * frame_offsets_host_out may be NULL. */

@@ -29,7 +29,7 @@ def _declared_symbols():
 
 def test_header_declares_the_operator_surface():
     names = _declared_symbols()
-    assert len(names) == len(set(names)) >= 21
+    assert len(names) == len(set(names)) >= 22
     for required in ("evf_plan_create", "evf_features_run", "evf_features_ragged", "evf_segment_mean",
                      "evf_stats_partial", "evf_normalize_inplace", "evf_energy_from_spec", "evf_log_compress",
                      "evf_last_error"):

@@ -372,6 +372,48 @@ def test_gathered_stats_merge_and_normalise_on_device(cuda_device):
     assert torch.equal(single, mine)  # [5] and [world, 5] forms agree bit for bit
 
 
+@pytest.mark.parametrize("dtype", ["f32", "s16"])
+def test_corpus_pipeline_equals_single_batch(cuda_device, dtype):
+    """The chunked three-stream host pipeline returns exactly what one resident batch does."""
+    import everyvoice_b200 as ev
+    from everyvoice_b200 import synth
+
+    pre = ev.Preprocessor(ev.AudioConfig(spec_type="mel"), device=cuda_device)
+    hop = 256
+    lens = synth.utterance_lengths(37, 22050, hop, 5, 0.3, 2.5)
+    lens[3] += 5   # every later chunk starts at an odd sample index: exercises the alignment lead-in
+    lens[11] += 2
+    rng = np.random.default_rng(8)
+    if dtype == "s16":
+        xs = [rng.integers(-30000, 30000, size=int(L)).astype(np.int16) for L in lens]
+        tdt = torch.int16
+    else:
+        xs = [synth.white_noise(int(L), 50 + i) for i, L in enumerate(lens)]
+        tdt = torch.float32
+    packed, off = synth.pack_ragged(xs)
+    durs = [synth.synthetic_durations(int(L) // hop, seed=70 + i) for i, L in enumerate(lens)]
+    d_packed, p_off = synth.pack_ragged(durs)
+    host = torch.from_numpy(packed).pin_memory()
+    pipe = pre.make_corpus_pipeline(off, tdt, torch.from_numpy(d_packed.astype(np.int64)), p_off,
+                                    chunk_bytes=200_000)  # forces ~10 chunks
+    assert len(pipe.chunks) >= 5
+    h_spec = torch.empty((pipe.total_frames, 80), dtype=torch.float32).pin_memory()
+    h_energy = torch.empty(pipe.total_frames, dtype=torch.float32).pin_memory()
+    h_phone = torch.empty(pipe.n_phones, dtype=torch.float32).pin_memory()
+    for _ in range(2):  # twice: buffers and events are reused across runs
+        h_spec.zero_(); h_energy.zero_(); h_phone.zero_()
+        pipe.run(host, h_spec, h_energy, h_phone)
+        torch.cuda.synchronize()
+        feats = pre.process_spec_batch(host.to(cuda_device), off)
+        phone, _ = pre.process_energy_batch(feats, torch.from_numpy(d_packed.astype(np.int64)), p_off)
+        s = ev.Scaler(cuda_device)
+        s.append(phone)
+        s.normalize_by_device_stats_(phone, s.partial_stats())
+        assert np.array_equal(pipe.frame_offsets, feats.frame_offsets)
+        assert torch.equal(h_spec, feats.spec.cpu()) and torch.equal(h_energy, feats.energy.cpu())
+        _same_with_nans(h_phone, phone.cpu(), atol=0.0)
+
+
 # ------------------------------------------------------------------------------------------
 # reference test-suite invariants (everyvoice/tests/test_preprocessing.py:385-435, 496-568)
 # ------------------------------------------------------------------------------------------
