@@ -463,3 +463,150 @@ def test_error_behaviour(cuda_device):
     # empty batch is fine and launches nothing
     f = tf.features_ragged(torch.zeros(0, device=cuda_device), np.array([0], dtype=np.int64))
     assert f.spec.shape == (0, 80) and f.energy.shape == (0,)
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties (the oracle is too slow here)
+# ------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def full_size_batch(cuda_device):
+    """configs[1]: 1 000 utterances of 1-10 s at 22.05 kHz (470 190 frames), white + speech-like."""
+    from everyvoice_b200 import synth
+
+    sr, hop = 22050, 256
+    lens = synth.utterance_lengths(1000, sr, hop, 1234)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(99)
+    x = torch.rand(int(off[-1]), device=cuda_device, generator=g) * 1.9 - 0.95
+    for b in range(0, 1000, 50):  # every 50th utterance is a speech-like signal (wide dynamic range)
+        x[off[b] : off[b + 1]] = torch.from_numpy(synth.speech_like(int(lens[b]), sr, seed=b)).to(cuda_device)
+    return lens, off, x
+
+
+def test_full_size_frame_counts_and_sampled_oracle(cuda_device, full_size_batch):
+    import everyvoice_b200 as ev
+    from oracle import ev_oracle as O
+
+    lens, off, x = full_size_batch
+    tf = ev.get_spectral_transform("mel", 1024, 1024, 256, 22050, 80, 0, 8000).to(cuda_device)
+    feats = tf.features_ragged(x, off)
+    assert np.array_equal(np.diff(feats.frame_offsets), lens // 256)      # bit-exact T = L // hop for all 1 000
+    assert feats.spec.shape == (int((lens // 256).sum()), 80) == (470190, 80)
+    assert bool(torch.isfinite(feats.spec).all()) and float(feats.spec.min()) >= np.log(1e-5) - 1e-6
+    otf = O.get_spectral_transform("mel", 1024, 1024, 256, 22050, 80, 0, 8000)
+    for b in (0, 50, 333, 500, 999):  # a sample of utterances against the oracle (first, last, speech-like, noise)
+        o_spec, o_energy, _ = O.features_one(x[off[b] : off[b + 1]].cpu(), otf, 256)
+        assert float((feats.utterance(b).cpu() - o_spec).abs().max()) <= ATOL_LOG
+        assert float((feats.utterance_energy(b).cpu() - o_energy).abs().max()) <= ATOL_LOG
+
+
+def test_full_size_energy_is_norm_of_log_spec_and_checksums(cuda_device, full_size_batch):
+    """energy == ||log-mel||_2 per frame (preprocessor.py:302-309) on all 470 190 frames, recomputed
+    by an independent kernel and by torch; running the batch twice gives bit-identical output."""
+    import everyvoice_b200 as ev
+
+    lens, off, x = full_size_batch
+    pre = ev.Preprocessor(ev.AudioConfig(spec_type="mel"), device=cuda_device)
+    f1 = pre.process_spec_batch(x, off)
+    f2 = pre.process_spec_batch(x, off)
+    assert torch.equal(f1.spec, f2.spec) and torch.equal(f1.energy, f2.energy)       # deterministic
+    e_kernel = pre.extract_energy(f1.spec.transpose(0, 1))                            # the stand-alone operator
+    e_torch = torch.linalg.norm(f1.spec, dim=1)
+    assert float((f1.energy - e_kernel).abs().max()) <= 2e-5 * float(e_torch.max())
+    assert float((f1.energy - e_torch).abs().max()) <= 2e-5 * float(e_torch.max())
+
+
+def test_full_size_parseval_on_raw_stft(cuda_device, full_size_batch):
+    """Parseval on every frame of a 100-utterance slice: sum_k c_k |X[k]|^2 == N * sum_n (w[n] x[n])^2
+    (c_k = 1 for DC / Nyquist, 2 otherwise).  Checks FFT, window, framing and reflect padding at
+    full ragged scale without the oracle."""
+    import everyvoice_b200 as ev
+
+    lens, off, x = full_size_batch
+    n_fft, hop = 1024, 256
+    tf = ev.get_spectral_transform("raw", n_fft, n_fft, hop).to(cuda_device)
+    sl = slice(200, 300)
+    o = off[sl.start : sl.stop + 1] - off[sl.start]
+    xs = x[off[sl.start] : off[sl.stop]]
+    feats = tf.features_ragged(xs, o, keep_last=True)
+    win = torch.hann_window(n_fft, device=cuda_device, dtype=torch.float64)
+    c = torch.full((n_fft // 2 + 1,), 2.0, device=cuda_device, dtype=torch.float64)
+    c[0] = c[-1] = 1.0
+    worst = 0.0
+    for b in range(sl.stop - sl.start):
+        X = feats.utterance(b)                                              # [513, T + 1] complex64
+        lhs = (c[:, None] * (X.real.double() ** 2 + X.imag.double() ** 2)).sum(dim=0)
+        u = xs[o[b] : o[b + 1]].double()
+        padded = torch.nn.functional.pad(u[None, None], (n_fft // 2, n_fft // 2), mode="reflect")[0, 0]
+        frames = padded.unfold(0, n_fft, hop)                               # [T + 1, 1024]
+        rhs = n_fft * ((frames * win) ** 2).sum(dim=1)
+        assert lhs.shape == rhs.shape
+        worst = max(worst, float(((lhs - rhs).abs() / rhs.clamp(min=1e-12)).max()))
+    assert worst <= 2e-5, worst
+
+
+def test_full_size_phone_average_round_trip(cuda_device, full_size_batch):
+    """Sum over phones of (mean * clipped length) == sum of the covered frames, for all 1 000
+    utterances (durations with zeros, overruns and underruns), and normalisation is idempotent:
+    normalising already normalised data changes nothing beyond float round-off."""
+    import everyvoice_b200 as ev
+    from everyvoice_b200 import synth
+
+    lens, off, x = full_size_batch
+    pre = ev.Preprocessor(ev.AudioConfig(spec_type="mel"), device=cuda_device)
+    T = lens // 256
+    f_off = np.concatenate([[0], np.cumsum(T)]).astype(np.int64)
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(5)
+    vals = torch.rand(int(f_off[-1]), device=cuda_device, generator=g) * 220 + 80
+    durs = [synth.synthetic_durations(int(t), seed=900 + i) for i, t in enumerate(T)]
+    d_packed, p_off = synth.pack_ragged(durs)
+    out = pre.average_data_by_durations_ragged(vals, f_off, torch.from_numpy(d_packed.astype(np.int64)), p_off).cpu().double()
+    v_cpu = vals.cpu().double()
+    for b in range(0, 1000, 7):
+        d = durs[b]
+        start = np.concatenate([[0], np.cumsum(d)[:-1]])
+        lo = np.clip(start, 0, T[b])
+        hi = np.clip(start + d, 0, T[b])
+        n = np.where(d > 0, hi - lo, 0)
+        o = out[p_off[b] : p_off[b + 1]]
+        assert torch.equal(torch.isnan(o), torch.from_numpy((d > 0) & (n == 0)))
+        assert bool((o[torch.from_numpy(d <= 0)] == float(np.float32(1e-7))).all())
+        covered = float(v_cpu[f_off[b] + lo.min() : f_off[b] + hi.max()].sum())
+        recon = float((torch.nan_to_num(o) * torch.from_numpy(n.astype(np.float64)))[torch.from_numpy(n > 0)].sum())
+        assert recon == pytest.approx(covered, rel=1e-5)
+    s = ev.Scaler(cuda_device)
+    phone = out.float().to(cuda_device)
+    s.append(phone)
+    s.normalize_by_device_stats_(phone, s.partial_stats())
+    s2 = ev.Scaler(cuda_device)
+    s2.append(phone)
+    st = s2.calculate_stats(distributed=False)
+    assert abs(st["mean"]) < 1e-4 and st["std"] == pytest.approx(1.0, abs=1e-4)
+
+
+@pytest.mark.parametrize("config,spec_type", [("B", "mel"), ("A", "linear"), ("A", "mel-librosa")])
+def test_other_baseline_configs_sampled_oracle(cuda_device, config, spec_type):
+    """configs[2] (44.1 kHz / 2048 / 512 / 128 mels) and configs[3] (linear + energy) at 200
+    ragged utterances: exact frame counts everywhere, oracle parity on a sample."""
+    import everyvoice_b200 as ev
+    from everyvoice_b200 import synth
+    from oracle import ev_oracle as O
+
+    sr, n_fft, win, hop, n_mels, f_min, f_max = CONFIGS[config]
+    lens = synth.utterance_lengths(200, sr, hop, 1236, 1.0, 10.0)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(1236)
+    x = torch.rand(int(off[-1]), device=cuda_device, generator=g) * 1.9 - 0.95
+    tf = ev.get_spectral_transform(spec_type, n_fft, win, hop, sr, n_mels, f_min, f_max).to(cuda_device)
+    feats = tf.features_ragged(x, off)
+    assert np.array_equal(np.diff(feats.frame_offsets), lens // hop)
+    otf = O.get_spectral_transform(spec_type, n_fft, win, hop, sr, n_mels, f_min, f_max)
+    for b in (0, 99, 199):
+        xb = x[off[b] : off[b + 1]].cpu()
+        o_spec, o_energy, _ = O.features_one(xb, otf, hop)
+        truth = O.truth_features(xb.numpy(), spec_type, n_fft, win, hop, sr, n_mels, f_min, f_max)[0] if spec_type == "linear" else None
+        assert_log_spec_close(feats.utterance(b).cpu(), o_spec, truth, spec_type)
+        assert float((feats.utterance_energy(b).cpu() - o_energy).abs().max()) <= ATOL_LOG
