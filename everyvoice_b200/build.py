@@ -14,7 +14,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libevfeat.so"
 SOURCES = ["evfeat_api.cu", "evfeat_features.cu", "evfeat_aux.cu"]
-HEADERS = ["evfeat_internal.h", "evfeat_fft.cuh"]
+HEADERS = ["evfeat_internal.h", "evfeat_fft.cuh", "evfeat_device.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

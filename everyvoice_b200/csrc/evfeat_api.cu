@@ -218,6 +218,10 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
     set_error("evf_plan_create: unknown sample_format");
     return EVF_ERR_INVALID_ARGUMENT;
   }
+  if (cfg->apply_log && !(cfg->log_clip >= 1.17549435e-38f)) {
+    set_error("evf_plan_create: log_clip must be a normal positive float (the reference uses 1e-5)");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
   if (mel && (!mel_fb_host || cfg->n_mels < 1)) {
     set_error("evf_plan_create: mel spec types need a filterbank and n_mels >= 1");
     return EVF_ERR_INVALID_ARGUMENT;

@@ -1,0 +1,145 @@
+// Device helpers shared by the feature kernels (included inside `namespace evf { namespace {`).
+//   ModeTraits      -- FFT packing per n_fft
+//   compress        -- log(max(v, clip)), utils/heavy.py:39-40
+//   warp_fft1024    -- one warp, one 1024-point complex FFT (32 x 32 four-step)
+//   mbarrier / cp.async.bulk primitives (TMA 1-D staging)
+#pragma once
+
+template <int MODE>
+struct ModeTraits;
+template <>
+struct ModeTraits<MODE_PACK2> {
+  static constexpr int kNfft = 1024;
+  static constexpr int kFramesPerJob = 2;
+};
+template <>
+struct ModeTraits<MODE_HALF> {
+  static constexpr int kNfft = 2048;
+  static constexpr int kFramesPerJob = 1;
+};
+template <>
+struct ModeTraits<MODE_HALF_L1> : ModeTraits<MODE_HALF> {};
+
+__device__ __forceinline__ float load_sample(const float* p, long long i) { return __ldg(p + i); }
+__device__ __forceinline__ float load_sample(const short* p, long long i) {
+  return (float)__ldg(p + i) * (1.0f / 32768.0f);
+}
+
+// log(max(v, clip)) as one MUFU.LG2 + one FMUL.  The plan guarantees clip >= FLT_MIN whenever
+// apply_log is set (evf_plan_create), so the clamped argument is a normal number and the
+// denormal pre-scaling of __logf is dead weight; a NaN input still propagates (torch.clamp).
+__device__ __forceinline__ float compress(float v, int apply_log, float clip) {
+  if (apply_log) {
+    v = (v < clip) ? clip : v;
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(v));
+    v = l * 0.69314718055994530942f;
+  }
+  return v;
+}
+
+// 1024-point complex FFT of the 32x32 values held by one warp.
+// In : lane n2 holds z[32*n1 + n2] at index n1.
+// Out: lane k1 holds Z[k1 + 32*k2] at index bitrev5(k2).
+// Shared-memory instruction diet: the inter-pass twiddles come as 16 LDS.128 (two per load), the
+// transposed reads as 2 x 16 LDS.64 (row stride 34 words keeps them 8-byte aligned and
+// conflict-free: half-warp lanes hit banks 2*lane, 2*lane + 1).
+__device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32],
+                                             const float4* __restrict__ s_tw4,
+                                             float* __restrict__ scr, int lane) {
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    dft32_dif(re, im);
+    if (pass == 0) {
+      {
+        // index p now holds k1 = bitrev5(p); multiply by W_1024^(n2*k1) (table is stored
+        // by register position, two positions per entry) and hand element k1 to lane k1.
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float4 t = s_tw4[q * 32 + lane];
+          if (q > 0) {  // position 0 is k1 = 0: twiddle 1
+            const float a = fmaf(-im[2 * q], t.y, re[2 * q] * t.x);
+            const float b = fmaf(re[2 * q], t.y, im[2 * q] * t.x);
+            re[2 * q] = a;
+            im[2 * q] = b;
+          }
+          const float c = fmaf(-im[2 * q + 1], t.w, re[2 * q + 1] * t.z);
+          const float d = fmaf(re[2 * q + 1], t.w, im[2 * q + 1] * t.z);
+          re[2 * q + 1] = c;
+          im[2 * q + 1] = d;
+        }
+        const float2* row = reinterpret_cast<const float2*>(scr + lane * kScrStride);
+#pragma unroll
+        for (int p = 0; p < 32; ++p) scr[bitrev5(p) * kScrStride + lane] = re[p];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const float2 v = row[m];
+          re[2 * m] = v.x;
+          re[2 * m + 1] = v.y;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 32; ++p) scr[bitrev5(p) * kScrStride + lane] = im[p];
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          const float2 v = row[m];
+          im[2 * m] = v.x;
+          im[2 * m + 1] = v.y;
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// sqrt for the mel-librosa magnitude: one MUFU (relative error <= 2^-22, far inside the 1e-3
+// log-domain budget) instead of the ~8-instruction correctly rounded sequence.
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// ---- mbarrier / bulk-copy (TMA 1-D) primitives ----------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (SASS: UBLKCP); completion is signalled on the mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ int reflect_index(int j, int L) {
+  j = (j < 0) ? -j : j;
+  j = (j >= L) ? 2 * (L - 1) - j : j;
+  return (j < 0) ? 0 : j;  // only reachable for frames beyond the last valid one
+}
+

@@ -31,132 +31,7 @@ namespace evf {
 
 namespace {
 
-template <int MODE>
-struct ModeTraits;
-template <>
-struct ModeTraits<MODE_PACK2> {
-  static constexpr int kNfft = 1024;
-  static constexpr int kFramesPerJob = 2;
-};
-template <>
-struct ModeTraits<MODE_HALF> {
-  static constexpr int kNfft = 2048;
-  static constexpr int kFramesPerJob = 1;
-};
-template <>
-struct ModeTraits<MODE_HALF_L1> : ModeTraits<MODE_HALF> {};
-
-__device__ __forceinline__ float load_sample(const float* p, long long i) { return __ldg(p + i); }
-__device__ __forceinline__ float load_sample(const short* p, long long i) {
-  return (float)__ldg(p + i) * (1.0f / 32768.0f);
-}
-
-__device__ __forceinline__ float compress(float v, int apply_log, float clip) {
-  if (apply_log) {
-    v = (v < clip) ? clip : v;  // torch.clamp(min=clip): NaN propagates
-    v = __logf(v);
-  }
-  return v;
-}
-
-// 1024-point complex FFT of the 32x32 values held by one warp.
-// In : lane n2 holds z[32*n1 + n2] at index n1.
-// Out: lane k1 holds Z[k1 + 32*k2] at index bitrev5(k2).
-// Shared-memory instruction diet: the inter-pass twiddles come as 16 LDS.128 (two per load), the
-// transposed reads as 2 x 16 LDS.64 (row stride 34 words keeps them 8-byte aligned and
-// conflict-free: half-warp lanes hit banks 2*lane, 2*lane + 1).
-__device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32],
-                                             const float4* __restrict__ s_tw4,
-                                             float* __restrict__ scr, int lane) {
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    dft32_dif(re, im);
-    if (pass == 0) {
-      {
-        // index p now holds k1 = bitrev5(p); multiply by W_1024^(n2*k1) (table is stored
-        // by register position, two positions per entry) and hand element k1 to lane k1.
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float4 t = s_tw4[q * 32 + lane];
-          if (q > 0) {  // position 0 is k1 = 0: twiddle 1
-            const float a = fmaf(-im[2 * q], t.y, re[2 * q] * t.x);
-            const float b = fmaf(re[2 * q], t.y, im[2 * q] * t.x);
-            re[2 * q] = a;
-            im[2 * q] = b;
-          }
-          const float c = fmaf(-im[2 * q + 1], t.w, re[2 * q + 1] * t.z);
-          const float d = fmaf(re[2 * q + 1], t.w, im[2 * q + 1] * t.z);
-          re[2 * q + 1] = c;
-          im[2 * q + 1] = d;
-        }
-        const float2* row = reinterpret_cast<const float2*>(scr + lane * kScrStride);
-#pragma unroll
-        for (int p = 0; p < 32; ++p) scr[bitrev5(p) * kScrStride + lane] = re[p];
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          const float2 v = row[m];
-          re[2 * m] = v.x;
-          re[2 * m + 1] = v.y;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int p = 0; p < 32; ++p) scr[bitrev5(p) * kScrStride + lane] = im[p];
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          const float2 v = row[m];
-          im[2 * m] = v.x;
-          im[2 * m + 1] = v.y;
-        }
-        __syncwarp();
-      }
-    }
-  }
-}
-
-// sqrt for the mel-librosa magnitude: one MUFU (relative error <= 2^-22, far inside the 1e-3
-// log-domain budget) instead of the ~8-instruction correctly rounded sequence.
-__device__ __forceinline__ float fast_sqrt(float x) {
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-
-// ---- mbarrier / bulk-copy (TMA 1-D) primitives ----------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// global -> shared bulk copy (SASS: UBLKCP); completion is signalled on the mbarrier.
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
+#include "evfeat_device.cuh"
 
 using TileInfo = TileDesc;  // host-built, 32 bytes, one per tile (evfeat_internal.h)
 
@@ -164,12 +39,6 @@ using TileInfo = TileDesc;  // host-built, 32 bytes, one per tile (evfeat_intern
 struct ManualRange {
   int a_lo, a_hi, total;
 };
-
-__device__ __forceinline__ int reflect_index(int j, int L) {
-  j = (j < 0) ? -j : j;
-  j = (j >= L) ? 2 * (L - 1) - j : j;
-  return (j < 0) ? 0 : j;  // only reachable for frames beyond the last valid one
-}
 
 template <int MODE, int SPEC, typename SampleT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const FeatParams p) {
@@ -480,7 +349,11 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
       manual_fill_now(nxt, mr, s_in);
     }
 
+#ifdef EVF_EXP_SKIP_BC
+    if constexpr (false) {
+#else
     if constexpr (kMel) {
+#endif
       // ---- phase B: mel projection, lane = frame ---------------------------------------
       // Each worker (a warp, or a half / quarter warp when the tile has fewer than 32 frames)
       // walks a contiguous run of bins that starts and ends on interval boundaries.  Two running
@@ -546,20 +419,33 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
       }
       __syncthreads();  // (2)
       // ---- phase C: combine, log, coalesced store of the log-mel rows + per-frame energy ---
+      // (32-bit offsets from one row pointer per frame; rows of intervals without bins are never
+      // flushed and stay zero, cleared at start)
+      const int n_mels = p.n_mels;
+      const int apply_log = p.apply_log;
+      const float clip = p.log_clip;
 #pragma unroll
       for (int q = 0; q < FPJ; ++q) {
         const int f = warp * FPJ + q;
         if (f < nvalid) {
-          float* dst = p.spec_out + (out_frame0 + f) * (long long)p.row_floats;
+          float* __restrict__ dst = p.spec_out + (out_frame0 + f) * (long long)p.row_floats;
+          const float* sa_f = s_sa + f + lane * FS;
+          const float* sb_f = s_sb + FS + f + lane * FS;
           float acc = 0.f;
-          const float* sa_f = s_sa + f;
-          const float* sb_f = s_sb + FS + f;
-          for (int m = lane; m < p.n_mels; m += 32) {
-            // rows of intervals without bins are never flushed and stay zero (cleared at start)
-            float v = sa_f[m * FS] + sb_f[m * FS];
-            v = compress(v, p.apply_log, p.log_clip);
-            dst[m] = v;
-            acc = fmaf(v, v, acc);
+          int m = lane;
+#pragma unroll 1
+          for (; m + 32 < n_mels; m += 64, sa_f += 64 * FS, sb_f += 64 * FS) {  // two rows of 32 per trip
+            const float v0 = compress(sa_f[0] + sb_f[0], apply_log, clip);
+            const float v1 = compress(sa_f[32 * FS] + sb_f[32 * FS], apply_log, clip);
+            dst[m] = v0;
+            dst[m + 32] = v1;
+            acc = fmaf(v0, v0, acc);
+            acc = fmaf(v1, v1, acc);
+          }
+          if (m < n_mels) {
+            const float v0 = compress(sa_f[0] + sb_f[0], apply_log, clip);
+            dst[m] = v0;
+            acc = fmaf(v0, v0, acc);
           }
           if (p.energy_out != nullptr) {
 #pragma unroll

@@ -22,6 +22,7 @@ WORK = {
     "linA": ("linear", 22050, 1024, 1024, 256, 80, 0, 8000),
     "melB": ("mel", 44100, 2048, 2048, 512, 128, 0, 8000),
     "librosaA": ("mel-librosa", 22050, 1024, 1024, 256, 80, 0, 8000),
+    "melA_s16": ("mel", 22050, 1024, 1024, 256, 80, 0, 8000),
 }
 
 
@@ -38,7 +39,9 @@ def main():
         g.manual_seed(1234)
         x = torch.rand(int(off[-1]), device=dev, generator=g) * 1.9 - 0.95
         tf = ev.get_spectral_transform(st, n_fft, win, hop, sr, n_mels, f_min, f_max).to(dev)
-        batch = tf.make_batch(off, dev)
+        if name.endswith("_s16"):
+            x = (x * 32767.0).round().to(torch.int16)
+        batch = tf.make_batch(off, dev, sample_dtype=x.dtype)
         spec = torch.empty((batch.total_frames, batch.plan.row_floats), device=dev)
         en = torch.empty(batch.total_frames, device=dev)
         for _ in range(3):
