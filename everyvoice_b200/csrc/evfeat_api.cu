@@ -259,27 +259,30 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   PlanTables t;
   t.window.resize(cfg->n_fft);
   if (p->mode == MODE_PACK2) {
-    // pair layout for LDS.64: [q][lane] = {w[32 * 2q + lane], w[32 * (2q + 1) + lane]}; 0.5 is exact
-    for (int q = 0; q < 16; ++q)
+    // pair layout for LDS.64: [r][lane] = {w[32 * r + lane], w[32 * (r + 16) + lane]}, r < 16: the two inputs of
+    // one first-stage butterfly of the first pass (evfeat_fft.cuh, win_head); 0.5 is exact
+    for (int r = 0; r < 16; ++r)
       for (int lane = 0; lane < 32; ++lane) {
-        t.window[(q * 32 + lane) * 2 + 0] = 0.5f * window_host[32 * (2 * q) + lane];
-        t.window[(q * 32 + lane) * 2 + 1] = 0.5f * window_host[32 * (2 * q + 1) + lane];
+        t.window[(r * 32 + lane) * 2 + 0] = 0.5f * window_host[32 * r + lane];
+        t.window[(r * 32 + lane) * 2 + 1] = 0.5f * window_host[32 * (r + 16) + lane];
       }
   } else {
     for (int i = 0; i < cfg->n_fft; ++i) t.window[i] = 0.5f * window_host[i];  // exact scaling
   }
+  // four-step twiddles W_1024^(n2 * k1), applied after the transpose (lane = k1) inside the first butterfly
+  // stage of the second pass: entry [n][lane] = {t[n], t[n + 16]}, n < 16
   t.tw4.resize(kFftSize / 2);
   const double two_pi = 6.283185307179586476925286766559;
-  for (int q = 0; q < 16; ++q) {
+  for (int n = 0; n < 16; ++n) {
     for (int lane = 0; lane < 32; ++lane) {
       float c[2], sn[2];
       for (int h = 0; h < 2; ++h) {
-        const int k1 = bitrev5(2 * q + h);
-        const double ang = -two_pi * (double)((lane * k1) % kFftSize) / (double)kFftSize;
+        const int n2 = n + 16 * h;
+        const double ang = -two_pi * (double)((lane * n2) % kFftSize) / (double)kFftSize;
         c[h] = (float)std::cos(ang);
         sn[h] = (float)std::sin(ang);
       }
-      t.tw4[q * 32 + lane] = make_float4(c[0], sn[0], c[1], sn[1]);
+      t.tw4[n * 32 + lane] = make_float4(c[0], sn[0], c[1], sn[1]);
     }
   }
   if (p->mode == MODE_HALF) {

@@ -38,60 +38,55 @@ __device__ __forceinline__ float compress(float v, int apply_log, float clip) {
   return v;
 }
 
-// 1024-point complex FFT of the 32x32 values held by one warp.
-// In : lane n2 holds z[32*n1 + n2] at index n1.
-// Out: lane k1 holds Z[k1 + 32*k2] at index bitrev5(k2).
-// Shared-memory instruction diet: the inter-pass twiddles come as 16 LDS.128 (two per load), the
+// 1024-point complex FFT of the 32x32 values held by one warp, after the caller has run the
+// (window-fused) first butterfly stage of the first pass.
+// In : lane n2; index i (even) / i + 1 hold the span-1 butterfly outputs of rows n1 = bitrev5(i), n1 + 16
+//      of z[32*n1 + n2].
+// Out: lane k1 holds Z[k1 + 32*k2] at index k2.
+// Shared-memory instruction diet: the four-step twiddles come as 16 LDS.128 (two per load), the
 // transposed reads as 2 x 16 LDS.64 (row stride 34 words keeps them 8-byte aligned and
 // conflict-free: half-warp lanes hit banks 2*lane, 2*lane + 1).
-__device__ __forceinline__ void warp_fft1024(float (&re)[32], float (&im)[32],
-                                             const float4* __restrict__ s_tw4,
-                                             float* __restrict__ scr, int lane) {
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    dft32_dif(re, im);
-    if (pass == 0) {
-      {
-        // index p now holds k1 = bitrev5(p); multiply by W_1024^(n2*k1) (table is stored
-        // by register position, two positions per entry) and hand element k1 to lane k1.
+__device__ __forceinline__ void warp_fft1024_tail(float (&re)[32], float (&im)[32],
+                                                  const float4* __restrict__ s_tw4,
+                                                  float* __restrict__ scr, int lane) {
+  dft32_dit_tail(re, im);  // index k1 holds Y[k1][n2 = lane]
+  float tr[32], ti[32];
+  {
+    const float2* row = reinterpret_cast<const float2*>(scr + lane * kScrStride);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float4 t = s_tw4[q * 32 + lane];
-          if (q > 0) {  // position 0 is k1 = 0: twiddle 1
-            const float a = fmaf(-im[2 * q], t.y, re[2 * q] * t.x);
-            const float b = fmaf(re[2 * q], t.y, im[2 * q] * t.x);
-            re[2 * q] = a;
-            im[2 * q] = b;
-          }
-          const float c = fmaf(-im[2 * q + 1], t.w, re[2 * q + 1] * t.z);
-          const float d = fmaf(re[2 * q + 1], t.w, im[2 * q + 1] * t.z);
-          re[2 * q + 1] = c;
-          im[2 * q + 1] = d;
-        }
-        const float2* row = reinterpret_cast<const float2*>(scr + lane * kScrStride);
+    for (int p = 0; p < 32; ++p) scr[p * kScrStride + lane] = re[p];
+    __syncwarp();
 #pragma unroll
-        for (int p = 0; p < 32; ++p) scr[bitrev5(p) * kScrStride + lane] = re[p];
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          const float2 v = row[m];
-          re[2 * m] = v.x;
-          re[2 * m + 1] = v.y;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int p = 0; p < 32; ++p) scr[bitrev5(p) * kScrStride + lane] = im[p];
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          const float2 v = row[m];
-          im[2 * m] = v.x;
-          im[2 * m + 1] = v.y;
-        }
-        __syncwarp();
-      }
+    for (int m = 0; m < 16; ++m) {
+      const float2 v = row[m];
+      tr[2 * m] = v.x;
+      tr[2 * m + 1] = v.y;
     }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 32; ++p) scr[p * kScrStride + lane] = im[p];
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const float2 v = row[m];
+      ti[2 * m] = v.x;
+      ti[2 * m + 1] = v.y;
+    }
+    __syncwarp();
   }
+  // lane = k1 now; element n2 needs W_1024^(n2*k1): table entry [n][lane] = {t[n], t[n + 16]}.
+  // The multiplication rides in the first butterfly stage of the second pass.
+  {
+    const float4 t = s_tw4[lane];  // n = 0: t[0] = 1
+    tw_head<true>(re[0], im[0], re[1], im[1], tr[0], ti[0], t.x, t.y, tr[16], ti[16], t.z, t.w);
+  }
+#pragma unroll
+  for (int n = 1; n < 16; ++n) {
+    const float4 t = s_tw4[n * 32 + lane];
+    const int i = bitrev5(n);
+    tw_head<false>(re[i], im[i], re[i + 1], im[i + 1], tr[n], ti[n], t.x, t.y, tr[n + 16], ti[n + 16], t.z, t.w);
+  }
+  dft32_dit_tail(re, im);  // index k2 holds Z[k1 + 32*k2]
 }
 
 // sqrt for the mel-librosa magnitude: one MUFU (relative error <= 2^-22, far inside the 1e-3
@@ -117,6 +112,16 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef EVF_EXP_BOUNDED_WAIT
+  for (int spin = 0; spin < 2000000; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  return;
+#endif
   asm volatile(
       "{\n"
       ".reg .pred p;\n"

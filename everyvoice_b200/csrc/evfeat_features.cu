@@ -139,6 +139,13 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
 
   int tile = blockIdx.x;
   if (tile >= p.n_tiles) return;
+#ifdef EVF_EXP_SKEW
+  {
+    const long long t0 = clock64();
+    while (clock64() - t0 < (long long)(warp >> 2) * EVF_EXP_SKEW) {
+    }
+  }
+#endif
   TileInfo cur = tile_info(tile);
   TileInfo nxt = (tile + (int)gridDim.x < p.n_tiles) ? tile_info(tile + gridDim.x) : cur;
   {
@@ -180,7 +187,8 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
     if (warp * FPJ < nvalid) {
       float re[32], im[32];
       if constexpr (MODE == MODE_PACK2) {
-        // window pairs: s_win holds {w[32*(2q) + lane], w[32*(2q+1) + lane]} at [q][lane] (16 LDS.64)
+        // window pairs: s_win holds {w[32*r + lane], w[32*(r + 16) + lane]} at [r][lane] (16 LDS.64): rows r and
+        // r + 16 are the two inputs of one first-stage butterfly, which absorbs the window multiplication
         const float* xa = s_in + (2 * warp) * hop + lane;
         const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
         if (hop == 256) {
@@ -190,36 +198,35 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
 #pragma unroll
           for (int r = 0; r < 40; ++r) v[r] = xa[32 * r];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float2 w = wv[32 * q];
-            re[2 * q] = w.x * v[2 * q];
-            im[2 * q] = w.x * v[2 * q + 8];
-            re[2 * q + 1] = w.y * v[2 * q + 1];
-            im[2 * q + 1] = w.y * v[2 * q + 9];
+          for (int r = 0; r < 16; ++r) {
+            const float2 w = wv[32 * r];
+            const int i = bitrev5(r);
+            win_head(re[i], re[i + 1], v[r], w.x, v[r + 16], w.y);
+            win_head(im[i], im[i + 1], v[r + 8], w.x, v[r + 24], w.y);
           }
         } else {
           const float* xb = xa + hop;
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float2 w = wv[32 * q];
-            re[2 * q] = w.x * xa[32 * (2 * q)];
-            im[2 * q] = w.x * xb[32 * (2 * q)];
-            re[2 * q + 1] = w.y * xa[32 * (2 * q + 1)];
-            im[2 * q + 1] = w.y * xb[32 * (2 * q + 1)];
+          for (int r = 0; r < 16; ++r) {
+            const float2 w = wv[32 * r];
+            const int i = bitrev5(r);
+            win_head(re[i], re[i + 1], xa[32 * r], w.x, xa[32 * (r + 16)], w.y);
+            win_head(im[i], im[i + 1], xb[32 * r], w.x, xb[32 * (r + 16)], w.y);
           }
         }
       } else {
         const float2* x2 = reinterpret_cast<const float2*>(s_in + warp * hop) + lane;
         const float2* w2 = reinterpret_cast<const float2*>(s_win) + lane;
 #pragma unroll
-        for (int n1 = 0; n1 < 32; ++n1) {
-          float2 w = w2[32 * n1];
-          float2 x = x2[32 * n1];
-          re[n1] = w.x * x.x;
-          im[n1] = w.y * x.y;
+        for (int r = 0; r < 16; ++r) {
+          const float2 wa = w2[32 * r], wb = w2[32 * (r + 16)];
+          const float2 xa = x2[32 * r], xb = x2[32 * (r + 16)];
+          const int i = bitrev5(r);
+          win_head(re[i], re[i + 1], xa.x, wa.x, xb.x, wb.x);
+          win_head(im[i], im[i + 1], xa.y, wa.y, xb.y, wb.y);
         }
       }
-      warp_fft1024(re, im, s_tw4, scr, lane);
+      warp_fft1024_tail(re, im, s_tw4, scr, lane);
 
       // ---- real-FFT separation; the mirrored bin lives in lane (32 - lane) % 32 -------
       const int src_lane = (32 - lane) & 31;
@@ -239,16 +246,16 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
         if (need) {
           float zr, zi, pr, pi;
           if (j < 16) {
-            zr = re[bitrev5(j)];
-            zi = im[bitrev5(j)];
+            zr = re[j];
+            zi = im[j];
             // lane 0 is its own partner, with a different register (bin 32*(32-j) instead of 32*(31-j)+32-lane)
-            const float sr = (lane == 0) ? re[bitrev5((32 - j) & 31)] : re[bitrev5(31 - j)];
-            const float si = (lane == 0) ? im[bitrev5((32 - j) & 31)] : im[bitrev5(31 - j)];
+            const float sr = (lane == 0) ? re[(32 - j) & 31] : re[31 - j];
+            const float si = (lane == 0) ? im[(32 - j) & 31] : im[31 - j];
             pr = __shfl_sync(0xffffffffu, sr, src_lane);
             pi = __shfl_sync(0xffffffffu, si, src_lane);
           } else {  // bin 512 (lane 0 only): its own mirror
-            zr = pr = re[bitrev5(16)];
-            zi = pi = im[bitrev5(16)];
+            zr = pr = re[16];
+            zi = pi = im[16];
           }
           if (j < 16 || lane == 0) {
             if constexpr (MODE == MODE_PACK2) {
@@ -342,7 +349,9 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
       if (tid < nmr.total) s_next[manual_word(nmr, tid)] = mv0;
       if (tid + kThreads < nmr.total) s_next[manual_word(nmr, tid + kThreads)] = mv1;
     }
+#ifndef EVF_EXP_NOSYNC1
     __syncthreads();  // (1) input tile consumed, P tile complete, next tile's manual words visible
+#endif
     if (has_next && nbuf == 1) {
       // single input buffer (large-footprint plans): restage now, overlapping phases B and C
       const ManualRange mr = stage_issue(nxt, s_in, &s_bar[0]);
@@ -417,7 +426,9 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
         }
 #undef EVF_BIN_STEP
       }
+#ifndef EVF_EXP_NOSYNC2
       __syncthreads();  // (2)
+#endif
       // ---- phase C: combine, log, coalesced store of the log-mel rows + per-frame energy ---
       // (32-bit offsets from one row pointer per frame; rows of intervals without bins are never
       // flushed and stay zero, cleared at start)

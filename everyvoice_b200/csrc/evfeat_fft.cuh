@@ -1,12 +1,23 @@
-// In-register radix-2 DIF DFT-32 used by the warp-level 1024-point complex FFT.
+// In-register radix-2 DIT DFT-32 used by the warp-level 1024-point complex FFT.
 //
 // One warp computes one 1024-point complex FFT as 32 x 32 (four-step): every lane holds 32
 // complex values in registers, does a 32-point DFT on them, the warp transposes through
-// shared memory (with the inter-pass twiddle applied), and every lane does a second
-// 32-point DFT.  All loops here are fully unrolled with compile-time indices so the
+// shared memory, and every lane does a second 32-point DFT whose first stage carries the
+// inter-pass twiddle.  All loops here are fully unrolled with compile-time indices so the
 // arrays live in registers and the DFT-32 twiddles fold into immediates.
+//
+// Instruction diet (the kernel is issue bound):
+//   * decimation in time, so every non-trivial butterfly is  a' = a + w*b ;  b' = 2a - a'
+//     = 6 FFMA instead of the 4 FADD + 2 FMUL + 2 FFMA of the decimation-in-frequency form;
+//   * the first stage (twiddle 1) is fused with whatever scales its inputs: the window in the
+//     first pass (3 instead of 4 instructions per real pair), the four-step twiddle in the
+//     second pass (10 instead of 12 per complex pair).
+// The functions are __host__ __device__ so tests/test_fft_host.py can run the exact index
+// arithmetic on the CPU against a double-precision DFT.
 #pragma once
 #include <cuda_runtime.h>
+
+#define EVF_HD __host__ __device__ __forceinline__
 
 namespace evf {
 
@@ -14,9 +25,9 @@ __host__ __device__ constexpr int bitrev5(int x) {
   return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
 }
 
-// cos(2*pi*k/32), sin(2*pi*k/32) for k = 0..8, correctly rounded from fp64.
-__device__ __forceinline__ constexpr float cos32(int k) {
-  switch (k) {
+// cos(2*pi*j/32) and sin(2*pi*j/32), j = 0..16, correctly rounded from fp64.
+EVF_HD constexpr float cos32(int j) {
+  switch (j) {
     case 0: return 1.0f;
     case 1: return 0.98078528040323043f;
     case 2: return 0.92387953251128674f;
@@ -25,79 +36,95 @@ __device__ __forceinline__ constexpr float cos32(int k) {
     case 5: return 0.55557023301960218f;
     case 6: return 0.38268343236508978f;
     case 7: return 0.19509032201612825f;
-    default: return 0.0f;
+    case 8: return 0.0f;
+    default: return -cos32(16 - j);  // 8 < j <= 16
   }
 }
-__device__ __forceinline__ constexpr float sin32(int k) { return cos32(8 - k); }
+EVF_HD constexpr float sin32(int j) { return (j <= 8) ? cos32(8 - j) : cos32(j - 8); }
 
-// (r, i) *= exp(-2*pi*i*K/32) for K in [0, 16)
-template <int K>
-__device__ __forceinline__ void mul_w32(float& r, float& i) {
-  if constexpr (K == 0) {
-    return;
-  } else if constexpr (K == 8) {  // -i
-    float t = r;
-    r = i;
-    i = -t;
-  } else if constexpr (K == 4) {  // (1 - i)/sqrt2
-    float a = (r + i) * 0.70710678118654757f;
-    float b = (i - r) * 0.70710678118654757f;
-    r = a;
-    i = b;
-  } else if constexpr (K == 12) {  // (-1 - i)/sqrt2
-    float a = (i - r) * 0.70710678118654757f;
-    float b = -(r + i) * 0.70710678118654757f;
-    r = a;
-    i = b;
-  } else if constexpr (K < 8) {
-    constexpr float c = cos32(K), s = sin32(K);  // w = c - i s
-    float a = fmaf(i, s, r * c);
-    float b = fmaf(-r, s, i * c);
-    r = a;
-    i = b;
-  } else {  // 8 < K < 16: w = -sin32(K-8) - i cos32(K-8)
-    constexpr float c = cos32(K - 8), s = sin32(K - 8);
-    float a = fmaf(i, c, -r * s);
-    float b = fmaf(-r, c, -i * s);
-    r = a;
-    i = b;
+// One DIT butterfly on (a, b) with w = exp(-2*pi*i*J/32):  a' = a + w b,  b' = a - w b.
+template <int J>
+EVF_HD void bfly_dit(float& ar, float& ai, float& br, float& bi) {
+  if constexpr (J == 0) {
+    const float xr = ar + br, xi = ai + bi;
+    br = ar - br;
+    bi = ai - bi;
+    ar = xr;
+    ai = xi;
+  } else if constexpr (J == 8) {  // w = -i:  w b = (bi, -br)
+    const float xr = ar + bi, xi = ai - br;
+    const float yr = ar - bi, yi = ai + br;
+    ar = xr;
+    ai = xi;
+    br = yr;
+    bi = yi;
+  } else {  // w = c - i s:  w b = (br c + bi s) + i (bi c - br s)
+    constexpr float c = cos32(J), s = sin32(J);
+    const float xr = fmaf(br, c, fmaf(bi, s, ar));
+    const float xi = fmaf(bi, c, fmaf(-br, s, ai));
+    br = fmaf(2.0f, ar, -xr);
+    bi = fmaf(2.0f, ai, -xi);
+    ar = xr;
+    ai = xi;
   }
 }
 
 template <int HALF, int G, int J>
-__device__ __forceinline__ void bfly(float (&re)[32], float (&im)[32]) {
-  constexpr int a = G + J, b = G + J + HALF;
-  float sr = re[a] + re[b], si = im[a] + im[b];
-  float dr = re[a] - re[b], di = im[a] - im[b];
-  mul_w32<J*(16 / HALF)>(dr, di);
-  re[a] = sr;
-  im[a] = si;
-  re[b] = dr;
-  im[b] = di;
-}
-
-template <int HALF, int G, int J>
-struct BflyLoop {
-  __device__ __forceinline__ static void run(float (&re)[32], float (&im)[32]) {
-    bfly<HALF, G, J>(re, im);
-    if constexpr (J + 1 < HALF) BflyLoop<HALF, G, J + 1>::run(re, im);
+struct DitJ {
+  EVF_HD static void run(float (&re)[32], float (&im)[32]) {
+    bfly_dit<J*(16 / HALF)>(re[G + J], im[G + J], re[G + J + HALF], im[G + J + HALF]);
+    if constexpr (J + 1 < HALF) DitJ<HALF, G, J + 1>::run(re, im);
   }
 };
 template <int HALF, int G>
-struct GroupLoop {
-  __device__ __forceinline__ static void run(float (&re)[32], float (&im)[32]) {
-    BflyLoop<HALF, G, 0>::run(re, im);
-    if constexpr (G + 2 * HALF < 32) GroupLoop<HALF, G + 2 * HALF>::run(re, im);
+struct DitG {
+  EVF_HD static void run(float (&re)[32], float (&im)[32]) {
+    DitJ<HALF, G, 0>::run(re, im);
+    if constexpr (G + 2 * HALF < 32) DitG<HALF, G + 2 * HALF>::run(re, im);
   }
 };
 
-// Forward DFT-32, decimation in frequency, in place.  X[k] ends up at index bitrev5(k).
-__device__ __forceinline__ void dft32_dif(float (&re)[32], float (&im)[32]) {
-  GroupLoop<16, 0>::run(re, im);
-  GroupLoop<8, 0>::run(re, im);
-  GroupLoop<4, 0>::run(re, im);
-  GroupLoop<2, 0>::run(re, im);
-  GroupLoop<1, 0>::run(re, im);
+// Stages 2..5 of the forward DIT DFT-32 (butterfly spans 2, 4, 8, 16), in place.
+// In : index i holds the output of the span-1 stage for the pair it belongs to, where the
+//      span-1 stage combined x[bitrev5(i & ~1)] (= some n < 16) and x[n + 16].
+// Out: index k holds X[k] (natural order).
+EVF_HD void dft32_dit_tail(float (&re)[32], float (&im)[32]) {
+  DitG<2, 0>::run(re, im);
+  DitG<4, 0>::run(re, im);
+  DitG<8, 0>::run(re, im);
+  DitG<16, 0>::run(re, im);
+}
+
+// Plain first stage (span 1, twiddle 1) for callers without anything to fuse into it.
+// In: index i holds x[bitrev5(i)].
+EVF_HD void dft32_dit_head(float (&re)[32], float (&im)[32]) { DitG<1, 0>::run(re, im); }
+
+// First stage fused with a real scaling of the inputs (the analysis window): the pair at
+// indices (i, i + 1), i even, combines rows n = bitrev5(i) < 16 and n + 16:
+//   out[i] = wa*xa + wb*xb ,  out[i + 1] = wa*xa - wb*xb          (3 instructions)
+EVF_HD void win_head(float& lo, float& hi, float xa, float wa, float xb, float wb) {
+  const float t = wa * xa;
+  lo = fmaf(wb, xb, t);
+  hi = fmaf(-wb, xb, t);
+}
+
+// First stage fused with a complex scaling (the four-step twiddles ta, tb = (cos, sin) of a
+// negative angle, i.e. t = c + i s with s <= 0 for the forward transform):
+//   A = ta*xa ;  out[i] = A + tb*xb ;  out[i + 1] = 2A - out[i]      (10 instructions)
+template <bool kUnitA>
+EVF_HD void tw_head(float& lor, float& loi, float& hir, float& hii, float xar, float xai, float tac,
+                    float tas, float xbr, float xbi, float tbc, float tbs) {
+  float Ar = xar, Ai = xai;
+  if constexpr (!kUnitA) {
+    Ar = fmaf(-xai, tas, xar * tac);
+    Ai = fmaf(xar, tas, xai * tac);
+  }
+  const float pr = fmaf(xbr, tbc, fmaf(-xbi, tbs, Ar));
+  const float pi = fmaf(xbr, tbs, fmaf(xbi, tbc, Ai));
+  hir = fmaf(2.0f, Ar, -pr);
+  hii = fmaf(2.0f, Ai, -pi);
+  lor = pr;
+  loi = pi;
 }
 
 }  // namespace evf

@@ -40,8 +40,8 @@ struct FeatParams {
   float* spec_out;
   float* energy_out;
   // plan tables (global memory; copied to shared memory once per CTA)
-  const float* window;   // [n_fft], pre-scaled by 0.5; n_fft 1024: stored as pairs {w[64q + lane], w[64q + 32 + lane]} at [q][lane]
-  const float4* tw4;     // [16][32] inter-pass twiddles {t[2q][lane], t[2q+1][lane]}, t indexed by register position
+  const float* window;   // [n_fft], pre-scaled by 0.5; n_fft 1024: stored as pairs {w[32r + lane], w[32(r+16) + lane]} at [r][lane], r < 16
+  const float4* tw4;     // [16][32] four-step twiddles {t[n][lane], t[n+16][lane]}, t[n2][k1] = W_1024^(n2*k1)
   const float2* wpost;   // MODE_HALF: exp(-2 pi i k / n_fft), k = 0..512
   const float4* melw4;   // [k_used] {rising weight -> mel j(k), falling weight -> mel j(k)-1, j(k), j(k+1)} (ints as bits)
   const int* vw_k;       // [n_vw + 1] bin range of every worker of the projection phase (interval aligned)

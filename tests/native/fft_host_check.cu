@@ -1,0 +1,100 @@
+// Host-side check of the index arithmetic of the warp-level 1024-point FFT (evfeat_fft.cuh):
+// the 32 lanes of a warp are simulated one after the other, the shared-memory transpose is a
+// plain array, and the result is compared with a double-precision DFT.  Test infrastructure
+// (built and run by tests/test_fft_host.py with nvcc; no GPU needed).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "evfeat_fft.cuh"
+
+using namespace evf;
+
+int main() {
+  const int N = 1024;
+  std::vector<double> xr(N), xi(N), w(N);
+  srand(1234);
+  for (int n = 0; n < N; ++n) {
+    xr[n] = rand() / (double)RAND_MAX * 2 - 1;
+    xi[n] = rand() / (double)RAND_MAX * 2 - 1;
+    w[n] = 0.5 - 0.5 * std::cos(2 * M_PI * n / N);
+  }
+  // pass 1, lane = n2: rows n1 of z[32*n1 + n2], window fused into the first stage
+  static float Yr[32][32], Yi[32][32];  // [k1][n2]
+  for (int lane = 0; lane < 32; ++lane) {
+    float re[32], im[32];
+    for (int r = 0; r < 16; ++r) {
+      const int i = bitrev5(r);
+      const int na = 32 * r + lane, nb = 32 * (r + 16) + lane;
+      win_head(re[i], re[i + 1], (float)xr[na], (float)w[na], (float)xr[nb], (float)w[nb]);
+      win_head(im[i], im[i + 1], (float)xi[na], (float)w[na], (float)xi[nb], (float)w[nb]);
+    }
+    dft32_dit_tail(re, im);
+    for (int p = 0; p < 32; ++p) {
+      Yr[p][lane] = re[p];
+      Yi[p][lane] = im[p];
+    }
+  }
+  // pass 2, lane = k1
+  std::vector<double> Zr(N), Zi(N);
+  for (int lane = 0; lane < 32; ++lane) {
+    float re[32], im[32], tr[32], ti[32];
+    for (int n2 = 0; n2 < 32; ++n2) {
+      tr[n2] = Yr[lane][n2];
+      ti[n2] = Yi[lane][n2];
+    }
+    for (int n = 0; n < 16; ++n) {
+      float c[2], s[2];
+      for (int h = 0; h < 2; ++h) {
+        const double ang = -2 * M_PI * ((lane * (n + 16 * h)) % N) / N;
+        c[h] = (float)std::cos(ang);
+        s[h] = (float)std::sin(ang);
+      }
+      const int i = bitrev5(n);
+      if (n == 0)
+        tw_head<true>(re[i], im[i], re[i + 1], im[i + 1], tr[n], ti[n], c[0], s[0], tr[n + 16], ti[n + 16], c[1], s[1]);
+      else
+        tw_head<false>(re[i], im[i], re[i + 1], im[i + 1], tr[n], ti[n], c[0], s[0], tr[n + 16], ti[n + 16], c[1], s[1]);
+    }
+    dft32_dit_tail(re, im);
+    for (int k2 = 0; k2 < 32; ++k2) {
+      Zr[lane + 32 * k2] = re[k2];
+      Zi[lane + 32 * k2] = im[k2];
+    }
+  }
+  // plain DFT-32 through head + tail as well
+  double worst32 = 0;
+  {
+    float re[32], im[32];
+    for (int i = 0; i < 32; ++i) {
+      re[i] = (float)xr[bitrev5(i)];
+      im[i] = (float)xi[bitrev5(i)];
+    }
+    dft32_dit_head(re, im);
+    dft32_dit_tail(re, im);
+    for (int k = 0; k < 32; ++k) {
+      double ar = 0, ai = 0;
+      for (int n = 0; n < 32; ++n) {
+        const double a = -2 * M_PI * k * n / 32;
+        ar += xr[n] * std::cos(a) - xi[n] * std::sin(a);
+        ai += xr[n] * std::sin(a) + xi[n] * std::cos(a);
+      }
+      worst32 = std::fmax(worst32, std::fmax(std::fabs(ar - re[k]), std::fabs(ai - im[k])));
+    }
+  }
+  double worst = 0, scale = 0;
+  for (int k = 0; k < N; ++k) {
+    double ar = 0, ai = 0;
+    for (int n = 0; n < N; ++n) {
+      const double a = -2 * M_PI * ((long long)k * n % N) / N;
+      const double vr = xr[n] * w[n], vi = xi[n] * w[n];
+      ar += vr * std::cos(a) - vi * std::sin(a);
+      ai += vr * std::sin(a) + vi * std::cos(a);
+    }
+    worst = std::fmax(worst, std::fmax(std::fabs(ar - Zr[k]), std::fabs(ai - Zi[k])));
+    scale = std::fmax(scale, std::hypot(ar, ai));
+  }
+  printf("dft32 max abs err %.3e ; fft1024 max abs err %.3e (max |Z| %.3f)\n", worst32, worst, scale);
+  return (worst32 < 2e-5 && worst < 2e-4 * (scale / 30 + 1)) ? 0 : 1;
+}
