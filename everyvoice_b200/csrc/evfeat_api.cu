@@ -24,8 +24,9 @@ struct evf_plan {
   float* d_window = nullptr;
   float4* d_tw4 = nullptr;
   float2* d_wpost = nullptr;
-  float4* d_melw4 = nullptr;
-  int* d_vwk = nullptr;
+  float2* d_wtab = nullptr;
+  unsigned* d_gtab = nullptr;
+  unsigned* d_ltab = nullptr;
 };
 
 struct evf_batch {
@@ -79,7 +80,7 @@ int upload(const std::vector<T>& h, T** d) {
 // Compress a dense [n_freq][n_mels] triangular filterbank: every frequency bin lies in
 // exactly one interval between adjacent filter centres, so it feeds at most two adjacent
 // filters.  j(k) = interval index (monotone in k); a[k] = fb[k][j], b[k] = fb[k][j-1].
-int compress_filterbank(const float* fb, int n_freq, int n_mels, int n_vw, PlanTables* t) {
+int compress_filterbank(const float* fb, int n_freq, int n_mels, PlanTables* t) {
   std::vector<int> jk(n_freq, 0);
   std::vector<float2> w(n_freq, make_float2(0.f, 0.f));
   int j_prev = 0, k_used = 0;
@@ -88,8 +89,8 @@ int compress_filterbank(const float* fb, int n_freq, int n_mels, int n_vw, PlanT
     int nz[3], cnt = 0;
     for (int m = 0; m < n_mels; ++m) {
       if (row[m] != 0.0f) {
-        if (!(row[m] == row[m]) || std::isinf(row[m])) {
-          set_error("mel filterbank contains NaN/Inf");
+        if (!(row[m] == row[m]) || std::isinf(row[m]) || row[m] < 0.0f) {
+          set_error("mel filterbank contains NaN/Inf or a negative weight");
           return EVF_ERR_FILTERBANK;
         }
         if (cnt < 3) nz[cnt] = m;
@@ -134,39 +135,70 @@ int compress_filterbank(const float* fb, int n_freq, int n_mels, int n_vw, PlanT
   }
   t->jk.assign(jk.begin(), jk.begin() + k_used);
   t->jk.push_back(-1);  // sentinel: the last bin always ends its interval
-  t->melw4.resize(k_used);
-  for (int k = 0; k < k_used; ++k) {
-    float jz, jw;
-    const int j0 = t->jk[k], j1 = t->jk[k + 1];
-    memcpy(&jz, &j0, 4);
-    memcpy(&jw, &j1, 4);
-    t->melw4[k] = make_float4(w[k].x, w[k].y, jz, jw);
-  }
-  // Split the bins over the projection workers: contiguous runs of whole intervals with the
-  // largest run as small as possible (binary search on the cap, greedy feasibility check).
-  // Interval j owns bins [kstart[j], kstart[j + 1]), j = 0 .. n_mels.
+  return EVF_OK;
+}
+
+// Tables of the per-warp mel walk (evfeat_features.cu, "mel").  Interval j (between filter centres
+// j - 1 and j) owns bins [kstart[j], kstart[j + 1]); its rising sums feed filter j, its falling
+// sums filter j - 1.  Lane l walks bins [n * l, n * l + n) with n odd.
+//   slots    : one per non-empty interval (dense ordinal q[j]), then 32 head slots (one per lane,
+//              for the partial of an interval that an earlier lane started), then one zero slot
+//   wtab     : per (i, lane) the two weights of bin n * lane + i; the sign bit of the rising weight
+//              says "flush after this bin" (last bin of an interval, of the chunk, or of all bins)
+//   ltab     : per lane the slot of its first flush and of its second (later ones are consecutive)
+//   gtab     : per filter m and c = 0 .. n_heads: (slot of the c-th partial of interval m) |
+//              (slot of the c-th partial of interval m + 1) << 16, the zero slot where there is none
+int build_walk_tables(int n_mels, PlanTables* t) {
+  const int k_used = t->k_used;
+  int n = (k_used + 31) / 32;
+  if (n < 1) n = 1;
+  if ((n & 1) == 0) ++n;
+  t->n_chunk = n;
   const int n_int = n_mels + 1;
-  auto feasible = [&](int cap, std::vector<int>* cuts) {
-    int j = 0;
-    if (cuts) cuts->assign(n_vw + 1, k_used);
-    if (cuts) (*cuts)[0] = 0;
-    for (int v = 0; v < n_vw && j < n_int; ++v) {
-      const int k0 = t->kstart[j];
-      int e = j + 1;
-      if (t->kstart[e] - k0 > cap) return false;
-      while (e < n_int && t->kstart[e + 1] - k0 <= cap) ++e;
-      j = e;
-      if (cuts) (*cuts)[v + 1] = t->kstart[j];
-    }
-    return j >= n_int;
-  };
-  int lo = 1, hi = k_used;
-  while (lo < hi) {
-    const int mid = (lo + hi) / 2;
-    if (feasible(mid, nullptr)) hi = mid; else lo = mid + 1;
+  std::vector<int> q(n_int, -1);
+  int Q = 0;
+  for (int j = 0; j < n_int; ++j)
+    if (t->kstart[j] < t->kstart[j + 1]) q[j] = Q++;
+  const int head0 = Q, zero = Q + 32;
+  t->n_slots = Q + 33;
+  if (t->n_slots > 0xffff) {
+    set_error("mel filterbank has too many filters");
+    return EVF_ERR_FILTERBANK;
   }
-  feasible(lo, &t->vw_k);
-  t->vw_k[n_vw] = k_used;
+  t->wtab.assign((size_t)n * 32, make_float2(0.f, 0.f));
+  for (int l = 0; l < 32; ++l)
+    for (int i = 0; i < n; ++i) {
+      const int k = n * l + i;
+      if (k >= k_used) continue;
+      float2 w = t->melw[k];
+      const bool flush = (i == n - 1) || (k == k_used - 1) || (t->jk[k + 1] != t->jk[k]);
+      if (flush) w.x = -w.x;  // weights are >= 0 (checked above); -0.0f carries the flag for a zero weight
+      t->wtab[(size_t)i * 32 + l] = w;
+    }
+  t->ltab.assign(32, (unsigned)zero | ((unsigned)zero << 16));
+  std::vector<std::vector<int>> parts(n_int);  // slots that sum to interval j, in lane order
+  for (int j = 0; j < n_int; ++j)
+    if (q[j] >= 0) parts[j].push_back(q[j]);
+  for (int l = 0; l < 32; ++l) {
+    const int k0 = n * l;
+    if (k0 >= k_used) break;
+    const int j0 = t->jk[k0];
+    const bool cont = k0 > t->kstart[j0];
+    const int d0 = cont ? head0 + l : q[j0];
+    t->ltab[l] = (unsigned)d0 | ((unsigned)(q[j0] + 1) << 16);
+    if (cont) parts[j0].push_back(head0 + l);
+  }
+  size_t most = 1;
+  for (int j = 0; j < n_int; ++j) most = parts[j].size() > most ? parts[j].size() : most;
+  t->n_heads = (int)most - 1;
+  t->m_pad = (n_mels + 31) & ~31;
+  t->gtab.assign((size_t)(t->n_heads + 1) * t->m_pad, (unsigned)zero | ((unsigned)zero << 16));
+  for (int m = 0; m < n_mels; ++m)
+    for (int c = 0; c <= t->n_heads; ++c) {
+      const unsigned r = c < (int)parts[m].size() ? parts[m][c] : zero;
+      const unsigned f = c < (int)parts[m + 1].size() ? parts[m + 1][c] : zero;
+      t->gtab[(size_t)c * t->m_pad + m] = r | (f << 16);
+    }
   return EVF_OK;
 }
 
@@ -174,8 +206,9 @@ void free_plan_tables(evf_plan* p) {
   cudaFree(p->d_window);
   cudaFree(p->d_tw4);
   cudaFree(p->d_wpost);
-  cudaFree(p->d_melw4);
-  cudaFree(p->d_vwk);
+  cudaFree(p->d_wtab);
+  cudaFree(p->d_gtab);
+  cudaFree(p->d_ltab);
 }
 
 }  // namespace
@@ -247,11 +280,7 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   p->device = device;
   p->mode = (cfg->n_fft == 1024) ? MODE_PACK2 : MODE_HALF;
   p->n_freq = cfg->n_fft / 2 + 1;
-  {
-    // CTA shape: 16 warps x 1 CTA/SM (default, measured faster) or 8 warps x 2 CTAs/SM (EVF_WARPS=8)
-    const char* e = getenv("EVF_WARPS");
-    p->warps = (e && atoi(e) == 8) ? 8 : 16;
-  }
+  p->warps = kMaxWarps;  // one 16-warp CTA per SM
   p->frames_per_tile = p->warps * (p->mode == MODE_PACK2 ? 2 : 1);
   p->num_sms = prop.multiProcessorCount;
   p->row_floats = mel ? cfg->n_mels : (cfg->spec_type == EVF_SPEC_RAW ? 2 * p->n_freq : p->n_freq);
@@ -294,41 +323,24 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   }
   int rc = EVF_OK;
   if (mel) {
-    const int n_vw = p->warps * (32 / p->frames_per_tile);
-    rc = compress_filterbank(mel_fb_host, p->n_freq, cfg->n_mels, n_vw, &t);
+    rc = compress_filterbank(mel_fb_host, p->n_freq, cfg->n_mels, &t);
+    if (rc == EVF_OK) rc = build_walk_tables(cfg->n_mels, &t);
     if (rc != EVF_OK) { delete p; return rc; }
     p->k_used = t.k_used;
   }
-  p->smem_bytes = features_smem_bytes(p->mode, cfg->spec_type, p->warps, cfg->hop_length, cfg->n_fft,
-                                      cfg->n_mels, p->k_used, &p->carve);
-  if (p->mode == MODE_HALF && (p->smem_bytes < 0 || p->carve.nbuf < 2)) {
-    // no room to stage the post-twiddles next to two input buffers: read them through L1 instead
-    evf::FeatParams alt{};
-    const int b = features_smem_bytes(MODE_HALF_L1, cfg->spec_type, p->warps, cfg->hop_length, cfg->n_fft,
-                                      cfg->n_mels, p->k_used, &alt);
-    if (b >= 0 && (p->smem_bytes < 0 || alt.nbuf > p->carve.nbuf)) {
-      p->mode = MODE_HALF_L1;
-      p->smem_bytes = b;
-      p->carve = alt;
-    }
-  }
-  if (p->smem_bytes < 0 && p->warps == 8) {  // does not fit twice per SM: one 16-warp CTA per SM
-    p->warps = 16;
-    p->frames_per_tile = p->warps * (p->mode == MODE_PACK2 ? 2 : 1);
-    p->smem_bytes = features_smem_bytes(p->mode, cfg->spec_type, p->warps, cfg->hop_length, cfg->n_fft,
-                                        cfg->n_mels, p->k_used, &p->carve);
-  }
+  p->smem_bytes = features_smem_bytes(p->mode, cfg->spec_type, p->warps, cfg->hop_length, cfg->n_fft, t, &p->carve);
   if (p->smem_bytes < 0) {
     delete p;
     set_error("evf_plan_create: this n_fft / hop_length / n_mels combination needs more than 227 KB of shared memory per CTA");
     return EVF_ERR_UNSUPPORTED;
   }
-  rc = features_configure(p->mode, cfg->spec_type, cfg->sample_format, p->warps, p->smem_bytes);
+  rc = features_configure(p->mode, cfg->spec_type, cfg->sample_format, p->smem_bytes);
   if (rc == EVF_OK) rc = upload(t.window, &p->d_window);
   if (rc == EVF_OK) rc = upload(t.tw4, &p->d_tw4);
   if (rc == EVF_OK) rc = upload(t.wpost, &p->d_wpost);
-  if (rc == EVF_OK) rc = upload(t.melw4, &p->d_melw4);
-  if (rc == EVF_OK) rc = upload(t.vw_k, &p->d_vwk);
+  if (rc == EVF_OK) rc = upload(t.wtab, &p->d_wtab);
+  if (rc == EVF_OK) rc = upload(t.gtab, &p->d_gtab);
+  if (rc == EVF_OK) rc = upload(t.ltab, &p->d_ltab);
   if (rc != EVF_OK) {
     free_plan_tables(p);
     delete p;
@@ -485,8 +497,9 @@ static int features_run_tiles(const evf_plan* plan, const evf_batch* batch, int 
   p.window = plan->d_window;
   p.tw4 = plan->d_tw4;
   p.wpost = plan->d_wpost;
-  p.melw4 = plan->d_melw4;
-  p.vw_k = plan->d_vwk;
+  p.wtab = plan->d_wtab;
+  p.gtab = plan->d_gtab;
+  p.ltab = plan->d_ltab;
   p.hop = plan->cfg.hop_length;
   p.n_mels = plan->cfg.n_mels;
   p.n_freq = plan->n_freq;
@@ -494,10 +507,9 @@ static int features_run_tiles(const evf_plan* plan, const evf_batch* batch, int 
   p.row_floats = plan->row_floats;
   p.apply_log = (plan->cfg.spec_type == EVF_SPEC_RAW) ? 0 : plan->cfg.apply_log;
   p.log_clip = plan->cfg.log_clip;
-  const int max_ctas = plan->num_sms * (16 / plan->warps);
-  const int grid = p.n_tiles < max_ctas ? p.n_tiles : max_ctas;
-  return features_launch(plan->mode, plan->cfg.spec_type, plan->cfg.sample_format, plan->warps, p, grid,
-                         plan->smem_bytes, static_cast<cudaStream_t>(stream));
+  const int grid = p.n_tiles < plan->num_sms ? p.n_tiles : plan->num_sms;
+  return features_launch(plan->mode, plan->cfg.spec_type, plan->cfg.sample_format, p, grid, plan->smem_bytes,
+                         static_cast<cudaStream_t>(stream));
 }
 
 int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* samples_dev,

@@ -11,18 +11,23 @@ template <>
 struct ModeTraits<MODE_PACK2> {
   static constexpr int kNfft = 1024;
   static constexpr int kFramesPerJob = 2;
+  using SlotT = float4;  // partial sums {rising a, rising b, falling a, falling b} of the two frames of a job
 };
 template <>
 struct ModeTraits<MODE_HALF> {
   static constexpr int kNfft = 2048;
   static constexpr int kFramesPerJob = 1;
+  using SlotT = float2;  // {rising, falling}
 };
-template <>
-struct ModeTraits<MODE_HALF_L1> : ModeTraits<MODE_HALF> {};
 
-__device__ __forceinline__ float load_sample(const float* p, long long i) { return __ldg(p + i); }
-__device__ __forceinline__ float load_sample(const short* p, long long i) {
-  return (float)__ldg(p + i) * (1.0f / 32768.0f);
+// Staged samples are kept in their input format (the bulk copy cannot convert); int16 PCM becomes
+// s / 32768 when it is loaded into registers, exactly what torchaudio.load yields for a PCM16 wav.
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(short v) { return (float)v * (1.0f / 32768.0f); }
+__device__ __forceinline__ float2 load_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 load_pair(const short* p) {
+  const short2 v = *reinterpret_cast<const short2*>(p);
+  return make_float2(to_float(v.x), to_float(v.y));
 }
 
 // log(max(v, clip)) as one MUFU.LG2 + one FMUL.  The plan guarantees clip >= FLT_MIN whenever
@@ -134,6 +139,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy
+// (bulk copy) accesses to the same locations.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // global -> shared bulk copy (SASS: UBLKCP); completion is signalled on the mbarrier.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -11,19 +11,30 @@
 //   grid   : persistent, one CTA of 16 warps per SM, static round-robin over frame tiles
 //   tile   : 16 FFT jobs of one utterance = 32 consecutive frames (n_fft 1024: two real
 //            frames ride as re/im of one complex FFT) or 16 frames (n_fft 2048: one frame
-//            = 1024 complex points + real-FFT split)
-//   phase 0: the tile's sample span ((FR-1)*hop + n_fft samples; every sample is read from
-//            HBM once, the 4x frame overlap is served from shared memory) is staged with
-//            reflect padding resolved by index mirroring at the utterance edges
-//   phase A: one warp per FFT job: window * samples -> registers, 32x32 four-step FFT
-//            (in-register radix-2 DFT-32, transpose + twiddle through shared memory),
-//            real-FFT separation with the mirrored bin fetched by warp shuffle, |X|^2
-//            (or sqrt(|X|^2+1e-9) for mel-librosa) -> shared P[bin][frame];
+//            = 1024 complex points + real-FFT split); warp w owns job w of every tile
+//   ring   : the tile's sample span ((FR-1)*hop + n_fft samples; every sample leaves HBM once,
+//            the 4x frame overlap is served from shared memory) is fetched with cp.async.bulk
+//            (TMA 1-D) into a ring of input buffers; "full" is an mbarrier per buffer, "empty"
+//            is a counter: a warp releases the buffer as soon as its samples sit in registers
+//            (before the FFT), and the LAST warp to release refills it with the tile after
+//            next (reflect padding at the utterance edges = index mirroring on the few margin
+//            words, by that warp).  There is NO block-wide barrier in the steady state: the
+//            16 warps drift apart, so one warp's shared-memory phases (sample loads, the
+//            transpose, the mel walk) overlap the FMA-bound butterflies of the others.
+//   job    : window * samples -> registers, 32x32 four-step FFT (in-register radix-2 DFT-32,
+//            transpose + twiddle through the warp's private scratch), real-FFT separation with
+//            the mirrored bin fetched by warp shuffle, |X|^2 (or sqrt(|X|^2+1e-9) for
+//            mel-librosa) -> the warp's private P column (aliases the transpose scratch);
 //            linear / raw write straight to HBM (lanes = consecutive bins, coalesced)
-//   phase B: mel projection with lane = frame: all lanes walk the same bins, weights are
-//            warp-uniform; each bin lies between two adjacent filter centres so it feeds
-//            exactly two filters: two running FMAs per bin, no atomics, no divergence
-//   phase C: log-mel tile -> HBM (coalesced rows) + per-frame energy = sqrt(sum log^2)
+//   mel    : per warp, no cross-warp traffic.  Every bin lies between two adjacent filter
+//            centres, so it feeds exactly two filters.  Step 1 (lane = bin chunk): lane l walks
+//            bins [n*l, n*l + n), n odd so that the 32 lanes read 32 distinct banks, two running
+//            FMAs per bin and frame; when the interval between two centres ends the sums are
+//            flushed to a slot (the lane that starts an interval owns its slot, a lane whose
+//            chunk begins inside an interval flushes that first partial to its head slot).
+//            Step 2 (lane = filter): mel[m] = rising partials of interval m + falling partials
+//            of interval m + 1, gathered in a fixed order through a host-built slot list, then
+//            log(max(., clip)), coalesced row stores and the per-frame energy sqrt(sum log^2).
 #include "evfeat_fft.cuh"
 #include "evfeat_internal.h"
 
@@ -35,64 +46,61 @@ namespace {
 
 using TileInfo = TileDesc;  // host-built, 32 bytes, one per tile (evfeat_internal.h)
 
-// The manual (non-bulk) part of a tile: tile words [0, a_lo) and [a_hi, span).
-struct ManualRange {
-  int a_lo, a_hi, total;
-};
-
 template <int MODE, int SPEC, typename SampleT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const FeatParams p) {
+__global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParams p) {
   using MT = ModeTraits<MODE>;
   constexpr int kThreads = WARPS * 32;
   constexpr int NFFT = MT::kNfft;
   constexpr int FPJ = MT::kFramesPerJob;
-  constexpr int FR = WARPS * FPJ;         // frames per tile
-  constexpr int FS = FR + 1;              // padded frame stride of the P tile
-  constexpr int PARTS = 32 / FR;          // projection workers per warp
   constexpr bool kMel = (SPEC == EVF_SPEC_MEL || SPEC == EVF_SPEC_MEL_LIBROSA);
-  constexpr bool kBulk = sizeof(SampleT) == 4;  // float samples can be bulk-copied as they are
   constexpr bool kHalf = (MODE != MODE_PACK2);          // n_fft 2048: one frame per FFT + real-FFT split
-  constexpr bool kStageWpost = (MODE == MODE_HALF);     // MODE_HALF_L1: post-twiddles read through L1
+  constexpr int kAlign = 16 / (int)sizeof(SampleT);     // samples per 16 bytes (bulk-copy granularity)
+  using SlotT = typename MT::SlotT;                      // {rise a, rise b, fall a, fall b} or {rise, fall}
 
   extern __shared__ __align__(16) float smem[];
   float* s_win = smem + p.off_win;
   float4* s_tw4 = reinterpret_cast<float4*>(smem + p.off_tw);
   const float2* s_wpost = reinterpret_cast<const float2*>(smem + p.off_wpost);
-  float4* s_mw4 = reinterpret_cast<float4*>(smem + p.off_melw);
-  int* s_vwk = reinterpret_cast<int*>(smem + p.off_vwk);
-  float* s_p = smem + p.off_p;
-  float* s_sa = smem + p.off_sa;
-  float* s_sb = smem + p.off_sb;
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  const float2* s_wtab = reinterpret_cast<const float2*>(smem + p.off_wtab);
+  const unsigned* s_gtab = reinterpret_cast<const unsigned*>(smem + p.off_gtab);
+  const unsigned* s_ltab = reinterpret_cast<const unsigned*>(smem + p.off_ltab);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);  // full[0], full[1]
+  int* s_cnt = reinterpret_cast<int*>(smem + p.off_bar + 4);         // released-by counters
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  float* scr = smem + p.off_scr + warp * (32 * kScrStride);
+  float* scr = smem + p.off_warp + warp * p.warp_words;  // transpose scratch; the P column aliases it
+  SlotT* slots = reinterpret_cast<SlotT*>(scr + 32 * kScrStride);
   const int nbuf = p.nbuf;
 
-  // ---- one-time setup: mbarriers + table copy --------------------------------------------
+  // ---- one-time setup: mbarriers, tables, zeroed scratch / slots ---------------------------
   if (tid == 0) {
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
+    s_cnt[0] = 0;
+    s_cnt[1] = 0;
     fence_mbar_init();
   }
   for (int i = tid; i < NFFT; i += kThreads) s_win[i] = p.window[i];
   for (int i = tid; i < kFftSize / 2; i += kThreads) s_tw4[i] = p.tw4[i];
-  if constexpr (kStageWpost) {
+  if constexpr (kHalf) {
     for (int i = tid; i <= 512; i += kThreads) reinterpret_cast<float2*>(smem + p.off_wpost)[i] = p.wpost[i];
   }
   if constexpr (kMel) {
-    for (int i = tid; i < p.k_used; i += kThreads) s_mw4[i] = p.melw4[i];
-    for (int i = tid; i < WARPS * PARTS + 1; i += kThreads) s_vwk[i] = p.vw_k[i];
-    for (int i = tid; i < 2 * (p.n_mels + 1) * FS; i += kThreads) s_sa[i] = 0.f;  // SA and SB are adjacent
+    for (int i = tid; i < p.n_chunk * 32; i += kThreads) reinterpret_cast<float2*>(smem + p.off_wtab)[i] = p.wtab[i];
+    for (int i = tid; i < (p.n_heads + 1) * p.m_pad; i += kThreads)
+      reinterpret_cast<unsigned*>(smem + p.off_gtab)[i] = p.gtab[i];
+    if (tid < 32) reinterpret_cast<unsigned*>(smem + p.off_ltab)[tid] = p.ltab[tid];
   }
-  __syncthreads();
+  // pad words of the scratch and never-flushed slots (empty intervals, the zero slot) stay zero
+  for (int i = tid; i < WARPS * p.warp_words; i += kThreads) smem[p.off_warp + i] = 0.f;
 
   const int hop = p.hop;
   const SampleT* __restrict__ samples = static_cast<const SampleT*>(p.samples);
+  const int G = gridDim.x;
 
-  // Tile descriptors are host-built (no dependent loads) and fetched one iteration ahead.
+  // Tile descriptors are host-built (no dependent loads) and fetched two tiles ahead.
   auto tile_info = [&](int tile) {
     const int4* q = reinterpret_cast<const int4*>(p.tiles + tile);
     const int4 a = __ldg(q), b = __ldg(q + 1);
@@ -106,97 +114,78 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
     return ti;
   };
 
-  // Issue the staging of a tile into `buf`: one bulk copy for the 16-byte aligned in-range part
-  // (thread 0), the rest (reflected margins, unaligned / int16 input) is left to the caller.
-  auto stage_issue = [&](const TileInfo& ti, float* buf, uint64_t* bar) {
-    ManualRange mr;
+  // Stage one tile into `buf`.  NT threads (a warp in the steady state, the CTA in the prologue)
+  // store the words the bulk copy cannot take -- reflected margins, a 16-byte-misaligned span --
+  // then `leader` arms the mbarrier and issues one bulk copy for the aligned in-range part.
+  // The caller orders the manual stores before the leader's arrive (__syncwarp / __syncthreads).
+  auto stage_manual = [&](const TileInfo& ti, SampleT* buf, int t, int nt, int& a_lo, int& a_hi) {
     const int lo = max(0, -ti.start);                 // first tile word inside the utterance
     const int hi = min(ti.span, ti.L - ti.start);     // one past the last
-    mr.a_lo = lo;
-    mr.a_hi = lo;
-    if constexpr (kBulk) {
-      // tile word i <-> packed sample s_off + start + i ; both sides must be 16-byte aligned
-      if ((((ti.s_off + ti.start + lo) | lo) & 3) == 0 && hi > lo) mr.a_hi = lo + ((hi - lo) & ~3);
-    }
-    mr.total = mr.a_lo + (ti.span - mr.a_hi);
-    if (tid == 0) {
-      const uint32_t bytes = (uint32_t)(mr.a_hi - mr.a_lo) * 4u;
-      mbar_arrive_expect_tx(bar, bytes);
-      if (bytes) bulk_g2s(buf + mr.a_lo, reinterpret_cast<const float*>(samples) + ti.s_off + ti.start + mr.a_lo, bytes, bar);
-    }
-    return mr;
-  };
-  auto manual_word = [&](const ManualRange& mr, int e) { return (e < mr.a_lo) ? e : mr.a_hi + (e - mr.a_lo); };
-  auto manual_load = [&](const TileInfo& ti, int word) {
-    return load_sample(samples + ti.s_off, (long long)reflect_index(ti.start + word, ti.L));
-  };
-  auto manual_fill_now = [&](const TileInfo& ti, const ManualRange& mr, float* buf) {
-    for (int e = tid; e < mr.total; e += kThreads) {
-      const int w = manual_word(mr, e);
-      buf[w] = manual_load(ti, w);
+    a_lo = lo;
+    a_hi = lo;
+    // tile word i <-> packed sample s_off + start + i ; both sides must be 16-byte aligned
+    if ((((ti.s_off + ti.start + lo) | lo) & (kAlign - 1)) == 0 && hi > lo) a_hi = lo + ((hi - lo) & ~(kAlign - 1));
+    const int total = a_lo + (ti.span - a_hi);
+    const SampleT* src = samples + ti.s_off;
+    for (int e = t; e < total; e += nt) {
+      const int w = (e < a_lo) ? e : a_hi + (e - a_lo);
+      buf[w] = __ldg(src + reflect_index(ti.start + w, ti.L));
     }
   };
+  auto stage_bulk = [&](const TileInfo& ti, SampleT* buf, uint64_t* bar, int a_lo, int a_hi) {
+    const uint32_t bytes = (uint32_t)(a_hi - a_lo) * (uint32_t)sizeof(SampleT);
+    fence_proxy_async();  // generic-proxy accesses to the buffer (reads of the previous tile) before the async write
+    mbar_arrive_expect_tx(bar, bytes);
+    if (bytes) bulk_g2s(buf + a_lo, samples + ti.s_off + ti.start + a_lo, bytes, bar);
+  };
+  auto in_buf = [&](int b) { return reinterpret_cast<SampleT*>(smem + (b ? p.off_in2 : p.off_in)); };
 
-  int tile = blockIdx.x;
-  if (tile >= p.n_tiles) return;
-#ifdef EVF_EXP_SKEW
-  {
-    const long long t0 = clock64();
-    while (clock64() - t0 < (long long)(warp >> 2) * EVF_EXP_SKEW) {
-    }
-  }
-#endif
+  int tile = blockIdx.x;  // grid <= n_tiles
   TileInfo cur = tile_info(tile);
-  TileInfo nxt = (tile + (int)gridDim.x < p.n_tiles) ? tile_info(tile + gridDim.x) : cur;
+  TileInfo nxt = (tile + G < p.n_tiles) ? tile_info(tile + G) : cur;
+  __syncthreads();  // barriers initialised, tables in place
   {
-    const ManualRange mr = stage_issue(cur, smem + p.off_in, &s_bar[0]);
-    manual_fill_now(cur, mr, smem + p.off_in);
-  }
-  __syncthreads();
-
-  for (int it = 0; tile < p.n_tiles; ++it, tile += gridDim.x) {
-    const int b = (nbuf == 2) ? (it & 1) : 0;
-    float* s_in = smem + (b ? p.off_in2 : p.off_in);
-    const uint32_t parity = (nbuf == 2) ? ((it >> 1) & 1) : (it & 1);
-    const int next_tile = tile + gridDim.x;
-    const bool has_next = next_tile < p.n_tiles;
-    const TileInfo fut = (next_tile + (int)gridDim.x < p.n_tiles) ? tile_info(next_tile + gridDim.x) : nxt;
-    ManualRange nmr{0, 0, 0};
-    float* s_next = smem + ((nbuf == 2 && !b) ? p.off_in2 : p.off_in);
-    uint64_t* bar_next = &s_bar[(nbuf == 2) ? (b ^ 1) : 0];
-    float mv0 = 0.f, mv1 = 0.f;
-    bool deferred = false;
-    if (has_next && nbuf == 2) {
-      // prefetch the next tile into the other buffer; its few manual words ride in registers
-      // across phase A (loads issued now, stores after the FFT)
-      nmr = stage_issue(nxt, s_next, bar_next);
-      if (nmr.total <= 2 * kThreads) {
-        deferred = true;
-        if (tid < nmr.total) mv0 = manual_load(nxt, manual_word(nmr, tid));
-        if (tid + kThreads < nmr.total) mv1 = manual_load(nxt, manual_word(nmr, tid + kThreads));
-      } else {
-        manual_fill_now(nxt, nmr, s_next);
-      }
+    int a_lo, a_hi;
+    stage_manual(cur, in_buf(0), tid, kThreads, a_lo, a_hi);
+    int b_lo = 0, b_hi = 0;
+    const bool second = (nbuf == 2) && (tile + G < p.n_tiles);
+    if (second) stage_manual(nxt, in_buf(1), tid, kThreads, b_lo, b_hi);
+    __syncthreads();
+    if (tid == 0) {
+      stage_bulk(cur, in_buf(0), &s_bar[0], a_lo, a_hi);
+      if (second) stage_bulk(nxt, in_buf(1), &s_bar[1], b_lo, b_hi);
     }
+  }
+
+  // per-lane constants of the mel walk
+  unsigned lt = 0;
+  if constexpr (kMel) lt = s_ltab[lane];
+
+  for (int it = 0; tile < p.n_tiles; ++it, tile += G) {
+    const int b = (nbuf == 2) ? (it & 1) : 0;
+    const SampleT* s_in = in_buf(b);
+    const uint32_t parity = (nbuf == 2) ? ((it >> 1) & 1) : (it & 1);
+    const TileInfo fut = (tile + 2 * G < p.n_tiles) ? tile_info(tile + 2 * G) : nxt;
     const int nvalid = cur.nvalid;
     const long long out_frame0 = cur.out_frame0;
+    const bool active = warp * FPJ < nvalid;
 
     mbar_wait(&s_bar[b], parity);
 
-    // ---- phase A: one FFT job per warp ------------------------------------------------
-    if (warp * FPJ < nvalid) {
-      float re[32], im[32];
+    float re[32], im[32];
+    if (active) {
+      // ---- samples -> registers, window fused into the first butterfly stage -------------
       if constexpr (MODE == MODE_PACK2) {
         // window pairs: s_win holds {w[32*r + lane], w[32*(r + 16) + lane]} at [r][lane] (16 LDS.64): rows r and
         // r + 16 are the two inputs of one first-stage butterfly, which absorbs the window multiplication
-        const float* xa = s_in + (2 * warp) * hop + lane;
+        const SampleT* xa = s_in + (2 * warp) * hop + lane;
         const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
         if (hop == 256) {
           // the two frames of the job overlap by 768 samples: sample rows 8..31 of frame a ARE rows
           // 0..23 of frame b, so 40 row loads feed both frames (instead of 64)
           float v[40];
 #pragma unroll
-          for (int r = 0; r < 40; ++r) v[r] = xa[32 * r];
+          for (int r = 0; r < 40; ++r) v[r] = to_float(xa[32 * r]);
 #pragma unroll
           for (int r = 0; r < 16; ++r) {
             const float2 w = wv[32 * r];
@@ -205,27 +194,54 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
             win_head(im[i], im[i + 1], v[r + 8], w.x, v[r + 24], w.y);
           }
         } else {
-          const float* xb = xa + hop;
+          const SampleT* xb = xa + hop;
 #pragma unroll
           for (int r = 0; r < 16; ++r) {
             const float2 w = wv[32 * r];
             const int i = bitrev5(r);
-            win_head(re[i], re[i + 1], xa[32 * r], w.x, xa[32 * (r + 16)], w.y);
-            win_head(im[i], im[i + 1], xb[32 * r], w.x, xb[32 * (r + 16)], w.y);
+            win_head(re[i], re[i + 1], to_float(xa[32 * r]), w.x, to_float(xa[32 * (r + 16)]), w.y);
+            win_head(im[i], im[i + 1], to_float(xb[32 * r]), w.x, to_float(xb[32 * (r + 16)]), w.y);
           }
         }
       } else {
-        const float2* x2 = reinterpret_cast<const float2*>(s_in + warp * hop) + lane;
+        const SampleT* x2 = s_in + warp * hop + 2 * lane;
         const float2* w2 = reinterpret_cast<const float2*>(s_win) + lane;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
           const float2 wa = w2[32 * r], wb = w2[32 * (r + 16)];
-          const float2 xa = x2[32 * r], xb = x2[32 * (r + 16)];
+          const float2 xa = load_pair(x2 + 64 * r), xb = load_pair(x2 + 64 * (r + 16));
           const int i = bitrev5(r);
           win_head(re[i], re[i + 1], xa.x, wa.x, xb.x, wb.x);
           win_head(im[i], im[i + 1], xa.y, wa.y, xb.y, wb.y);
         }
       }
+    }
+
+    // ---- release the input buffer; the last warp to do so refills it ---------------------
+    {
+      const int refill_tile = tile + nbuf * G;
+      int last = 0;
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();  // this warp's reads of the buffer are done before the release is visible
+        last = (atomicAdd(&s_cnt[b], 1) == WARPS - 1);
+        __threadfence_block();  // ... and the other warps' releases are visible before the refill
+      }
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) {
+        if (lane == 0) s_cnt[b] = 0;
+        if (refill_tile < p.n_tiles) {
+          const TileInfo& rt = (nbuf == 2) ? fut : nxt;
+          SampleT* dst = in_buf(b);
+          int a_lo, a_hi;
+          stage_manual(rt, dst, lane, 32, a_lo, a_hi);
+          __syncwarp();
+          if (lane == 0) stage_bulk(rt, dst, &s_bar[b], a_lo, a_hi);
+        }
+      }
+    }
+
+    if (active) {
       warp_fft1024_tail(re, im, s_tw4, scr, lane);
 
       // ---- real-FFT separation; the mirrored bin lives in lane (32 - lane) % 32 -------
@@ -235,7 +251,12 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
       float* ga = p.spec_out + (out_frame0 + fa) * (long long)p.row_floats;
       float* gb = ga + p.row_floats;
       const bool b_valid = (MODE == MODE_PACK2) && (fa + 1 < nvalid);
-      const int kcap = kMel ? p.k_used : (NFFT / 2 + 1);
+      // mel: every bin the walk below reads is rewritten by this job (zero-weight bins past k_used
+      // included), so nothing stale -- a NaN of an earlier job -- can leak into this one
+      const int kcap = kMel ? min(p.n_chunk * 32, NFFT / 2 + 1) : (NFFT / 2 + 1);
+      // the P column of this job: PACK2 float2 {frame a, frame b} per bin, HALF one float per bin
+      float2* P2 = reinterpret_cast<float2*>(scr);
+      float* P1 = scr;
 
 #pragma unroll
       for (int j = 0; j <= 16; ++j) {
@@ -273,10 +294,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
                   pb = fast_sqrt(pb + 1e-9f);
                 }
                 if constexpr (kMel) {
-                  if (k < kcap) {
-                    s_p[k * FS + fa] = pa;
-                    s_p[k * FS + fa + 1] = pb;
-                  }
+                  P2[k] = make_float2(pa, pb);
                 } else {
                   const float va = compress(pa, p.apply_log, p.log_clip);
                   const float vb = compress(pb, p.apply_log, p.log_clip);
@@ -292,15 +310,13 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
               // X[k] = E - T, X[M-k] = conj(E + T), E = Z[k] + conj(Z[M-k]), T = i * w_k * (Z[k] - conj(Z[M-k]))
               const float er = zr + pr, ei = zi - pi;
               const float orr = zr - pr, oi = zi + pi;
-              // (cos, -sin)(2 pi k / 2048): from shared memory, or through L1 when the plan has no room to stage it
-              const float2 w = kStageWpost ? s_wpost[k] : __ldg(p.wpost + k);
+              const float2 w = s_wpost[k];  // (cos, -sin)(2 pi k / 2048)
               const float tr = -fmaf(w.x, oi, w.y * orr);
               const float ti = fmaf(w.x, orr, -w.y * oi);
               const float x0r = er - tr, x0i = ei - ti;      // bin k
               const float x1r = er + tr, x1i = -(ei + ti);   // bin 1024 - k
               const int km = 1024 - k;
-              constexpr bool kHasMirrorRow = true;
-              const bool has_mirror = kHasMirrorRow && (j < 16);  // k == 512 is its own mirror
+              const bool has_mirror = (j < 16);  // k == 512 is its own mirror
               if constexpr (SPEC == EVF_SPEC_RAW) {
                 reinterpret_cast<float2*>(ga)[k] = make_float2(x0r, x0i);
                 if (has_mirror) reinterpret_cast<float2*>(ga)[km] = make_float2(x1r, x1i);
@@ -312,8 +328,8 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
                   p1 = fast_sqrt(p1 + 1e-9f);
                 }
                 if constexpr (kMel) {
-                  if (k < kcap) s_p[k * FS + fa] = p0;
-                  if (has_mirror && km < kcap) s_p[km * FS + fa] = p1;
+                  if (k < kcap) P1[k] = p0;
+                  if (has_mirror && km < kcap) P1[km] = p1;
                 } else {
                   const float v0 = compress(p0, p.apply_log, p.log_clip);
                   ga[k] = v0;
@@ -329,12 +345,100 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
           }
         }
       }
-      if constexpr (SPEC == EVF_SPEC_LINEAR) {
+
+      if constexpr (kMel) {
+        // ---- mel step 1: lane = chunk of n bins; two running FMAs per bin and frame ---------
+        __syncwarp();
+        const int n = p.n_chunk;
+        {
+          const float2* wp = s_wtab + lane;
+          SlotT* dst = slots + (lt & 0xffffu);
+          SlotT* dst_next = slots + (lt >> 16);
+          if constexpr (MODE == MODE_PACK2) {
+            const float2* pp = P2 + n * lane;
+            float ra = 0.f, rb = 0.f, fa_ = 0.f, fb = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < n; ++i, ++pp, wp += 32) {
+              const float2 pv = *pp;
+              const float2 w = *wp;
+              const float wr = fabsf(w.x);
+              ra = fmaf(wr, pv.x, ra);
+              rb = fmaf(wr, pv.y, rb);
+              fa_ = fmaf(w.y, pv.x, fa_);
+              fb = fmaf(w.y, pv.y, fb);
+              if (__float_as_int(w.x) < 0) {  // the interval (or the chunk) ends with this bin
+                *dst = make_float4(ra, rb, fa_, fb);
+                dst = dst_next;
+                ++dst_next;
+                ra = rb = fa_ = fb = 0.f;
+              }
+            }
+          } else {
+            const float* pp = P1 + n * lane;
+            float ra = 0.f, fa_ = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < n; ++i, ++pp, wp += 32) {
+              const float pv = *pp;
+              const float2 w = *wp;
+              ra = fmaf(fabsf(w.x), pv, ra);
+              fa_ = fmaf(w.y, pv, fa_);
+              if (__float_as_int(w.x) < 0) {
+                *dst = make_float2(ra, fa_);
+                dst = dst_next;
+                ++dst_next;
+                ra = fa_ = 0.f;
+              }
+            }
+          }
+        }
+        __syncwarp();
+        // ---- mel step 2: lane = filter; gather, log, coalesced row stores, energy -----------
+        const int n_mels = p.n_mels;
+        const int apply_log = p.apply_log;
+        const float clip = p.log_clip;
+        const int nh = p.n_heads;
+        const int m_pad = p.m_pad;
+        for (int m = lane; m < n_mels; m += 32) {
+          const unsigned* gp = s_gtab + m;
+          if constexpr (MODE == MODE_PACK2) {
+            float va = 0.f, vb = 0.f;
+            for (int c = 0; c <= nh; ++c, gp += m_pad) {
+              const unsigned g = *gp;
+              const float2 r = reinterpret_cast<const float2*>(slots + (g & 0xffffu))[0];
+              const float2 f = reinterpret_cast<const float2*>(slots + (g >> 16))[1];
+              va += r.x;
+              vb += r.y;
+              va += f.x;
+              vb += f.y;
+            }
+            va = compress(va, apply_log, clip);
+            vb = compress(vb, apply_log, clip);
+            ga[m] = va;
+            esum_a = fmaf(va, va, esum_a);
+            if (b_valid) {
+              gb[m] = vb;
+              esum_b = fmaf(vb, vb, esum_b);
+            }
+          } else {
+            float va = 0.f;
+            for (int c = 0; c <= nh; ++c, gp += m_pad) {
+              const unsigned g = *gp;
+              va += slots[g & 0xffffu].x;
+              va += slots[g >> 16].y;
+            }
+            va = compress(va, apply_log, clip);
+            ga[m] = va;
+            esum_a = fmaf(va, va, esum_a);
+          }
+        }
+      }
+
+      if constexpr (SPEC != EVF_SPEC_RAW) {
         if (p.energy_out != nullptr) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
             esum_a += __shfl_xor_sync(0xffffffffu, esum_a, o);
-            esum_b += __shfl_xor_sync(0xffffffffu, esum_b, o);
+            if constexpr (MODE == MODE_PACK2) esum_b += __shfl_xor_sync(0xffffffffu, esum_b, o);
           }
           if (lane == 0) {
             p.energy_out[out_frame0 + fa] = sqrtf(esum_a);
@@ -343,177 +447,44 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
         }
       }
     }
-
-    // the next tile's manual words (reflected margins) were loaded before the FFT: store them now
-    if (deferred) {
-      if (tid < nmr.total) s_next[manual_word(nmr, tid)] = mv0;
-      if (tid + kThreads < nmr.total) s_next[manual_word(nmr, tid + kThreads)] = mv1;
-    }
-#ifndef EVF_EXP_NOSYNC1
-    __syncthreads();  // (1) input tile consumed, P tile complete, next tile's manual words visible
-#endif
-    if (has_next && nbuf == 1) {
-      // single input buffer (large-footprint plans): restage now, overlapping phases B and C
-      const ManualRange mr = stage_issue(nxt, s_in, &s_bar[0]);
-      manual_fill_now(nxt, mr, s_in);
-    }
-
-#ifdef EVF_EXP_SKIP_BC
-    if constexpr (false) {
-#else
-    if constexpr (kMel) {
-#endif
-      // ---- phase B: mel projection, lane = frame ---------------------------------------
-      // Each worker (a warp, or a half / quarter warp when the tile has fewer than 32 frames)
-      // walks a contiguous run of bins that starts and ends on interval boundaries.  Two running
-      // FMAs per bin; when the interval index changes the two sums are flushed (fire-and-forget
-      // stores, linear domain): SA[j] = sum of rising-slope weights * P over interval j,
-      // SB[j] = the same for the falling slopes.  mel[m] = SA[m] + SB[m + 1] (phase C).
-      {
-        const float* __restrict__ sp = s_p;
-        float* __restrict__ sa_out = s_sa;
-        float* __restrict__ sb_out = s_sb;
-        const float4* __restrict__ mw = s_mw4;  // per bin: {rising w, falling w, interval, interval of next bin}
-        if constexpr (PARTS == 1) {
-          // lane = frame, warp = worker: everything but the P value is warp-uniform
-          const int wu = __shfl_sync(0xffffffffu, warp, 0);
-          int k = s_vwk[wu];
-          const int k1 = s_vwk[wu + 1];
-          const float* pp = sp + k * FS + lane;
-          const float4* wp = mw + k;
-          float sa = 0.f, sb = 0.f;
-          for (; k + 4 <= k1; k += 4, pp += 4 * FS, wp += 4) {
-            const float p0 = pp[0], p1 = pp[FS], p2 = pp[2 * FS], p3 = pp[3 * FS];
-            const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
-#define EVF_BIN_STEP(W, P)                                                     \
-  sa = fmaf(W.x, P, sa);                                                       \
-  sb = fmaf(W.y, P, sb);                                                       \
-  if (__float_as_int(W.z) != __float_as_int(W.w)) {                            \
-    sa_out[__float_as_int(W.z) * FS + lane] = sa;                              \
-    sb_out[__float_as_int(W.z) * FS + lane] = sb;                              \
-    sa = 0.f;                                                                  \
-    sb = 0.f;                                                                  \
-  }
-            EVF_BIN_STEP(w0, p0)
-            EVF_BIN_STEP(w1, p1)
-            EVF_BIN_STEP(w2, p2)
-            EVF_BIN_STEP(w3, p3)
-          }
-          for (; k < k1; ++k, pp += FS, ++wp) {
-            const float p0 = pp[0];
-            const float4 w0 = wp[0];
-            EVF_BIN_STEP(w0, p0)
-          }
-        } else {
-          // several workers per warp (tiles of 16 or 8 frames): same walk, per-lane bin ranges
-          const int fr = lane % FR;
-          const int vw = warp * PARTS + lane / FR;
-          int k = s_vwk[vw];
-          const int k1 = s_vwk[vw + 1];
-          float sa = 0.f, sb = 0.f;
-          for (; k < k1; ++k) {
-            const float pv = sp[k * FS + fr];
-            const float4 w = mw[k];
-            sa = fmaf(w.x, pv, sa);
-            sb = fmaf(w.y, pv, sb);
-            if (__float_as_int(w.z) != __float_as_int(w.w)) {
-              sa_out[__float_as_int(w.z) * FS + fr] = sa;
-              sb_out[__float_as_int(w.z) * FS + fr] = sb;
-              sa = 0.f;
-              sb = 0.f;
-            }
-          }
-        }
-#undef EVF_BIN_STEP
-      }
-#ifndef EVF_EXP_NOSYNC2
-      __syncthreads();  // (2)
-#endif
-      // ---- phase C: combine, log, coalesced store of the log-mel rows + per-frame energy ---
-      // (32-bit offsets from one row pointer per frame; rows of intervals without bins are never
-      // flushed and stay zero, cleared at start)
-      const int n_mels = p.n_mels;
-      const int apply_log = p.apply_log;
-      const float clip = p.log_clip;
-#pragma unroll
-      for (int q = 0; q < FPJ; ++q) {
-        const int f = warp * FPJ + q;
-        if (f < nvalid) {
-          float* __restrict__ dst = p.spec_out + (out_frame0 + f) * (long long)p.row_floats;
-          const float* sa_f = s_sa + f + lane * FS;
-          const float* sb_f = s_sb + FS + f + lane * FS;
-          float acc = 0.f;
-          int m = lane;
-#pragma unroll 1
-          for (; m + 32 < n_mels; m += 64, sa_f += 64 * FS, sb_f += 64 * FS) {  // two rows of 32 per trip
-            const float v0 = compress(sa_f[0] + sb_f[0], apply_log, clip);
-            const float v1 = compress(sa_f[32 * FS] + sb_f[32 * FS], apply_log, clip);
-            dst[m] = v0;
-            dst[m + 32] = v1;
-            acc = fmaf(v0, v0, acc);
-            acc = fmaf(v1, v1, acc);
-          }
-          if (m < n_mels) {
-            const float v0 = compress(sa_f[0] + sb_f[0], apply_log, clip);
-            dst[m] = v0;
-            acc = fmaf(v0, v0, acc);
-          }
-          if (p.energy_out != nullptr) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) p.energy_out[out_frame0 + f] = sqrtf(acc);
-          }
-        }
-      }
-    } else {
-      if (nbuf == 1) __syncthreads();  // the restaged manual words must be visible to the next FFT
-    }
     cur = nxt;
     nxt = fut;
   }
 }
 
-template <int MODE, int SPEC, typename SampleT, int WARPS>
-int launch_w(const FeatParams& p, int grid, int smem, cudaStream_t stream, bool configure_only) {
-  auto kern = features_kernel<MODE, SPEC, SampleT, WARPS>;
+template <int MODE, int SPEC, typename SampleT>
+int launch_t(const FeatParams& p, int grid, int smem, cudaStream_t stream, bool configure_only) {
+  auto kern = features_kernel<MODE, SPEC, SampleT, kMaxWarps>;
   if (configure_only) {
     EVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return EVF_OK;
   }
-  kern<<<grid, WARPS * 32, smem, stream>>>(p);
+  kern<<<grid, kMaxWarps * 32, smem, stream>>>(p);
   EVF_CUDA(cudaGetLastError());
   return EVF_OK;
 }
 
-template <int MODE, int SPEC, typename SampleT>
-int launch_t(int warps, const FeatParams& p, int grid, int smem, cudaStream_t stream, bool cfg) {
-  if (warps == 8) return launch_w<MODE, SPEC, SampleT, 8>(p, grid, smem, stream, cfg);
-  return launch_w<MODE, SPEC, SampleT, 16>(p, grid, smem, stream, cfg);
-}
-
 template <int MODE, int SPEC>
-int launch_s(int fmt, int warps, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
-  if (fmt == EVF_SAMPLES_S16) return launch_t<MODE, SPEC, short>(warps, p, grid, smem, st, cfg);
-  return launch_t<MODE, SPEC, float>(warps, p, grid, smem, st, cfg);
+int launch_s(int fmt, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
+  if (fmt == EVF_SAMPLES_S16) return launch_t<MODE, SPEC, short>(p, grid, smem, st, cfg);
+  return launch_t<MODE, SPEC, float>(p, grid, smem, st, cfg);
 }
 
 template <int MODE>
-int launch_m(int spec, int fmt, int warps, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
+int launch_m(int spec, int fmt, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
   switch (spec) {
-    case EVF_SPEC_MEL: return launch_s<MODE, EVF_SPEC_MEL>(fmt, warps, p, grid, smem, st, cfg);
-    case EVF_SPEC_MEL_LIBROSA: return launch_s<MODE, EVF_SPEC_MEL_LIBROSA>(fmt, warps, p, grid, smem, st, cfg);
-    case EVF_SPEC_LINEAR: return launch_s<MODE, EVF_SPEC_LINEAR>(fmt, warps, p, grid, smem, st, cfg);
-    case EVF_SPEC_RAW: return launch_s<MODE, EVF_SPEC_RAW>(fmt, warps, p, grid, smem, st, cfg);
+    case EVF_SPEC_MEL: return launch_s<MODE, EVF_SPEC_MEL>(fmt, p, grid, smem, st, cfg);
+    case EVF_SPEC_MEL_LIBROSA: return launch_s<MODE, EVF_SPEC_MEL_LIBROSA>(fmt, p, grid, smem, st, cfg);
+    case EVF_SPEC_LINEAR: return launch_s<MODE, EVF_SPEC_LINEAR>(fmt, p, grid, smem, st, cfg);
+    case EVF_SPEC_RAW: return launch_s<MODE, EVF_SPEC_RAW>(fmt, p, grid, smem, st, cfg);
   }
   set_error("unknown spec_type");
   return EVF_ERR_UNSUPPORTED;
 }
 
-int dispatch(int mode, int spec, int fmt, int warps, const FeatParams& p, int grid, int smem, cudaStream_t st,
-             bool cfg) {
-  if (mode == MODE_PACK2) return launch_m<MODE_PACK2>(spec, fmt, warps, p, grid, smem, st, cfg);
-  if (mode == MODE_HALF) return launch_m<MODE_HALF>(spec, fmt, warps, p, grid, smem, st, cfg);
-  if (mode == MODE_HALF_L1) return launch_m<MODE_HALF_L1>(spec, fmt, warps, p, grid, smem, st, cfg);
+int dispatch(int mode, int spec, int fmt, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
+  if (mode == MODE_PACK2) return launch_m<MODE_PACK2>(spec, fmt, p, grid, smem, st, cfg);
+  if (mode == MODE_HALF) return launch_m<MODE_HALF>(spec, fmt, p, grid, smem, st, cfg);
   set_error("unknown FFT mode");
   return EVF_ERR_UNSUPPORTED;
 }
@@ -521,24 +492,26 @@ int dispatch(int mode, int spec, int fmt, int warps, const FeatParams& p, int gr
 }  // namespace
 
 // Computes the shared-memory carve-up for a plan; returns bytes (or -1 if it cannot fit).
-int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, int n_mels, int k_used,
+int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, const PlanTables& t,
                         FeatParams* c) {
   const bool mel = (spec_type == EVF_SPEC_MEL || spec_type == EVF_SPEC_MEL_LIBROSA);
   const int fpj = (mode == MODE_PACK2) ? 2 : 1;
   const int fr = warps * fpj;
-  const int parts = 32 / fr;
-  // 16 warps: one CTA per SM (227 KB); 8 warps: two CTAs per SM (228 KB - 2 x 1 KB reserved, halved)
-  const long long limit = (warps == 16) ? 227 * 1024 : 113 * 1024;
+  const long long limit = 227 * 1024;  // one CTA per SM
   auto up4 = [](int w) { return (w + 3) & ~3; };
-  // Prefer two input buffers (the next tile's bulk copy overlaps this tile's FFTs); fall back
-  // to one when the plan's tables do not leave room for it.  (The caller retries with
-  // MODE_HALF_L1 -- post-twiddles read through L1 instead of staged -- when MODE_HALF cannot fit.)
-  const int stage_wpost = (mode == MODE_HALF) ? 1 : 0;
+  c->n_chunk = t.n_chunk;
+  c->n_heads = t.n_heads;
+  c->m_pad = t.m_pad;
+  c->n_slots = t.n_slots;
+  // the P column must fit into the transpose scratch it aliases
+  if (mel && t.n_chunk * 32 * fpj > 32 * kScrStride) return -1;
+  // Prefer a ring of two input buffers (the refill of one overlaps the FFTs on the other); fall back
+  // to one when the hop is so large that two do not fit.
   for (int nbuf = 2; nbuf >= 1; --nbuf) {
     int w = 0;
     c->nbuf = nbuf;
     c->off_bar = w;
-    w += 4;  // two 8-byte mbarriers
+    w += 8;  // two 8-byte mbarriers + two release counters (+ pad)
     c->off_in = w;
     c->in_words = up4((fr - 1) * hop + n_fft);
     w += c->in_words;
@@ -552,40 +525,32 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
     c->off_tw = w;
     w += 2 * kFftSize;
     c->off_wpost = w;
-    if (stage_wpost) w += up4(2 * 513);
-    c->off_melw = w;
-    c->off_vwk = w;
-    c->off_p = w;
-    c->off_sa = w;
-    c->off_sb = w;
+    if (mode == MODE_HALF) w += up4(2 * 513);
+    c->off_wtab = c->off_gtab = c->off_ltab = w;
     if (mel) {
-      w += 4 * k_used;
-      c->off_vwk = w;
-      w += up4(warps * parts + 1);
-      c->off_p = w;
-      w += up4(k_used * (fr + 1));
-      c->off_sa = w;
-      w += (n_mels + 1) * (fr + 1);
-      c->off_sb = w;  // directly after SA (cleared together)
-      w += (n_mels + 1) * (fr + 1);
-      w = up4(w);
+      w += 2 * 32 * t.n_chunk;
+      c->off_gtab = w;
+      w += up4((t.n_heads + 1) * t.m_pad);
+      c->off_ltab = w;
+      w += 32;
     }
-    c->off_scr = w;
-    w += warps * 32 * kScrStride;
+    c->off_warp = w;
+    c->warp_words = 32 * kScrStride + (mel ? up4(t.n_slots * 2 * fpj) : 0);
+    w += warps * c->warp_words;
     const long long bytes = 4ll * w;
     if (bytes <= limit) return (int)bytes;
   }
   return -1;
 }
 
-int features_configure(int mode, int spec_type, int sample_format, int warps, int smem_bytes) {
+int features_configure(int mode, int spec_type, int sample_format, int smem_bytes) {
   FeatParams dummy{};
-  return dispatch(mode, spec_type, sample_format, warps, dummy, 1, smem_bytes, nullptr, true);
+  return dispatch(mode, spec_type, sample_format, dummy, 1, smem_bytes, nullptr, true);
 }
 
-int features_launch(int mode, int spec_type, int sample_format, int warps, const FeatParams& p, int grid,
-                    int smem_bytes, cudaStream_t stream) {
-  return dispatch(mode, spec_type, sample_format, warps, p, grid, smem_bytes, stream, false);
+int features_launch(int mode, int spec_type, int sample_format, const FeatParams& p, int grid, int smem_bytes,
+                    cudaStream_t stream) {
+  return dispatch(mode, spec_type, sample_format, p, grid, smem_bytes, stream, false);
 }
 
 }  // namespace evf

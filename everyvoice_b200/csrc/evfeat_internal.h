@@ -10,14 +10,13 @@
 
 namespace evf {
 
-constexpr int kMaxWarps = 16;        // warps per CTA (16 x 1 CTA/SM or 8 x 2 CTAs/SM); one FFT job per warp per tile
+constexpr int kMaxWarps = 16;        // warps per CTA (one CTA per SM); one FFT job per warp per tile
 constexpr int kFftSize = 1024;       // complex points per warp-level FFT
 constexpr int kScrStride = 34;       // padded row stride of the per-warp transpose scratch (even: LDS.64 rows)
 
 enum FftMode : int {
   MODE_PACK2 = 0,  // n_fft == 1024: two real frames packed as re/im of one complex FFT
   MODE_HALF = 1,   // n_fft == 2048: one real frame as a 1024-point complex FFT + split
-  MODE_HALF_L1 = 2,  // same, post-twiddle table read through L1 (plans whose tables fill shared memory)
 };
 
 // One frame tile of one utterance; built on the host by evf_batch_create so that the kernel
@@ -43,31 +42,39 @@ struct FeatParams {
   const float* window;   // [n_fft], pre-scaled by 0.5; n_fft 1024: stored as pairs {w[32r + lane], w[32(r+16) + lane]} at [r][lane], r < 16
   const float4* tw4;     // [16][32] four-step twiddles {t[n][lane], t[n+16][lane]}, t[n2][k1] = W_1024^(n2*k1)
   const float2* wpost;   // MODE_HALF: exp(-2 pi i k / n_fft), k = 0..512
-  const float4* melw4;   // [k_used] {rising weight -> mel j(k), falling weight -> mel j(k)-1, j(k), j(k+1)} (ints as bits)
-  const int* vw_k;       // [n_vw + 1] bin range of every worker of the projection phase (interval aligned)
+  // mel projection (per-warp bin walk, see evfeat_features.cu):
+  const float2* wtab;    // [n_chunk][32] {rising weight (sign bit = flush after this bin), falling weight} of bin n_chunk*lane + i
+  const unsigned* gtab;  // [(n_heads + 1)][m_pad] per filter: slot of the c-th rising partial | slot of the c-th falling partial << 16
+  const unsigned* ltab;  // [32] per lane: slot of the first flush | slot of the second flush << 16 (later ones follow consecutively)
   int hop;
   int n_mels;
   int n_freq;
   int k_used;            // bins [0, k_used) carry a non-zero mel weight
+  int n_chunk;           // bins walked by one lane (odd, so that the lanes' reads fall into distinct banks)
+  int n_heads;           // most lanes that continue one interval started by an earlier lane
+  int m_pad;             // n_mels rounded up to 32
+  int n_slots;           // partial-sum slots per warp (non-empty intervals + 32 heads + 1 zero slot)
   int row_floats;
   int apply_log;
   float log_clip;
   // shared-memory carve-up, in 4-byte words from the start of dynamic shared memory
-  int off_bar, off_in, off_in2, off_win, off_tw, off_wpost, off_melw, off_vwk, off_p, off_sa, off_sb, off_scr;
-  int nbuf;              // input tile buffers: 2 = bulk-copy prefetch of the next tile, 1 = restage in place
-  int in_words;          // capacity of the input tile
+  int off_bar, off_in, off_in2, off_win, off_tw, off_wpost, off_wtab, off_gtab, off_ltab, off_warp;
+  int warp_words;        // per-warp region: transpose scratch (aliased by the P column) + partial-sum slots
+  int nbuf;              // input tile buffers in the ring (2 or 1)
+  int in_words;          // capacity of one input tile
 };
 
 struct PlanTables {
   std::vector<float> window;      // n_fft, pre-scaled
   std::vector<float4> tw4;        // 512
   std::vector<float2> wpost;      // 513 (MODE_HALF) or empty
-  std::vector<float2> melw;       // k_used
-  std::vector<float4> melw4;      // k_used
-  std::vector<int> kstart;        // n_mels + 2
-  std::vector<int> vw_k;          // n_vw + 1
-  std::vector<int> jk;            // k_used + 1
-  int k_used = 0;
+  std::vector<float2> melw;       // k_used {rising, falling}
+  std::vector<int> kstart;        // n_mels + 2: interval j owns bins [kstart[j], kstart[j + 1])
+  std::vector<int> jk;            // k_used + 1 interval of every bin (+ sentinel)
+  std::vector<float2> wtab;       // n_chunk * 32
+  std::vector<unsigned> gtab;     // (n_heads + 1) * m_pad
+  std::vector<unsigned> ltab;     // 32
+  int k_used = 0, n_chunk = 1, n_heads = 0, m_pad = 32, n_slots = 34;
 };
 
 void set_error(const std::string& msg);
@@ -79,11 +86,11 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 // evfeat_features.cu
-int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, int n_mels, int k_used,
+int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, const PlanTables& t,
                         FeatParams* carve);
-int features_configure(int mode, int spec_type, int sample_format, int warps, int smem_bytes);
-int features_launch(int mode, int spec_type, int sample_format, int warps, const FeatParams& p, int grid,
-                    int smem_bytes, cudaStream_t stream);
+int features_configure(int mode, int spec_type, int sample_format, int smem_bytes);
+int features_launch(int mode, int spec_type, int sample_format, const FeatParams& p, int grid, int smem_bytes,
+                    cudaStream_t stream);
 
 // evfeat_aux.cu
 int launch_energy_from_spec(const float* spec, int64_t n_frames, int row, float* out, cudaStream_t s);
