@@ -279,15 +279,21 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   p->cfg = *cfg;
   p->device = device;
   p->mode = (cfg->n_fft == 1024) ? MODE_PACK2 : MODE_HALF;
+  if (p->mode == MODE_PACK2) {
+    // A/B switch (tools/kbench.py, tests): the packed two-jobs-per-warp kernel computes the same bits
+    // (evfeat_features_x2.cu; not the default, DESIGN.md section 4.1 has the counters)
+    const char* v = std::getenv("EVF_FEATURES_VARIANT");
+    if (v && std::strcmp(v, "x2") == 0) p->mode = MODE_PACK2X2;
+  }
   p->n_freq = cfg->n_fft / 2 + 1;
-  p->warps = kMaxWarps;  // one 16-warp CTA per SM
-  p->frames_per_tile = p->warps * (p->mode == MODE_PACK2 ? 2 : 1);
+  p->warps = (p->mode == MODE_PACK2X2) ? kX2Warps : kMaxWarps;  // one CTA per SM
+  p->frames_per_tile = (p->mode == MODE_HALF) ? p->warps : 32;     // 16 jobs of two frames (n_fft 1024)
   p->num_sms = prop.multiProcessorCount;
   p->row_floats = mel ? cfg->n_mels : (cfg->spec_type == EVF_SPEC_RAW ? 2 * p->n_freq : p->n_freq);
 
   PlanTables t;
   t.window.resize(cfg->n_fft);
-  if (p->mode == MODE_PACK2) {
+  if (mode_is_pack2(p->mode)) {
     // pair layout for LDS.64: [r][lane] = {w[32 * r + lane], w[32 * (r + 16) + lane]}, r < 16: the two inputs of
     // one first-stage butterfly of the first pass (evfeat_fft.cuh, win_head); 0.5 is exact
     for (int r = 0; r < 16; ++r)
@@ -383,7 +389,7 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
   std::vector<long long> s_off(n_utts + 1, 0), f_off(n_utts + 1, 0);
   std::vector<TileDesc> tiles;
   std::vector<int> tile_start(n_utts + 1, 0);
-  const int fpj = (plan->mode == MODE_PACK2) ? 2 : 1;
+  const int fpj = mode_is_pack2(plan->mode) ? 2 : 1;  // frames per FFT job
   for (int b = 0; b < n_utts; ++b) {
     tile_start[b] = (int)tiles.size();
     const int64_t L = sample_offsets_host[b + 1] - sample_offsets_host[b];

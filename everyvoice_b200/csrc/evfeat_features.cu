@@ -165,7 +165,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
     const int b = (nbuf == 2) ? (it & 1) : 0;
     const SampleT* s_in = in_buf(b);
     const uint32_t parity = (nbuf == 2) ? ((it >> 1) & 1) : (it & 1);
-    const TileInfo fut = (tile + 2 * G < p.n_tiles) ? tile_info(tile + 2 * G) : nxt;
+    // clamped index instead of a select on the loaded values: nothing consumes the descriptor before the refill
+    // (or the end of the iteration), so the load latency stays off the critical path; past the end it is unused
+    const TileInfo fut = tile_info(min(tile + 2 * G, p.n_tiles - 1));
     const int nvalid = cur.nvalid;
     const long long out_frame0 = cur.out_frame0;
     const bool active = warp * FPJ < nvalid;
@@ -485,6 +487,7 @@ int launch_m(int spec, int fmt, const FeatParams& p, int grid, int smem, cudaStr
 int dispatch(int mode, int spec, int fmt, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
   if (mode == MODE_PACK2) return launch_m<MODE_PACK2>(spec, fmt, p, grid, smem, st, cfg);
   if (mode == MODE_HALF) return launch_m<MODE_HALF>(spec, fmt, p, grid, smem, st, cfg);
+  if (mode == MODE_PACK2X2) return features_x2_dispatch(spec, fmt, p, grid, smem, st, cfg);
   set_error("unknown FFT mode");
   return EVF_ERR_UNSUPPORTED;
 }
@@ -495,7 +498,8 @@ int dispatch(int mode, int spec, int fmt, const FeatParams& p, int grid, int sme
 int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, const PlanTables& t,
                         FeatParams* c) {
   const bool mel = (spec_type == EVF_SPEC_MEL || spec_type == EVF_SPEC_MEL_LIBROSA);
-  const int fpj = (mode == MODE_PACK2) ? 2 : 1;
+  const bool x2 = (mode == MODE_PACK2X2);           // two jobs per warp, 8-byte scratch elements, 32-byte slots
+  const int fpj = (mode == MODE_HALF) ? 1 : (x2 ? 4 : 2);  // frames per warp and tile
   const int fr = warps * fpj;
   const long long limit = 227 * 1024;  // one CTA per SM
   auto up4 = [](int w) { return (w + 3) & ~3; };
@@ -504,7 +508,7 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
   c->m_pad = t.m_pad;
   c->n_slots = t.n_slots;
   // the P column must fit into the transpose scratch it aliases
-  if (mel && t.n_chunk * 32 * fpj > 32 * kScrStride) return -1;
+  if (mel && t.n_chunk * 32 * fpj > 32 * kScrStride * (x2 ? 2 : 1)) return -1;
   // Prefer a ring of two input buffers (the refill of one overlaps the FFTs on the other); fall back
   // to one when the hop is so large that two do not fit.
   for (int nbuf = 2; nbuf >= 1; --nbuf) {
@@ -535,7 +539,7 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
       w += 32;
     }
     c->off_warp = w;
-    c->warp_words = 32 * kScrStride + (mel ? up4(t.n_slots * 2 * fpj) : 0);
+    c->warp_words = 32 * kScrStride * (x2 ? 2 : 1) + (mel ? up4(t.n_slots * 2 * fpj) : 0);
     w += warps * c->warp_words;
     const long long bytes = 4ll * w;
     if (bytes <= limit) return (int)bytes;

@@ -16,6 +16,7 @@
 // arithmetic on the CPU against a double-precision DFT.
 #pragma once
 #include <cuda_runtime.h>
+#include <string.h>
 
 #define EVF_HD __host__ __device__ __forceinline__
 
@@ -42,28 +43,112 @@ EVF_HD constexpr float cos32(int j) {
 }
 EVF_HD constexpr float sin32(int j) { return (j <= 8) ? cos32(8 - j) : cos32(j - 8); }
 
+// ---- value types -----------------------------------------------------------------------------
+// The butterflies are written once over a value type V with the operations below.  V = float is
+// the scalar form (one FFT per warp; also what the host-side index check runs).  V = f32x2 packs
+// the same element of TWO independent FFTs into one 64-bit register pair and maps every operation
+// to one packed instruction (FFMA2 / FADD2 / FMUL2: same lane throughput as the scalar forms, half
+// the issue slots; a scalar multiplier -- immediate twiddle, window or table value -- is broadcast
+// by the instruction itself, SASS `R.F32` / immediate operand, so nothing is duplicated).
+EVF_HD float v_add(float a, float b) { return a + b; }
+EVF_HD float v_sub(float a, float b) { return a - b; }
+EVF_HD float v_neg(float a) { return -a; }
+EVF_HD float v_mul(float a, float s) { return a * s; }                 // a * s
+EVF_HD float v_fma(float a, float s, float c) { return fmaf(a, s, c); }  // a * s + c, s scalar
+
+// Two floats in one 64-bit register pair.  Device: the packed sm_100 instructions through inline PTX.
+// Host (tests/native/fft_host_check.cu): the same operations on the two halves, so that the packed
+// index arithmetic can be checked without a GPU.
+struct f32x2 {
+  unsigned long long v;  // low 32 bits = first element, high 32 bits = second element
+};
+EVF_HD f32x2 v_pack(float lo, float hi) {
+  f32x2 r;
+#ifdef __CUDA_ARCH__
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+#else
+  unsigned a, b;
+  memcpy(&a, &lo, 4);
+  memcpy(&b, &hi, 4);
+  r.v = (unsigned long long)a | ((unsigned long long)b << 32);
+#endif
+  return r;
+}
+EVF_HD void v_unpack(f32x2 x, float& lo, float& hi) {
+#ifdef __CUDA_ARCH__
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x.v));
+#else
+  const unsigned a = (unsigned)x.v, b = (unsigned)(x.v >> 32);
+  memcpy(&lo, &a, 4);
+  memcpy(&hi, &b, 4);
+#endif
+}
+#ifdef __CUDA_ARCH__
+#define EVF_F32X2_OP2(name, ptx)                                              \
+  EVF_HD f32x2 name(f32x2 a, f32x2 b) {                                        \
+    f32x2 r;                                                                   \
+    asm(ptx " %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));                  \
+    return r;                                                                  \
+  }
+#else
+#define EVF_F32X2_OP2(name, ptx)                                              \
+  EVF_HD f32x2 name(f32x2 a, f32x2 b) {                                        \
+    float a0, a1, b0, b1;                                                      \
+    v_unpack(a, a0, a1);                                                       \
+    v_unpack(b, b0, b1);                                                       \
+    return v_pack(name(a0, b0), name(a1, b1));                                 \
+  }
+#endif
+EVF_F32X2_OP2(v_add, "add.rn.f32x2")
+EVF_F32X2_OP2(v_sub, "sub.rn.f32x2")
+EVF_F32X2_OP2(v_mul, "mul.rn.f32x2")  // element-wise product
+#undef EVF_F32X2_OP2
+EVF_HD f32x2 v_fma(f32x2 a, f32x2 b, f32x2 c) {  // element-wise a * b + c
+#ifdef __CUDA_ARCH__
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+#else
+  float a0, a1, b0, b1, c0, c1;
+  v_unpack(a, a0, a1);
+  v_unpack(b, b0, b1);
+  v_unpack(c, c0, c1);
+  return v_pack(fmaf(a0, b0, c0), fmaf(a1, b1, c1));
+#endif
+}
+EVF_HD f32x2 v_neg(f32x2 a) {  // folds into the consumer's operand modifier
+  float lo, hi;
+  v_unpack(a, lo, hi);
+  return v_pack(-lo, -hi);
+}
+// scalar multiplier broadcast to both halves (SASS: immediate or `R.F32` operand, no extra instruction)
+EVF_HD f32x2 v_mul(f32x2 a, float s) { return v_mul(a, v_pack(s, s)); }
+EVF_HD f32x2 v_fma(f32x2 a, float s, f32x2 c) { return v_fma(a, v_pack(s, s), c); }
+EVF_HD f32x2 v_mul2(f32x2 a, f32x2 b) { return v_mul(a, b); }
+EVF_HD f32x2 v_fma2(f32x2 a, f32x2 b, f32x2 c) { return v_fma(a, b, c); }
+
 // One DIT butterfly on (a, b) with w = exp(-2*pi*i*J/32):  a' = a + w b,  b' = a - w b.
-template <int J>
-EVF_HD void bfly_dit(float& ar, float& ai, float& br, float& bi) {
+template <int J, typename V>
+EVF_HD void bfly_dit(V& ar, V& ai, V& br, V& bi) {
   if constexpr (J == 0) {
-    const float xr = ar + br, xi = ai + bi;
-    br = ar - br;
-    bi = ai - bi;
+    const V xr = v_add(ar, br), xi = v_add(ai, bi);
+    br = v_sub(ar, br);
+    bi = v_sub(ai, bi);
     ar = xr;
     ai = xi;
   } else if constexpr (J == 8) {  // w = -i:  w b = (bi, -br)
-    const float xr = ar + bi, xi = ai - br;
-    const float yr = ar - bi, yi = ai + br;
+    const V xr = v_add(ar, bi), xi = v_sub(ai, br);
+    const V yr = v_sub(ar, bi), yi = v_add(ai, br);
     ar = xr;
     ai = xi;
     br = yr;
     bi = yi;
   } else {  // w = c - i s:  w b = (br c + bi s) + i (bi c - br s)
     constexpr float c = cos32(J), s = sin32(J);
-    const float xr = fmaf(br, c, fmaf(bi, s, ar));
-    const float xi = fmaf(bi, c, fmaf(-br, s, ai));
-    br = fmaf(2.0f, ar, -xr);
-    bi = fmaf(2.0f, ai, -xi);
+    const V xr = v_fma(br, c, v_fma(bi, s, ar));
+    const V xi = v_fma(bi, c, v_fma(br, -s, ai));
+    br = v_fma(ar, 2.0f, v_neg(xr));
+    bi = v_fma(ai, 2.0f, v_neg(xi));
     ar = xr;
     ai = xi;
   }
@@ -71,16 +156,18 @@ EVF_HD void bfly_dit(float& ar, float& ai, float& br, float& bi) {
 
 template <int HALF, int G, int J>
 struct DitJ {
-  EVF_HD static void run(float (&re)[32], float (&im)[32]) {
+  template <typename V, int N>
+  EVF_HD static void run(V (&re)[N], V (&im)[N]) {
     bfly_dit<J*(16 / HALF)>(re[G + J], im[G + J], re[G + J + HALF], im[G + J + HALF]);
     if constexpr (J + 1 < HALF) DitJ<HALF, G, J + 1>::run(re, im);
   }
 };
 template <int HALF, int G>
 struct DitG {
-  EVF_HD static void run(float (&re)[32], float (&im)[32]) {
+  template <typename V, int N>
+  EVF_HD static void run(V (&re)[N], V (&im)[N]) {
     DitJ<HALF, G, 0>::run(re, im);
-    if constexpr (G + 2 * HALF < 32) DitG<HALF, G + 2 * HALF>::run(re, im);
+    if constexpr (G + 2 * HALF < N) DitG<HALF, G + 2 * HALF>::run(re, im);
   }
 };
 
@@ -88,7 +175,8 @@ struct DitG {
 // In : index i holds the output of the span-1 stage for the pair it belongs to, where the
 //      span-1 stage combined x[bitrev5(i & ~1)] (= some n < 16) and x[n + 16].
 // Out: index k holds X[k] (natural order).
-EVF_HD void dft32_dit_tail(float (&re)[32], float (&im)[32]) {
+template <typename V>
+EVF_HD void dft32_dit_tail(V (&re)[32], V (&im)[32]) {
   DitG<2, 0>::run(re, im);
   DitG<4, 0>::run(re, im);
   DitG<8, 0>::run(re, im);
@@ -97,32 +185,33 @@ EVF_HD void dft32_dit_tail(float (&re)[32], float (&im)[32]) {
 
 // Plain first stage (span 1, twiddle 1) for callers without anything to fuse into it.
 // In: index i holds x[bitrev5(i)].
-EVF_HD void dft32_dit_head(float (&re)[32], float (&im)[32]) { DitG<1, 0>::run(re, im); }
+template <typename V>
+EVF_HD void dft32_dit_head(V (&re)[32], V (&im)[32]) { DitG<1, 0>::run(re, im); }
 
 // First stage fused with a real scaling of the inputs (the analysis window): the pair at
 // indices (i, i + 1), i even, combines rows n = bitrev5(i) < 16 and n + 16:
 //   out[i] = wa*xa + wb*xb ,  out[i + 1] = wa*xa - wb*xb          (3 instructions)
-EVF_HD void win_head(float& lo, float& hi, float xa, float wa, float xb, float wb) {
-  const float t = wa * xa;
-  lo = fmaf(wb, xb, t);
-  hi = fmaf(-wb, xb, t);
+template <typename V, typename W>
+EVF_HD void win_head(V& lo, V& hi, V xa, W wa, V xb, W wb) {
+  const V t = v_mul(xa, wa);
+  lo = v_fma(xb, wb, t);
+  hi = v_fma(xb, v_neg(wb), t);
 }
 
 // First stage fused with a complex scaling (the four-step twiddles ta, tb = (cos, sin) of a
 // negative angle, i.e. t = c + i s with s <= 0 for the forward transform):
 //   A = ta*xa ;  out[i] = A + tb*xb ;  out[i + 1] = 2A - out[i]      (10 instructions)
-template <bool kUnitA>
-EVF_HD void tw_head(float& lor, float& loi, float& hir, float& hii, float xar, float xai, float tac,
-                    float tas, float xbr, float xbi, float tbc, float tbs) {
-  float Ar = xar, Ai = xai;
+template <bool kUnitA, typename V, typename W>
+EVF_HD void tw_head(V& lor, V& loi, V& hir, V& hii, V xar, V xai, W tac, W tas, V xbr, V xbi, W tbc, W tbs) {
+  V Ar = xar, Ai = xai;
   if constexpr (!kUnitA) {
-    Ar = fmaf(-xai, tas, xar * tac);
-    Ai = fmaf(xar, tas, xai * tac);
+    Ar = v_fma(xai, v_neg(tas), v_mul(xar, tac));
+    Ai = v_fma(xar, tas, v_mul(xai, tac));
   }
-  const float pr = fmaf(xbr, tbc, fmaf(-xbi, tbs, Ar));
-  const float pi = fmaf(xbr, tbs, fmaf(xbi, tbc, Ai));
-  hir = fmaf(2.0f, Ar, -pr);
-  hii = fmaf(2.0f, Ai, -pi);
+  const V pr = v_fma(xbr, tbc, v_fma(xbi, v_neg(tbs), Ar));
+  const V pi = v_fma(xbr, tbs, v_fma(xbi, tbc, Ai));
+  hir = v_fma(Ar, 2.0f, v_neg(pr));
+  hii = v_fma(Ai, 2.0f, v_neg(pi));
   lor = pr;
   loi = pi;
 }
