@@ -1,0 +1,416 @@
+// Audio front-end of the feature path (sm_100a): what Preprocessor.process_audio does to a loaded
+// waveform before process_spec sees it.
+//
+//   everyvoice/preprocessor/preprocessor.py:177-186   BS.1770 loudness gate  (torchaudio.transforms.Loudness)
+//   everyvoice/preprocessor/preprocessor.py:196-198   torchaudio.functional.resample(audio, sr, resample_rate)
+//   everyvoice/preprocessor/preprocessor.py:199-201   audio /= max|audio| ; audio *= 0.95
+//   everyvoice/preprocessor/preprocessor.py:216-218   truncation to a multiple of the hop size
+//   everyvoice/preprocessor/helpers.py:31-44          save_wav(..., PCM_S, 16 bit)  -> int16 samples
+//
+// Ragged batches throughout: utterance b owns [offsets[b], offsets[b + 1]) of a packed buffer.  The
+// arithmetic of the third-party pieces (torchaudio 2.7.1 functional.resample / functional.loudness /
+// lfilter) is restated from their published algorithm; oracle/ev_oracle.py holds the CPU restatement
+// and tests/golden/frontend_*.npz the outputs of the live reference.
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "evfeat_internal.h"
+
+struct evf_resampler {
+  int device = 0;
+  int orig = 1, neu = 1;  // reduced by their gcd
+  int width = 0;          // zero padding on the left, torchaudio's `width`
+  int taps = 0;           // 2 * width + orig
+  float* d_kt = nullptr;  // [taps][neu] transposed kernel bank: consecutive output phases are consecutive words
+};
+
+namespace evf {
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+__device__ __forceinline__ float sample_to_float(float v) { return v; }
+__device__ __forceinline__ float sample_to_float(short v) { return (float)v * (1.0f / 32768.0f); }
+
+constexpr int kRsThreads = 256;
+
+// y[j] = sum_k K[j % new][k] * xpad[(j / new) * orig + k],  xpad = x shifted by `width` zeros
+// (torchaudio _apply_sinc_resample_kernel: pad (width, width + orig), conv1d with stride orig, transpose, crop).
+// One block = 256 consecutive outputs of one utterance; their input span is staged in shared memory once
+// (coalesced), the kernel bank is read transposed so that the 32 lanes of a warp (consecutive phases) read
+// consecutive words.
+template <typename SampleT>
+__global__ void __launch_bounds__(kRsThreads) resample_kernel(const SampleT* __restrict__ x,
+                                                              const long long* __restrict__ in_off,
+                                                              const long long* __restrict__ out_off,
+                                                              const float* __restrict__ kt, int orig, int neu,
+                                                              int width, int taps, int span_cap,
+                                                              float* __restrict__ y) {
+  extern __shared__ float s_x[];
+  const int b = blockIdx.y;
+  const long long i0 = in_off[b], L = in_off[b + 1] - i0;
+  const long long o0 = out_off[b], Lo = out_off[b + 1] - o0;
+  const long long j0 = (long long)blockIdx.x * kRsThreads;
+  if (j0 >= Lo) return;
+  const long long blk0 = j0 / neu;                  // first input block of this tile
+  const long long base = blk0 * orig - width;       // utterance-relative index of s_x[0]
+  for (int e = threadIdx.x; e < span_cap; e += kRsThreads) {
+    const long long n = base + e;
+    s_x[e] = (n >= 0 && n < L) ? sample_to_float(x[i0 + n]) : 0.f;
+  }
+  __syncthreads();
+  const long long j = j0 + threadIdx.x;
+  if (j >= Lo) return;
+  const int phase = (int)(j % neu);
+  const int rel = (int)(j / neu - blk0) * orig;
+  const float* kp = kt + phase;
+  const float* xp = s_x + rel;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < taps; ++k) acc = fmaf(kp[(long long)k * neu], xp[k], acc);
+  y[o0 + j] = acc;
+}
+
+// max |x| per utterance (NaN-propagating like torch.max(torch.abs(.)): a NaN sample yields NaN).
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, const long long* __restrict__ off,
+                                                     unsigned* __restrict__ out_bits) {
+  const int b = blockIdx.y;
+  const long long o0 = off[b], L = off[b + 1] - o0;
+  float m = 0.f;
+  bool nan = false;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += (long long)gridDim.x * blockDim.x) {
+    const float v = fabsf(x[o0 + j]);
+    nan |= (v != v);
+    m = fmaxf(m, v);
+  }
+  unsigned bits = nan ? 0x7fc00000u : __float_as_uint(m);  // quiet NaN orders above every finite |x| and +inf
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+  __shared__ unsigned s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = bits;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned r = s[0];
+    for (int w = 1; w < 8; ++w) r = max(r, s[w]);
+    atomicMax(out_bits + b, r);
+  }
+}
+
+// out = (x / max) * 0.95 (two roundings, exactly `audio /= max; audio *= 0.95` in fp32), truncated to the kept
+// length, as float32 and / or PCM16 (round to nearest even of x * 32768, clipped: ffmpeg swresample flt -> s16)
+__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ x,
+                                                       const long long* __restrict__ src_off,
+                                                       const long long* __restrict__ dst_off,
+                                                       const float* __restrict__ absmax, float* __restrict__ out_f32,
+                                                       short* __restrict__ out_s16) {
+  const int b = blockIdx.y;
+  const long long s0 = src_off[b], d0 = dst_off[b], n = dst_off[b + 1] - d0;
+  const float m = absmax ? absmax[b] : 1.f;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+    float v = x[s0 + j];
+    if (absmax) v = __fmul_rn(__fdiv_rn(v, m), 0.95f);
+    if (out_f32) out_f32[d0 + j] = v;
+    if (out_s16) {
+      float q = rintf(v * 32768.0f);
+      q = fminf(fmaxf(q, -32768.f), 32767.f);
+      out_s16[d0 + j] = (v == v) ? (short)q : (short)0;
+    }
+  }
+}
+
+// ---- BS.1770-4 loudness (torchaudio.functional.loudness) ---------------------------------------
+struct Biquad {
+  float b0, b1, b2, a1, a2;  // already divided by a0
+};
+struct LoudnessParams {
+  Biquad shelf, highpass;
+  int gate, step;  // gate == 4 * step
+};
+
+// One thread per utterance: the two K-weighting biquads (direct form I, output clamped to [-1, 1] like
+// torchaudio's lfilter(clamp=True); the recursion itself runs on the unclamped state), squared and summed
+// per `step` samples; then the two gating passes over the 400 ms blocks (75 % overlap = 4 steps).
+__global__ void __launch_bounds__(32) loudness_kernel(const float* __restrict__ x, const long long* __restrict__ off,
+                                                      int n_utts, LoudnessParams P, float* __restrict__ scratch,
+                                                      const long long* __restrict__ scratch_off,
+                                                      float* __restrict__ lkfs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_utts) return;
+  const float* xs = x + off[b];
+  const long long L = off[b + 1] - off[b];
+  float* sub = scratch + scratch_off[b];
+  const long long n_sub = L / P.step;
+  const long long n_blk = (L >= P.gate) ? (L - P.gate) / P.step + 1 : 0;
+  if (n_blk == 0) {
+    lkfs[b] = __int_as_float(0x7fc00000);  // shorter than one gating block: the reference cannot measure it
+    return;
+  }
+  float x1 = 0.f, x2 = 0.f, u1 = 0.f, u2 = 0.f;   // shelf: inputs and unclamped outputs
+  float c1 = 0.f, c2 = 0.f, v1 = 0.f, v2 = 0.f;   // high-pass: (clamped) inputs and unclamped outputs
+  const Biquad s = P.shelf, h = P.highpass;
+  long long t = 0;
+  for (long long q = 0; q < n_sub; ++q) {
+    float acc = 0.f;
+    for (int i = 0; i < P.step; ++i, ++t) {
+      const float x0 = xs[t];
+      float u0 = fmaf(s.b0, x0, fmaf(s.b1, x1, s.b2 * x2));
+      u0 = fmaf(-s.a1, u1, fmaf(-s.a2, u2, u0));
+      x2 = x1;
+      x1 = x0;
+      u2 = u1;
+      u1 = u0;
+      const float c0 = fminf(fmaxf(u0, -1.f), 1.f);
+      float v0 = fmaf(h.b0, c0, fmaf(h.b1, c1, h.b2 * c2));
+      v0 = fmaf(-h.a1, v1, fmaf(-h.a2, v2, v0));
+      c2 = c1;
+      c1 = c0;
+      v2 = v1;
+      v1 = v0;
+      const float z = fminf(fmaxf(v0, -1.f), 1.f);
+      acc = fmaf(z, z, acc);
+    }
+    sub[q] = acc;
+  }
+  const float inv_gate = 1.0f / (float)P.gate;
+  auto energy = [&](long long i) { return ((sub[i] + sub[i + 1]) + (sub[i + 2] + sub[i + 3])) * inv_gate; };
+  auto lk = [](float e) { return -0.691f + 10.0f * log10f(e); };
+  // absolute gate (-70 LKFS)
+  float sum = 0.f;
+  int cnt = 0;
+  for (long long i = 0; i < n_blk; ++i) {
+    const float e = energy(i);
+    if (lk(e) > -70.0f) {
+      sum += e;
+      ++cnt;
+    }
+  }
+  const float gamma_rel = lk(sum / (float)cnt) - 10.0f;  // cnt == 0 -> NaN, like the reference
+  sum = 0.f;
+  cnt = 0;
+  for (long long i = 0; i < n_blk; ++i) {
+    const float e = energy(i);
+    const float l = lk(e);
+    if (l > -70.0f && l > gamma_rel) {
+      sum += e;
+      ++cnt;
+    }
+  }
+  lkfs[b] = lk(sum / (float)cnt);
+}
+
+// RBJ cookbook biquads as torchaudio.functional.{treble_biquad, highpass_biquad} build them: every operation in
+// the waveform's dtype (float32), then a1, a2 (and here b0..b2, which lfilter applies before dividing) over a0.
+Biquad make_treble(float sr, float gain_db, float fc, float Q) {
+  const float w0 = 6.283185307179586f * fc / sr, alpha = sinf(w0) / 2.0f / Q;
+  const float A = expf(gain_db / 40.0f * 2.302585092994046f);
+  const float t1 = 2.0f * sqrtf(A) * alpha, t2 = (A - 1.0f) * cosf(w0), t3 = (A + 1.0f) * cosf(w0);
+  const float b0 = A * ((A + 1.0f) + t2 + t1), b1 = -2.0f * A * ((A - 1.0f) + t3), b2 = A * ((A + 1.0f) + t2 - t1);
+  const float a0 = (A + 1.0f) - t2 + t1, a1 = 2.0f * ((A - 1.0f) - t3), a2 = (A + 1.0f) - t2 - t1;
+  return Biquad{b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0};
+}
+Biquad make_highpass(float sr, float fc, float Q) {
+  const float w0 = 6.283185307179586f * fc / sr, alpha = sinf(w0) / 2.0f / Q;
+  const float b0 = (1.0f + cosf(w0)) / 2.0f, b1 = -1.0f - cosf(w0), b2 = b0;
+  const float a0 = 1.0f + alpha, a1 = -2.0f * cosf(w0), a2 = 1.0f - alpha;
+  return Biquad{b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0};
+}
+
+long long gcd_ll(long long a, long long b) {
+  while (b) {
+    const long long t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+}  // namespace
+}  // namespace evf
+
+using namespace evf;
+
+extern "C" {
+
+int evf_resampler_create(int32_t orig_freq, int32_t new_freq, int32_t lowpass_filter_width, double rolloff,
+                         int32_t device, evf_resampler** out) {
+  if (out) *out = nullptr;
+  if (!out || orig_freq < 1 || new_freq < 1 || lowpass_filter_width < 1 || !(rolloff > 0.0)) {
+    set_error("evf_resampler_create: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+    set_error("evf_resampler_create: no such CUDA device; libevfeat has no CPU path");
+    return EVF_ERR_NO_DEVICE;
+  }
+  DeviceGuard guard(device);
+  if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+  evf_resampler* r = new (std::nothrow) evf_resampler();
+  if (!r) return EVF_ERR_OUT_OF_MEMORY;
+  r->device = device;
+  const long long g = gcd_ll(orig_freq, new_freq);
+  r->orig = (int)(orig_freq / g);
+  r->neu = (int)(new_freq / g);
+  // torchaudio _get_sinc_resample_kernel, sinc_interp_hann, evaluated in double then cast to float
+  const double base_freq = (double)(r->orig < r->neu ? r->orig : r->neu) * rolloff;
+  r->width = (int)std::ceil((double)lowpass_filter_width * r->orig / base_freq);
+  r->taps = 2 * r->width + r->orig;
+  if ((long long)r->taps * r->neu > (64ll << 20)) {
+    delete r;
+    set_error("evf_resampler_create: rate ratio needs a kernel bank of more than 64 Mi entries");
+    return EVF_ERR_UNSUPPORTED;
+  }
+  std::vector<float> kt((size_t)r->taps * r->neu);
+  const double lpw = (double)lowpass_filter_width, scale = base_freq / r->orig;
+  for (int p = 0; p < r->neu; ++p)
+    for (int k = 0; k < r->taps; ++k) {
+      double t = (double)(-p) / r->neu + (double)(k - r->width) / r->orig;
+      t *= base_freq;
+      t = t < -lpw ? -lpw : (t > lpw ? lpw : t);
+      const double c = std::cos(t * M_PI / lpw / 2.0);
+      const double window = c * c;
+      t *= M_PI;
+      const double sinc = (t == 0.0) ? 1.0 : std::sin(t) / t;
+      kt[(size_t)k * r->neu + p] = (float)(sinc * window * scale);
+    }
+  cudaError_t e = cudaMalloc(&r->d_kt, kt.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(r->d_kt, kt.data(), kt.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(r->d_kt);
+    delete r;
+    return cuda_fail(e, "resampler kernel bank upload");
+  }
+  *out = r;
+  return EVF_OK;
+}
+
+int evf_resampler_destroy(evf_resampler* r) {
+  if (!r) return EVF_OK;
+  DeviceGuard guard(r->device);
+  cudaFree(r->d_kt);
+  delete r;
+  return EVF_OK;
+}
+
+int64_t evf_resampler_out_length(const evf_resampler* r, int64_t n_in) {
+  if (!r || n_in < 0) return -1;
+  return (n_in * r->neu + r->orig - 1) / r->orig;  // ceil(new * n / orig), exact in integers
+}
+
+int evf_audio_resample(const evf_resampler* r, const void* in_dev, int32_t in_format, const int64_t* in_offsets_dev,
+                       const int64_t* out_offsets_dev, int32_t n_utts, int64_t max_out_len, float* out_dev,
+                       void* stream) {
+  if (!r || (n_utts > 0 && (!in_dev || !in_offsets_dev || !out_offsets_dev || !out_dev)) || n_utts < 0 ||
+      max_out_len < 0 || (in_format != EVF_SAMPLES_F32 && in_format != EVF_SAMPLES_S16)) {
+    set_error("evf_audio_resample: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (n_utts == 0 || max_out_len == 0) return EVF_OK;
+  DeviceGuard guard(r->device);
+  const int span = ((kRsThreads - 1) / r->neu + 2) * r->orig + r->taps;
+  const size_t smem = (size_t)span * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("evf_audio_resample: rate ratio needs more than 200 KB of shared memory per block");
+    return EVF_ERR_UNSUPPORTED;
+  }
+  const dim3 grid((unsigned)((max_out_len + kRsThreads - 1) / kRsThreads), (unsigned)n_utts);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long* io = reinterpret_cast<const long long*>(in_offsets_dev);
+  const long long* oo = reinterpret_cast<const long long*>(out_offsets_dev);
+  if (in_format == EVF_SAMPLES_S16) {
+    auto k = resample_kernel<short>;
+    if (smem > 48 * 1024) EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kRsThreads, smem, st>>>(static_cast<const short*>(in_dev), io, oo, r->d_kt, r->orig, r->neu, r->width,
+                                      r->taps, span, out_dev);
+  } else {
+    auto k = resample_kernel<float>;
+    if (smem > 48 * 1024) EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, kRsThreads, smem, st>>>(static_cast<const float*>(in_dev), io, oo, r->d_kt, r->orig, r->neu, r->width,
+                                      r->taps, span, out_dev);
+  }
+  EVF_CUDA(cudaGetLastError());
+  return EVF_OK;
+}
+
+int evf_audio_absmax(const float* x_dev, const int64_t* offsets_dev, int32_t n_utts, int64_t max_len,
+                     float* absmax_dev, void* stream) {
+  if (n_utts < 0 || max_len < 0 || (n_utts > 0 && (!x_dev || !offsets_dev || !absmax_dev))) {
+    set_error("evf_audio_absmax: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (n_utts == 0) return EVF_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EVF_CUDA(cudaMemsetAsync(absmax_dev, 0, (size_t)n_utts * sizeof(float), st));
+  if (max_len == 0) return EVF_OK;
+  long long gx = (max_len + 256 * 8 - 1) / (256 * 8);
+  if (gx < 1) gx = 1;
+  absmax_kernel<<<dim3((unsigned)gx, (unsigned)n_utts), 256, 0, st>>>(
+      x_dev, reinterpret_cast<const long long*>(offsets_dev), reinterpret_cast<unsigned*>(absmax_dev));
+  EVF_CUDA(cudaGetLastError());
+  return EVF_OK;
+}
+
+int evf_audio_finalize(const float* x_dev, const int64_t* src_offsets_dev, const int64_t* dst_offsets_dev,
+                       int32_t n_utts, int64_t max_kept_len, const float* absmax_dev, float* out_f32_dev,
+                       int16_t* out_s16_dev, void* stream) {
+  if (n_utts < 0 || max_kept_len < 0) {
+    set_error("evf_audio_finalize: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (n_utts == 0 || max_kept_len == 0) return EVF_OK;  // nothing kept: no output buffer needed
+  if (!x_dev || !src_offsets_dev || !dst_offsets_dev || (!out_f32_dev && !out_s16_dev)) {
+    set_error("evf_audio_finalize: null pointer");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  long long gx = (max_kept_len + 256 * 8 - 1) / (256 * 8);
+  finalize_kernel<<<dim3((unsigned)gx, (unsigned)n_utts), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_dev, reinterpret_cast<const long long*>(src_offsets_dev), reinterpret_cast<const long long*>(dst_offsets_dev),
+      absmax_dev, out_f32_dev, reinterpret_cast<short*>(out_s16_dev));
+  EVF_CUDA(cudaGetLastError());
+  return EVF_OK;
+}
+
+int64_t evf_audio_loudness_scratch_floats(int32_t sample_rate, int64_t n_samples) {
+  if (sample_rate < 1 || n_samples < 0) return -1;
+  const long long gate = (long long)std::nearbyint(0.4 * (double)sample_rate);
+  const long long step = (long long)std::nearbyint((double)gate * (1.0 - 0.75));
+  if (step < 1) return -1;
+  return n_samples / step + 4;  // one partial sum per 100 ms step; the block energies read up to 3 past their index
+}
+
+int evf_audio_loudness(const float* x_dev, const int64_t* offsets_dev, int32_t n_utts, int32_t sample_rate,
+                       float* scratch_dev, const int64_t* scratch_offsets_dev, float* lkfs_dev, void* stream) {
+  if (n_utts < 0 || sample_rate < 1 || (n_utts > 0 && (!x_dev || !offsets_dev || !scratch_dev || !scratch_offsets_dev || !lkfs_dev))) {
+    set_error("evf_audio_loudness: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  LoudnessParams P;
+  // Python's round() is round-half-even; 0.4 * sr and gate * 0.25 are compared on the same doubles
+  P.gate = (int)std::nearbyint(0.4 * (double)sample_rate);
+  P.step = (int)std::nearbyint((double)P.gate * (1.0 - 0.75));
+  if (P.step < 1 || P.gate != 4 * P.step) {
+    set_error("evf_audio_loudness: sample rate whose 400 ms gating block is not four 100 ms steps is not supported");
+    return EVF_ERR_UNSUPPORTED;
+  }
+  if (n_utts == 0) return EVF_OK;
+  P.shelf = make_treble((float)sample_rate, 4.0f, 1500.0f, (float)(1.0 / std::sqrt(2.0)));
+  P.highpass = make_highpass((float)sample_rate, 38.0f, 0.5f);
+  loudness_kernel<<<(n_utts + 31) / 32, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_dev, reinterpret_cast<const long long*>(offsets_dev), n_utts, P, scratch_dev,
+      reinterpret_cast<const long long*>(scratch_offsets_dev), lkfs_dev);
+  EVF_CUDA(cudaGetLastError());
+  return EVF_OK;
+}
+
+}  // extern "C"

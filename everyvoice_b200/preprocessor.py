@@ -10,8 +10,12 @@ Mirrors, with the reference's names and argument meaning:
   batched, ragged calls (one kernel launch for a whole list of utterances), and
   ``compute_stats`` / ``normalize_stats`` (:378-490) over in-memory shards.
 
-File I/O, text processing, audio ingest, config locks and the CLI are out of scope (they
-stay with the reference; see INTEGRATION.md for where these calls slot in).
+* ``process_audio``'s numerics (:131-218: length / loudness gates, resampling, peak normalisation,
+  truncation to a multiple of the hop size) as ``process_audio_batch`` / ``process_audio``
+  (``everyvoice_b200.audio``).
+
+File decoding beyond PCM wav, sox effects, text processing, config locks and the CLI are out of
+scope (they stay with the reference; see INTEGRATION.md for where these calls slot in).
 """
 
 from __future__ import annotations
@@ -68,6 +72,53 @@ class Preprocessor:
         if device is not None:
             self.input_spectral_transform.to(device)
             self.output_spectral_transform.to(device)
+
+    # ------------------------------------------------------------------------------------------
+    # Audio front-end (preprocessor.py:131-218)
+    # ------------------------------------------------------------------------------------------
+    @property
+    def audio_front_end(self):
+        from .audio import AudioFrontEnd
+
+        if getattr(self, "_audio_front_end", None) is None:
+            self._audio_front_end = AudioFrontEnd(self.audio_config, _require_cuda(self.device))
+            self.counters = self._audio_front_end.counters
+            self.multichannel_files_list = self._audio_front_end.multichannel_files_list
+        return self._audio_front_end
+
+    def process_audio_batch(self, audios, sr, normalize=True, resample_rate=None, hop_size=None,
+                            out_dtype=torch.float32, update_counters=True, names=None):
+        """``process_audio`` for a list of loaded waveforms (what ``load_audio`` returns) at rate ``sr``: gates,
+        loudness, resampling, peak normalisation and truncation on the device; see ``audio.ProcessedAudio``."""
+        return self.audio_front_end.process_audio_batch(audios, sr, normalize, resample_rate, hop_size, out_dtype,
+                                                        update_counters, names)
+
+    def process_audio(self, wav_path, normalize=True, resample_rate=None, sox_effects=None, hop_size=None,
+                      update_counters=True):
+        """Reference: preprocessor.py:131-218, same arguments and return value ``(audio[L] float32, sr)`` or
+        ``(None, None)`` when a gate skips the file.  Reads PCM wav files (8/16/32 bit) with the standard library;
+        ``sox_effects`` must be empty (sox stays with the reference)."""
+        import wave
+
+        if sox_effects:
+            raise NotImplementedError("sox effects are applied by the reference before this call")
+        with wave.open(str(wav_path), "rb") as w:
+            sr, ch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+            raw = w.readframes(n)
+        if width == 2:
+            a = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+        elif width == 4:
+            a = (np.frombuffer(raw, dtype="<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
+        elif width == 1:
+            a = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
+        else:
+            raise ValueError(f"unsupported PCM sample width {width}")
+        audio = torch.from_numpy(np.ascontiguousarray(a.reshape(-1, ch).T))
+        res = self.process_audio_batch([audio], sr, normalize, resample_rate, hop_size, torch.float32,
+                                       update_counters, [wav_path])
+        if not res.kept:
+            return None, None
+        return res.utterance(0).cpu(), res.sr
 
     # ------------------------------------------------------------------------------------------
     # The reference's per-utterance operators

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define EVF_ABI_VERSION 3
+#define EVF_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define EVF_API __attribute__((visibility("default")))
@@ -183,6 +183,42 @@ EVF_API int evf_stats_merge(const double* parts_dev, int32_t n_parts, int32_t st
                     void* stream);
 EVF_API int evf_normalize_by_gathered_stats(float* values_dev, int64_t n, const double* parts_dev, int32_t n_parts,
                                     int32_t stride_doubles, void* stream);
+
+/* ---- audio front-end: the numerics of Preprocessor.process_audio ----------------
+ * everyvoice/preprocessor/preprocessor.py:131-218.  Ragged batches: utterance b owns [offsets[b], offsets[b+1])
+ * of a packed buffer; every offsets array has n_utts + 1 entries. */
+typedef struct evf_resampler evf_resampler;
+
+/* torchaudio.functional.resample(audio, orig_freq, new_freq) as process_audio calls it (preprocessor.py:196-198):
+ * sinc_interp_hann; torchaudio's defaults are lowpass_filter_width = 6, rolloff = 0.99.  The kernel bank is built
+ * in double precision on the host exactly as torchaudio builds it. */
+EVF_API int evf_resampler_create(int32_t orig_freq, int32_t new_freq, int32_t lowpass_filter_width, double rolloff,
+                                 int32_t device, evf_resampler** resampler_out);
+EVF_API int evf_resampler_destroy(evf_resampler* resampler);
+/* ceil(new_freq * n_in / orig_freq): the length torchaudio crops the resampled waveform to; -1 on bad input */
+EVF_API int64_t evf_resampler_out_length(const evf_resampler* resampler, int64_t n_in);
+/* in_dev: packed float32 or int16 PCM (evf_sample_format; int16 is s / 32768 like torchaudio.load); out_dev: packed
+ * float32 laid out by out_offsets_dev, whose lengths must be evf_resampler_out_length of the input lengths;
+ * max_out_len = the longest of them (grid sizing). */
+EVF_API int evf_audio_resample(const evf_resampler* resampler, const void* in_dev, int32_t in_format,
+                               const int64_t* in_offsets_dev, const int64_t* out_offsets_dev, int32_t n_utts,
+                               int64_t max_out_len, float* out_dev, void* stream);
+/* absmax_dev[b] = max |x| of utterance b (NaN if it holds a NaN): torch.max(torch.abs(audio)), preprocessor.py:200 */
+EVF_API int evf_audio_absmax(const float* x_dev, const int64_t* offsets_dev, int32_t n_utts, int64_t max_len,
+                             float* absmax_dev, void* stream);
+/* Peak normalisation + truncation + output format in one pass (preprocessor.py:199-201, 216-218; helpers.py:31-44):
+ * for j < dst length: v = x[src_offsets[b] + j]; if absmax_dev: v = (v / absmax[b]) * 0.95f (two roundings, as the
+ * reference's two in-place ops); written as float32 (out_f32_dev) and / or PCM16 (out_s16_dev: round-half-even of
+ * v * 32768, clipped) at dst_offsets[b] + j.  dst lengths are the kept lengths (L // hop) * hop <= src lengths. */
+EVF_API int evf_audio_finalize(const float* x_dev, const int64_t* src_offsets_dev, const int64_t* dst_offsets_dev,
+                               int32_t n_utts, int64_t max_kept_len, const float* absmax_dev, float* out_f32_dev,
+                               int16_t* out_s16_dev, void* stream);
+/* torchaudio.transforms.Loudness(sr)(audio) for mono utterances (preprocessor.py:177-186: skipped when NaN or
+ * < -36): ITU-R BS.1770-4 K-weighting, 400 ms blocks with 75 % overlap, absolute (-70) and relative (-10) gates.
+ * scratch_dev: float32, evf_audio_loudness_scratch_floats(sr, L_b) entries per utterance at scratch_offsets_dev. */
+EVF_API int64_t evf_audio_loudness_scratch_floats(int32_t sample_rate, int64_t n_samples);
+EVF_API int evf_audio_loudness(const float* x_dev, const int64_t* offsets_dev, int32_t n_utts, int32_t sample_rate,
+                               float* scratch_dev, const int64_t* scratch_offsets_dev, float* lkfs_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -367,3 +367,150 @@ def truth_features(x, spec_type, n_fft, win_length, hop, sample_rate, n_mels, f_
     T = x.shape[-1] // hop
     logS = np.log(np.maximum(S, 1e-5))[:, :T]
     return logS, np.sqrt((logS**2).sum(axis=0))
+
+
+# ------------------------------------------------------------------------------------------------
+# audio front-end: the numerics of Preprocessor.process_audio
+# everyvoice/preprocessor/preprocessor.py:131-218.  Third-party arithmetic restated from
+# torchaudio 2.7.1 (pinned in pyproject.toml:78-80): functional.resample (_get_sinc_resample_kernel,
+# _apply_sinc_resample_kernel), functional.loudness, functional.{treble,highpass}_biquad, lfilter.
+# Pinned against the live reference by oracle/make_golden_frontend.py -> tests/golden/frontend.npz.
+# ------------------------------------------------------------------------------------------------
+def sinc_resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """torchaudio _get_sinc_resample_kernel (sinc_interp_hann, dtype=None: float64 math, float32 result).
+    Returns ``(kernel[new, taps] float32, width, orig, new)`` with the frequencies reduced by their gcd."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base_freq = min(orig, new) * rolloff
+    width = math.ceil(lowpass_filter_width * orig / base_freq)
+    idx = np.arange(-width, width + orig, dtype=np.float64)[None, :] / orig
+    t = np.arange(0, -new, -1, dtype=np.float64)[:, None] / new + idx
+    t = t * base_freq
+    t = np.clip(t, -lowpass_filter_width, lowpass_filter_width)
+    window = np.cos(t * math.pi / lowpass_filter_width / 2) ** 2
+    t = t * math.pi
+    scale = base_freq / orig
+    with np.errstate(invalid="ignore", divide="ignore"):
+        kern = np.where(t == 0, 1.0, np.sin(t) / t)
+    kern = kern * window * scale
+    return kern.astype(np.float32), width, orig, new
+
+
+def resample(x: np.ndarray, orig_freq: int, new_freq: int) -> np.ndarray:
+    """torchaudio.functional.resample(x[L], orig_freq, new_freq) (preprocessor.py:196-198), float32
+    accumulation through a strided sliding-window matmul."""
+    if orig_freq == new_freq:
+        return np.asarray(x, dtype=np.float32)
+    kern, width, orig, new = sinc_resample_kernel(orig_freq, new_freq)
+    x = np.asarray(x, dtype=np.float32)
+    L = len(x)
+    xp = np.concatenate([np.zeros(width, np.float32), x, np.zeros(width + orig, np.float32)])
+    taps = kern.shape[1]
+    n_blocks = (len(xp) - taps) // orig + 1
+    win = np.lib.stride_tricks.sliding_window_view(xp, taps)[::orig][:n_blocks]  # [blocks, taps]
+    y = (win @ kern.T).reshape(-1)  # block-major, phase-minor == conv1d(...).transpose(1, 2).reshape
+    target = -((-new * L) // orig)  # ceil(new * L / orig)
+    return np.ascontiguousarray(y[:target], dtype=np.float32)
+
+
+def _biquad_f32(x: np.ndarray, b, a) -> np.ndarray:
+    """Direct-form-I biquad in float32 like torchaudio's lfilter: feed-forward part, divided by a0, then the
+    recursion on the unclamped outputs; the result is clamped to [-1, 1] (lfilter's clamp=True)."""
+    f = np.float32
+    b0, b1, b2 = (f(v) for v in b)
+    a0, a1, a2 = (f(v) for v in a)
+    a1, a2 = f(a1 / a0), f(a2 / a0)
+    xp = np.concatenate([np.zeros(2, f), x.astype(f)])
+    ff = ((b2 * xp[:-2] + b1 * xp[1:-1]).astype(f) + b0 * xp[2:]).astype(f)
+    ff = (ff / a0).astype(f)
+    y = np.zeros(len(x) + 2, f)
+    for t in range(len(x)):
+        y[t + 2] = f(f(ff[t] - f(a2 * y[t])) - f(a1 * y[t + 1]))  # the order of torchaudio's CPU loop
+    return np.clip(y[2:], -1.0, 1.0)
+
+
+def k_weighting_coeffs(sample_rate: int):
+    """Coefficients of torchaudio's treble_biquad(4 dB, 1500 Hz, Q=1/sqrt(2)) and highpass_biquad(38 Hz, Q=0.5),
+    evaluated in float32 like torchaudio does (tensor math in the waveform dtype)."""
+    f = np.float32
+    sr = f(sample_rate)
+
+    def treble(gain, fc, Q):
+        w0 = f(f(f(2 * math.pi) * f(fc)) / sr)
+        alpha = f(f(np.sin(w0)) / f(2) / f(Q))
+        A = f(np.exp(f(f(gain) / f(40) * f(math.log(10)))))
+        t1 = f(f(2) * f(np.sqrt(A)) * alpha)
+        t2 = f((A - f(1)) * f(np.cos(w0)))
+        t3 = f((A + f(1)) * f(np.cos(w0)))
+        b = (A * ((A + 1) + t2 + t1), -2 * A * ((A - 1) + t3), A * ((A + 1) + t2 - t1))
+        a = ((A + 1) - t2 + t1, 2 * ((A - 1) - t3), (A + 1) - t2 - t1)
+        return tuple(f(v) for v in b), tuple(f(v) for v in a)
+
+    def highpass(fc, Q):
+        w0 = f(f(f(2 * math.pi) * f(fc)) / sr)
+        alpha = f(f(np.sin(w0)) / f(2) / f(Q))
+        c = f(np.cos(w0))
+        b0 = f((f(1) + c) / f(2))
+        return (b0, f(f(-1) - c), b0), (f(f(1) + alpha), f(f(-2) * c), f(f(1) - alpha))
+
+    return treble(4.0, 1500.0, 1 / math.sqrt(2)), highpass(38.0, 0.5)
+
+
+def loudness(x: np.ndarray, sample_rate: int) -> float:
+    """torchaudio.functional.loudness for a mono waveform (ITU-R BS.1770-4), preprocessor.py:177-179."""
+    gate = int(round(0.4 * sample_rate))
+    step = int(round(gate * (1 - 0.75)))
+    (tb, ta), (hb, ha) = k_weighting_coeffs(sample_rate)
+    z = _biquad_f32(_biquad_f32(np.asarray(x, np.float32), tb, ta), hb, ha)
+    if len(z) < gate:
+        return float("nan")
+    sq = np.square(z).astype(np.float32)
+    blocks = np.lib.stride_tricks.sliding_window_view(sq, gate)[::step]
+    energy = blocks.mean(axis=-1, dtype=np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lk = np.float32(-0.691) + np.float32(10) * np.log10(energy)
+        g1 = lk > -70.0
+        e1 = np.float32(energy[g1].sum(dtype=np.float32)) / np.float32(g1.sum())
+        gamma_rel = np.float32(-0.691) + np.float32(10) * np.log10(e1) - np.float32(10)
+        g2 = g1 & (lk > gamma_rel)
+        e2 = np.float32(energy[g2].sum(dtype=np.float32)) / np.float32(g2.sum())
+        return float(np.float32(-0.691) + np.float32(10) * np.log10(e2))
+
+
+def pcm16(x: np.ndarray) -> np.ndarray:
+    """float -> PCM_S 16 bit as torchaudio.save(encoding="PCM_S", bits_per_sample=16) stores it
+    (helpers.py:31-44).  PARITY UNPINNED: torchaudio.save needs torchcodec, which this container lacks; the rule is
+    restated from ffmpeg swresample's flt -> s16 conversion (lrintf(x * 32768), clipped)."""
+    return np.clip(np.rint(np.asarray(x, np.float32) * np.float32(32768.0)), -32768, 32767).astype(np.int16)
+
+
+def process_audio_tensor(audio: np.ndarray, sr: int, *, normalize=True, resample_rate=None, hop_size=None,
+                         min_audio_length=0.4, max_audio_length=11.0):
+    """Preprocessor.process_audio after load_audio (preprocessor.py:148-218) for a [C, L] float32 waveform.
+    Returns ``(audio[L'], sr)`` or ``(None, reason)`` when a gate skips the file."""
+    audio = np.asarray(audio, np.float32)
+    if audio.ndim == 1:
+        audio = audio[None]
+    if audio.shape[0] > 2:
+        return None, "multichannel_files"
+    seconds = audio.shape[1] / sr
+    if seconds > max_audio_length:
+        return None, "audio_too_long"
+    if seconds < min_audio_length:
+        return None, "audio_too_short"
+    if audio.shape[0] != 1:
+        raise NotImplementedError("the restatement covers mono input")
+    lk = loudness(audio[0], sr)
+    if math.isnan(lk) or lk < -36:
+        return None, "audio_empty"
+    x = audio[0]
+    if resample_rate is not None and resample_rate != sr:
+        x = resample(x, sr, resample_rate)
+        sr = resample_rate
+    if normalize:
+        x = (x / np.max(np.abs(x))).astype(np.float32)
+        x = (x * np.float32(0.95)).astype(np.float32)
+    if hop_size is None:
+        raise ValueError("We must know the hop size for processing audio because EveryVoice enforces that the "
+                         "number of samples is evenly divisible by the hop size")
+    return x[: (len(x) // hop_size) * hop_size], sr

@@ -1,0 +1,149 @@
+"""GPU parity of the audio front-end (evfeat_audio.cu behind ``Preprocessor.process_audio_batch`` /
+``process_audio``; reference: everyvoice/preprocessor/preprocessor.py:131-218) against the live-reference
+goldens (tests/golden/frontend.npz) and the CPU oracle on seeded ragged batches."""
+import math
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ATOL_RESAMPLED = 5e-5   # float32 FIR accumulation order; see tests/test_frontend_oracle.py
+ATOL_LOUDNESS = 2e-3    # LKFS
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(golden_dir / "frontend.npz")
+
+
+def _pre(cuda_device, **kw):
+    import everyvoice_b200 as ev
+
+    return ev.Preprocessor(ev.AudioConfig(spec_type="mel", **kw), device=cuda_device)
+
+
+def test_golden_cases_one_by_one(cuda_device, golden):
+    from oracle.make_golden_frontend import CASES, frontend_inputs
+
+    pre = _pre(cuda_device)
+    for name, (sr_in, rs, hop, *_rest) in CASES.items():
+        x, sr = frontend_inputs(name)
+        res = pre.process_audio_batch([torch.from_numpy(x)[None]], sr, resample_rate=rs, hop_size=hop)
+        if int(golden[f"{name}/skipped"]):
+            assert res.kept == [] and len(res.skipped) == 1, name
+            continue
+        ref = golden[f"{name}/audio"]
+        got = res.utterance(0).cpu().numpy()
+        assert res.kept == [0] and got.shape == ref.shape and res.sr == int(golden[f"{name}/sr"]), name
+        if rs is None or rs == sr_in:
+            assert np.array_equal(got, ref), name   # peak division, * 0.95, truncation: bit-exact
+        else:
+            assert float(np.abs(got - ref).max()) <= ATOL_RESAMPLED, (name, float(np.abs(got - ref).max()))
+        lk = float(res.loudness[0])
+        assert abs(lk - float(golden[f"{name}/loudness"])) <= ATOL_LOUDNESS, name
+
+
+def test_golden_cases_as_one_ragged_batch_with_gates(cuda_device, golden):
+    """All 22.05 kHz cases in ONE call: kept / skipped bookkeeping, counters and packing."""
+    from oracle.make_golden_frontend import CASES, frontend_inputs
+
+    names = [n for n, c in CASES.items() if c[0] == 22050]
+    pre = _pre(cuda_device)
+    res = pre.process_audio_batch([torch.from_numpy(frontend_inputs(n)[0]) for n in names], 22050,
+                                  resample_rate=22050, hop_size=256)
+    want_kept = [i for i, n in enumerate(names) if not int(golden[f"{n}/skipped"])]
+    assert res.kept == want_kept
+    for j, i in enumerate(res.kept):
+        assert np.array_equal(res.utterance(j).cpu().numpy(), golden[f"{names[i]}/audio"])
+    reasons = {names[i]: r for i, r in res.skipped.items()}
+    assert reasons == {"quiet_gated": "audio_empty", "silence_gated": "audio_empty", "too_short": "audio_too_short"}
+    assert pre.counters["processed_files"] == len(want_kept) and pre.counters["audio_empty"] == 2
+    assert int(res.offsets[-1]) == res.samples.numel() and all(int(o) % 256 == 0 for o in res.offsets)
+
+
+@pytest.mark.parametrize("orig,new", [(44100, 22050), (48000, 22050), (16000, 22050), (22050, 44100)])
+def test_resample_ragged_matches_oracle(cuda_device, orig, new):
+    from everyvoice_b200 import Resampler, synth
+    from oracle import ev_oracle as O
+
+    rng = np.random.default_rng(orig + new)
+    xs = [synth.speech_like(int(n), orig, seed=60 + i) for i, n in enumerate(rng.integers(300, 30000, size=6))]
+    xs.append(synth.white_noise(1, seed=1))  # a single sample
+    packed, off = synth.pack_ragged(xs)
+    rs = Resampler(orig, new, cuda_device)
+    y, y_off = rs(torch.from_numpy(packed).to(cuda_device), off)
+    for b, x in enumerate(xs):
+        want = O.resample(x, orig, new)
+        got = y[int(y_off[b]) : int(y_off[b + 1])].cpu().numpy()
+        assert got.shape == want.shape and len(got) == math.ceil(new * len(x) / orig)
+        assert float(np.abs(got - want).max()) <= 1e-5
+    # int16 PCM input is s / 32768 on load
+    pcm = (packed * 32767).round().astype(np.int16)
+    y16, _ = rs(torch.from_numpy(pcm).to(cuda_device), off)
+    yf, _ = rs(torch.from_numpy(pcm.astype(np.float32) / 32768.0).to(cuda_device), off)
+    assert torch.equal(y16, yf)
+
+
+def test_pcm16_output_and_feature_kernel_round_trip(cuda_device):
+    """process_audio_batch(out_dtype=int16) is what save_wav + torchaudio.load would hand to process_spec: the
+    feature kernel consumes it directly, bit-identical to the float path on the dequantised samples."""
+    from everyvoice_b200 import synth
+    from oracle import ev_oracle as O
+
+    pre = _pre(cuda_device)
+    xs = [synth.speech_like(int(22050 * s) + 11, 22050, seed=70 + i) * np.float32(0.5) for i, s in enumerate((0.6, 1.4, 0.9))]
+    res_f = pre.process_audio_batch(xs, 22050, hop_size=256, out_dtype=torch.float32)
+    res_i = pre.process_audio_batch(xs, 22050, hop_size=256, out_dtype=torch.int16)
+    assert np.array_equal(res_f.offsets, res_i.offsets)
+    assert np.array_equal(res_i.samples.cpu().numpy(), O.pcm16(res_f.samples.cpu().numpy()))
+    peak = float(res_f.utterance(1).abs().max())
+    assert abs(peak - 0.95) <= 1e-6
+    tf = pre.input_spectral_transform
+    f_i = tf.features_ragged(res_i.samples, res_i.offsets)
+    f_f = tf.features_ragged(res_i.samples.float() / 32768.0, res_i.offsets)
+    assert torch.equal(f_i.spec, f_f.spec)
+    assert f_i.spec.shape[0] == int(res_i.offsets[-1]) // 256
+
+
+def test_loudness_batch_matches_oracle(cuda_device):
+    from everyvoice_b200 import loudness_batch, synth
+    from oracle import ev_oracle as O
+
+    for sr in (22050, 44100, 16000):
+        xs = [synth.speech_like(int(sr * s), sr, seed=80 + i) * np.float32(g)
+              for i, (s, g) in enumerate(((0.5, 0.7), (1.1, 0.05), (0.45, 1.0), (0.8, 0.002)))]
+        packed, off = synth.pack_ragged(xs)
+        got = loudness_batch(torch.from_numpy(packed).to(cuda_device), off, sr).cpu().numpy()
+        for b, x in enumerate(xs):
+            want = O.loudness(x, sr)
+            assert abs(float(got[b]) - want) <= ATOL_LOUDNESS, (sr, b, float(got[b]), want)
+
+
+def test_process_audio_file_mirror(cuda_device, tmp_path):
+    """The single-file surface: (audio, sr) / (None, None), ValueError without hop_size (the reference's
+    test_process_audio, everyvoice/tests/test_preprocessing.py:356-383)."""
+    from everyvoice_b200 import synth
+    from oracle import ev_oracle as O
+
+    pre = _pre(cuda_device)
+    x = synth.speech_like(44100, 44100, seed=91) * np.float32(0.4)
+    pcm = O.pcm16(x)
+    path = tmp_path / "a.wav"
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(44100)
+        w.writeframes(pcm.tobytes())
+    with pytest.raises(ValueError):
+        pre.process_audio(path)
+    audio, sr = pre.process_audio(path, resample_rate=22050, hop_size=256)
+    want, want_sr = O.process_audio_tensor(pcm.astype(np.float32) / 32768.0, 44100, resample_rate=22050, hop_size=256)
+    assert sr == want_sr == 22050 and audio.dtype == torch.float32 and audio.shape[0] % 256 == 0
+    assert audio.shape[0] == len(want) and len(x) * 22050 // 44100 - audio.shape[0] < 256
+    assert float(np.abs(audio.numpy() - want).max()) <= ATOL_RESAMPLED
+    pre2 = _pre(cuda_device, min_audio_length=2.0)
+    assert pre2.process_audio(path, hop_size=256) == (None, None)
+    assert pre2.counters["audio_too_short"] == 1
