@@ -80,7 +80,7 @@ PROTOTYPES = {
     "evf_audio_absmax": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, _P]),
     "evf_audio_finalize": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, _P, _P, _P, _P]),
     "evf_audio_loudness_scratch_floats": (C.c_int64, [C.c_int32, C.c_int64]),
-    "evf_audio_loudness": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "evf_audio_loudness": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P]),
 }
 
 

@@ -71,21 +71,30 @@ class Resampler:
     def out_length(self, n: int) -> int:
         return int(self._lib.evf_resampler_out_length(self.handle, int(n)))
 
+    def out_lengths(self, lens: np.ndarray) -> np.ndarray:
+        """``ceil(new * n / orig)`` for an array of lengths (the integer form of evf_resampler_out_length)."""
+        g = int(np.gcd(self.orig_freq, self.new_freq))
+        o, n = self.orig_freq // g, self.new_freq // g
+        return (np.asarray(lens, dtype=np.int64) * n + o - 1) // o
+
+    def launch(self, samples, d_in_off, d_out_off, n_utts: int, max_out_len: int, out: torch.Tensor):
+        """The raw asynchronous call with offsets already on the device."""
+        fmt = _lib.SAMPLES_S16 if samples.dtype == torch.int16 else _lib.SAMPLES_F32
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.evf_audio_resample(self.handle, _ptr(samples), fmt, _ptr(d_in_off), _ptr(d_out_off),
+                                                    int(n_utts), int(max_out_len), _ptr(out), _stream_ptr(self.device)))
+
     def __call__(self, samples: torch.Tensor, offsets) -> tuple[torch.Tensor, np.ndarray]:
         """``samples``: packed float32 / int16 device tensor; returns ``(packed float32, out_offsets)``."""
         offsets = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
         lens = np.diff(offsets)
-        out_lens = np.array([self.out_length(int(n)) for n in lens], dtype=np.int64)
+        out_lens = self.out_lengths(lens)
         out_off = np.concatenate([[0], np.cumsum(out_lens)]).astype(np.int64)
         out = torch.empty(int(out_off[-1]), dtype=torch.float32, device=self.device)
-        fmt = _lib.SAMPLES_S16 if samples.dtype == torch.int16 else _lib.SAMPLES_F32
         if samples.dtype not in (torch.float32, torch.int16) or not samples.is_contiguous():
             raise ValueError("samples must be a contiguous float32 or int16 tensor")
         d_in, d_out = torch.from_numpy(offsets).to(self.device), torch.from_numpy(out_off).to(self.device)
-        with torch.cuda.device(self.device):
-            _lib.check(self._lib.evf_audio_resample(self.handle, _ptr(samples), fmt, _ptr(d_in), _ptr(d_out), len(lens),
-                                                    int(out_lens.max()) if len(lens) else 0, _ptr(out),
-                                                    _stream_ptr(self.device)))
+        self.launch(samples, d_in, d_out, len(lens), int(out_lens.max()) if len(lens) else 0, out)
         return out, out_off
 
 
@@ -95,15 +104,18 @@ def loudness_batch(samples: torch.Tensor, offsets, sample_rate: int) -> torch.Te
     device = samples.device
     offsets = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
     lens = np.diff(offsets)
-    per = np.array([lib.evf_audio_loudness_scratch_floats(int(sample_rate), int(n)) for n in lens], dtype=np.int64)
-    if (per < 0).any():
+    one = int(lib.evf_audio_loudness_scratch_floats(int(sample_rate), int(sample_rate)))  # floats per second + 4
+    if one < 0:
         raise ValueError("unsupported sampling rate for the loudness measurement")
+    step = int(sample_rate) // (one - 4)  # the 100 ms step in samples
+    per = lens // step + 4                # == evf_audio_loudness_scratch_floats(sr, n) for every n
     s_off = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
     scratch = torch.empty(int(s_off[-1]), dtype=torch.float32, device=device)
     out = torch.empty(len(lens), dtype=torch.float32, device=device)
     d_off, d_soff = torch.from_numpy(offsets).to(device), torch.from_numpy(s_off).to(device)
     with torch.cuda.device(device):
-        _lib.check(lib.evf_audio_loudness(_ptr(samples), _ptr(d_off), len(lens), int(sample_rate), _ptr(scratch),
+        _lib.check(lib.evf_audio_loudness(_ptr(samples), _ptr(d_off), len(lens), int(lens.max()) if len(lens) else 0,
+                                          int(sample_rate), _ptr(scratch),
                                           _ptr(d_soff), _ptr(out), _stream_ptr(device)))
     return out
 
@@ -167,7 +179,10 @@ class AudioFrontEnd:
                                   int(resample_rate or sr), [], skipped, loud)
         lens = np.array([w.numel() for w in waves], dtype=np.int64)
         off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-        x = torch.cat(waves).to(dev, non_blocking=True).contiguous()
+        # one device buffer, one asynchronous copy per utterance (pinned host tensors overlap; no host-side concat)
+        x = torch.empty(int(off[-1]), dtype=torch.float32, device=dev)
+        for j, w in enumerate(waves):
+            x[int(off[j]) : int(off[j + 1])].copy_(w, non_blocking=True)
         # ---- loudness gate (:177-186) -----------------------------------------------------------
         lk = loudness_batch(x, off, sr).cpu().numpy()
         loud[cand] = lk

@@ -215,10 +215,13 @@ EVF_API int evf_audio_finalize(const float* x_dev, const int64_t* src_offsets_de
                                int16_t* out_s16_dev, void* stream);
 /* torchaudio.transforms.Loudness(sr)(audio) for mono utterances (preprocessor.py:177-186: skipped when NaN or
  * < -36): ITU-R BS.1770-4 K-weighting, 400 ms blocks with 75 % overlap, absolute (-70) and relative (-10) gates.
- * scratch_dev: float32, evf_audio_loudness_scratch_floats(sr, L_b) entries per utterance at scratch_offsets_dev. */
+ * scratch_dev: float32, evf_audio_loudness_scratch_floats(sr, L_b) entries per utterance at scratch_offsets_dev;
+ * max_len = the longest utterance (grid sizing).  The filters' recursion is restarted every 100 ms with a 100 ms
+ * run-in (state error < 1e-7 relative), so all steps of all utterances run in parallel. */
 EVF_API int64_t evf_audio_loudness_scratch_floats(int32_t sample_rate, int64_t n_samples);
-EVF_API int evf_audio_loudness(const float* x_dev, const int64_t* offsets_dev, int32_t n_utts, int32_t sample_rate,
-                               float* scratch_dev, const int64_t* scratch_offsets_dev, float* lkfs_dev, void* stream);
+EVF_API int evf_audio_loudness(const float* x_dev, const int64_t* offsets_dev, int32_t n_utts, int64_t max_len,
+                               int32_t sample_rate, float* scratch_dev, const int64_t* scratch_offsets_dev,
+                               float* lkfs_dev, void* stream);
 
 #ifdef __cplusplus
 }
