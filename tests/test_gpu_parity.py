@@ -643,3 +643,64 @@ def test_other_baseline_configs_sampled_oracle(cuda_device, config, spec_type):
         truth = O.truth_features(xb.numpy(), spec_type, n_fft, win, hop, sr, n_mels, f_min, f_max)[0] if spec_type == "linear" else None
         assert_log_spec_close(feats.utterance(b).cpu(), o_spec, truth, spec_type)
         assert float((feats.utterance_energy(b).cpu() - o_energy).abs().max()) <= ATOL_LOG
+
+
+def test_config5_rank_shard_of_100h_corpus(cuda_device):
+    """BASELINE.json configs[4]: a 100 h corpus at 22.05 kHz sharded by utterance over 8 GPUs.  One rank's shard
+    (1/8 of the corpus: ~8.2 k utterances, 12.5 h, 4 GB of float32 samples) runs here at full size as ONE ragged
+    batch; the corpus statistics are exchanged between 8 LOGICAL shards of it exactly as the ranks do after the
+    all-gather.  Size-independent properties: exact frame counts, energy == ||log-mel||, the greedy shard balance,
+    merged == global statistics, normalise-then-denormalise round trip."""
+    import everyvoice_b200 as ev
+    from everyvoice_b200 import synth
+    from everyvoice_b200.distributed import finalize_stats, merge_stats, shard_utterances
+    from oracle import ev_oracle as O
+
+    sr, hop, world = 22050, 256, 8
+    n_corpus = 65455                                         # SURVEY 8d: ~65 455 utterances of mean 5.5 s = 100 h
+    lens_all = synth.utterance_lengths(n_corpus, sr, hop, 1238)
+    assert abs(lens_all.sum() / sr / 3600 - 100.0) < 1.0     # the corpus IS about 100 hours
+    shards = shard_utterances(lens_all, world)
+    loads = np.array([lens_all[s].sum() for s in shards], dtype=np.float64)
+    assert loads.max() / loads.mean() < 1.001                # greedy longest-first: < 0.1 % imbalance
+    assert sorted(np.concatenate(shards).tolist()) == list(range(n_corpus))
+    mine = np.asarray(shards[3])                              # this "rank"
+    lens = lens_all[mine]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(1238 + 3)
+    x = torch.rand(int(off[-1]), device=cuda_device, generator=g) * 1.9 - 0.95
+    pre = ev.Preprocessor(ev.AudioConfig(spec_type="mel"), device=cuda_device)
+    feats = pre.process_spec_batch(x, off)
+    T = lens // hop
+    assert np.array_equal(np.diff(feats.frame_offsets), T) and feats.spec.shape == (int(T.sum()), 80)
+    e_torch = torch.linalg.norm(feats.spec, dim=1)
+    assert float((feats.energy - e_torch).abs().max()) <= 2e-5 * float(e_torch.max())
+    otf = O.get_spectral_transform("mel", 1024, 1024, hop, sr, 80, 0, 8000)
+    for b in (0, len(lens) // 2, len(lens) - 1):
+        o_spec, o_energy, _ = O.features_one(x[off[b] : off[b + 1]].cpu(), otf, hop)
+        assert float((feats.utterance(b).cpu() - o_spec).abs().max()) <= ATOL_LOG
+        assert float((feats.utterance_energy(b).cpu() - o_energy).abs().max()) <= ATOL_LOG
+    # statistics of the frame-level energy: 8 logical shards -> [8, 5] summaries -> merged == one global pass
+    f_off = feats.frame_offsets
+    cuts = [int(f_off[i]) for i in np.linspace(0, len(lens), world + 1).astype(int)]
+    parts = []
+    for r in range(world):
+        s = ev.Scaler(cuda_device)
+        s.append(feats.energy[cuts[r] : cuts[r + 1]])
+        parts.append(s.partial_stats().clone())
+    gathered = torch.stack(parts).contiguous()
+    whole = ev.Scaler(cuda_device)
+    whole.append(feats.energy)
+    m, w = merge_stats(gathered).cpu(), whole.partial_stats().cpu()
+    assert m[0] == w[0] == float(T.sum()) and m[3] == w[3] and m[4] == w[4]
+    assert torch.allclose(m[1:3], w[1:3], rtol=1e-12, atol=0)
+    st = finalize_stats(m.tolist(), len(lens))
+    e64 = feats.energy.double()
+    assert st["mean"] == pytest.approx(float(e64.mean()), rel=1e-9)
+    assert st["std"] == pytest.approx(float(e64.std(unbiased=True)), rel=1e-7)
+    normed = feats.energy.clone()
+    ev.Scaler(cuda_device).normalize_by_device_stats_(normed, gathered)
+    assert abs(float(normed.double().mean())) < 1e-4 and abs(float(normed.double().std()) - 1.0) < 1e-4
+    back = normed * st["std"] + st["mean"]
+    assert float((back - feats.energy).abs().max()) <= 1e-4 * float(feats.energy.abs().max())
