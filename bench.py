@@ -299,6 +299,8 @@ def run_ours(args, w, wname):
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its version banner to stdout; stdout carries exactly ONE JSON line (bench contract)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     # CPU baseline first (rank 0, N == 1 only), before the GPU gets busy
