@@ -697,8 +697,9 @@ def test_config5_rank_shard_of_100h_corpus(cuda_device):
     assert torch.allclose(m[1:3], w[1:3], rtol=1e-12, atol=0)
     st = finalize_stats(m.tolist(), len(lens))
     e64 = feats.energy.double()
-    assert st["mean"] == pytest.approx(float(e64.mean()), rel=1e-9)
-    assert st["std"] == pytest.approx(float(e64.std(unbiased=True)), rel=1e-7)
+    # finalize_stats reports float32-rounded numbers like the reference's Scaler (helpers.py:86-106)
+    assert st["mean"] == pytest.approx(float(e64.mean()), rel=2e-7)
+    assert st["std"] == pytest.approx(float(e64.std(unbiased=True)), rel=1e-6)
     normed = feats.energy.clone()
     ev.Scaler(cuda_device).normalize_by_device_stats_(normed, gathered)
     assert abs(float(normed.double().mean())) < 1e-4 and abs(float(normed.double().std()) - 1.0) < 1e-4
