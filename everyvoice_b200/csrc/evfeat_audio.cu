@@ -23,6 +23,7 @@ struct evf_resampler {
   int width = 0;          // zero padding on the left, torchaudio's `width`
   int taps = 0;           // 2 * width + orig
   float* d_kt = nullptr;  // [taps][neu] transposed kernel bank: consecutive output phases are consecutive words
+  std::vector<float> h_kt;  // host copy: the small-ratio kernels take the bank by value (constant bank operands)
 };
 
 namespace evf {
@@ -83,28 +84,43 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(const SampleT* __r
 }
 
 // Small integer ratios (44.1 -> 22.05 kHz and back): a thread owns R consecutive input blocks = R * NEU consecutive
-// outputs, whose (R - 1) * ORIG + TAPS input samples sit in registers; the kernel bank is read with warp-uniform
-// loads.  Same summation order as resample_kernel (bit-identical results), 3-4x fewer memory instructions per output.
+// outputs, whose (R - 1) * ORIG + TAPS input samples sit in registers.  The block's input span is staged in shared
+// memory with coalesced loads; sample n lives at word n + n / (R * ORIG), so the windows of neighbouring threads start
+// R * ORIG + 1 words apart (odd: the 32 lanes of a window read hit 32 distinct banks).  The kernel bank (<= 30
+// coefficients) is a by-value kernel parameter, i.e. constant-bank operands of the FFMAs: no load instructions.
+// Same summation order as resample_kernel (bit-identical results).
+template <int N>
+struct SmallBank {
+  float k[N];
+};
 template <typename SampleT, int ORIG, int NEU, int TAPS, int R>
 __global__ void __launch_bounds__(kRsThreads) resample_small_kernel(const SampleT* __restrict__ x,
                                                                     const long long* __restrict__ in_off,
                                                                     const long long* __restrict__ out_off,
-                                                                    const float* __restrict__ kt, int width,
+                                                                    const SmallBank<TAPS * NEU> kt, int width,
                                                                     float* __restrict__ y) {
+  constexpr int S = R * ORIG;                          // samples between the windows of neighbouring threads
+  constexpr int W = (R - 1) * ORIG + TAPS;             // window of one thread
+  constexpr int SPAN = (kRsThreads - 1) * S + W;       // samples of one block
+  __shared__ float s_x[SPAN + SPAN / S + 1];
   const int b = blockIdx.y;
   const long long i0 = in_off[b], L = in_off[b + 1] - i0;
   const long long o0 = out_off[b], Lo = out_off[b + 1] - o0;
-  const long long ib = ((long long)blockIdx.x * kRsThreads + threadIdx.x) * R;  // first input block of this thread
-  if (ib * NEU >= Lo) return;
-  constexpr int W = (R - 1) * ORIG + TAPS;
-  float w[W];
-  const long long base = ib * ORIG - width;
+  const long long ib0 = (long long)blockIdx.x * kRsThreads * R;  // first input block of this CTA
+  if (ib0 * NEU >= Lo) return;
+  const long long base = ib0 * ORIG - width;           // utterance-relative sample index of staged word 0
   const SampleT* xs = x + i0;
-#pragma unroll
-  for (int e = 0; e < W; ++e) {
+  for (int e = threadIdx.x; e < SPAN; e += kRsThreads) {
     const long long n = base + e;
-    w[e] = (n >= 0 && n < L) ? sample_to_float(__ldg(xs + n)) : 0.f;
+    s_x[e + e / S] = (n >= 0 && n < L) ? sample_to_float(__ldg(xs + n)) : 0.f;
   }
+  __syncthreads();
+  const long long ib = ib0 + (long long)threadIdx.x * R;
+  if (ib * NEU >= Lo) return;
+  float w[W];
+  const float* sw = s_x + threadIdx.x * (S + 1);       // word of sample threadIdx.x * S
+#pragma unroll
+  for (int e = 0; e < W; ++e) w[e] = sw[e + e / S];
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -112,22 +128,32 @@ __global__ void __launch_bounds__(kRsThreads) resample_small_kernel(const Sample
       const long long j = (ib + r) * NEU + ph;
       float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < TAPS; ++k) acc = fmaf(__ldg(kt + k * NEU + ph), w[r * ORIG + k], acc);
+      for (int k = 0; k < TAPS; ++k) acc = fmaf(kt.k[k * NEU + ph], w[r * ORIG + k], acc);
       if (j < Lo) y[o0 + j] = acc;
     }
 }
 
-// max |x| per utterance (NaN-propagating like torch.max(torch.abs(.)): a NaN sample yields NaN).
+// max |x| per utterance (NaN-propagating like torch.max(torch.abs(.)): a NaN sample yields NaN).  A block owns 2048
+// consecutive samples of one utterance; the 8 loads of a thread are independent (64 KB in flight per SM).
+constexpr int kStreamItems = 8;
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, const long long* __restrict__ off,
                                                      unsigned* __restrict__ out_bits) {
   const int b = blockIdx.y;
   const long long o0 = off[b], L = off[b + 1] - o0;
+  const long long j0 = (long long)blockIdx.x * (256 * kStreamItems) + threadIdx.x;
+  if ((long long)blockIdx.x * (256 * kStreamItems) >= L) return;
+  float v[kStreamItems];
+#pragma unroll
+  for (int i = 0; i < kStreamItems; ++i) {
+    const long long j = j0 + i * 256;
+    v[i] = (j < L) ? fabsf(__ldg(x + o0 + j)) : 0.f;
+  }
   float m = 0.f;
   bool nan = false;
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < L; j += (long long)gridDim.x * blockDim.x) {
-    const float v = fabsf(x[o0 + j]);
-    nan |= (v != v);
-    m = fmaxf(m, v);
+#pragma unroll
+  for (int i = 0; i < kStreamItems; ++i) {
+    nan |= (v[i] != v[i]);
+    m = fmaxf(m, v[i]);
   }
   unsigned bits = nan ? 0x7fc00000u : __float_as_uint(m);  // quiet NaN orders above every finite |x| and +inf
 #pragma unroll
@@ -151,15 +177,26 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
                                                        short* __restrict__ out_s16) {
   const int b = blockIdx.y;
   const long long s0 = src_off[b], d0 = dst_off[b], n = dst_off[b + 1] - d0;
+  if ((long long)blockIdx.x * (256 * kStreamItems) >= n) return;
   const float m = absmax ? absmax[b] : 1.f;
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
-    float v = x[s0 + j];
-    if (absmax) v = __fmul_rn(__fdiv_rn(v, m), 0.95f);
-    if (out_f32) out_f32[d0 + j] = v;
+  const long long j0 = (long long)blockIdx.x * (256 * kStreamItems) + threadIdx.x;
+  float v[kStreamItems];
+#pragma unroll
+  for (int i = 0; i < kStreamItems; ++i) {
+    const long long j = j0 + i * 256;
+    v[i] = (j < n) ? __ldg(x + s0 + j) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < kStreamItems; ++i) {
+    const long long j = j0 + i * 256;
+    if (j >= n) break;
+    float t = v[i];
+    if (absmax) t = __fmul_rn(__fdiv_rn(t, m), 0.95f);
+    if (out_f32) out_f32[d0 + j] = t;
     if (out_s16) {
-      float q = rintf(v * 32768.0f);
+      float q = rintf(t * 32768.0f);
       q = fminf(fmaxf(q, -32768.f), 32767.f);
-      out_s16[d0 + j] = (v == v) ? (short)q : (short)0;
+      out_s16[d0 + j] = (t == t) ? (short)q : (short)0;
     }
   }
 }
@@ -362,6 +399,7 @@ int evf_resampler_create(int32_t orig_freq, int32_t new_freq, int32_t lowpass_fi
     delete r;
     return cuda_fail(e, "resampler kernel bank upload");
   }
+  r->h_kt.swap(kt);
   *out = r;
   return EVF_OK;
 }
@@ -400,22 +438,26 @@ int evf_audio_resample(const evf_resampler* r, const void* in_dev, int32_t in_fo
     return dim3((unsigned)((blocks_in + (long long)R * kRsThreads - 1) / ((long long)R * kRsThreads)), (unsigned)n_utts);
   };
   if (r->orig == 2 && r->neu == 1 && r->taps == 28) {
+    SmallBank<28> bank;
+    for (int i = 0; i < 28; ++i) bank.k[i] = r->h_kt[i];
     if (s16)
       resample_small_kernel<short, 2, 1, 28, R><<<small_grid(1), kRsThreads, 0, st>>>(
-          static_cast<const short*>(in_dev), io, oo, r->d_kt, r->width, out_dev);
+          static_cast<const short*>(in_dev), io, oo, bank, r->width, out_dev);
     else
       resample_small_kernel<float, 2, 1, 28, R><<<small_grid(1), kRsThreads, 0, st>>>(
-          static_cast<const float*>(in_dev), io, oo, r->d_kt, r->width, out_dev);
+          static_cast<const float*>(in_dev), io, oo, bank, r->width, out_dev);
     EVF_CUDA(cudaGetLastError());
     return EVF_OK;
   }
   if (r->orig == 1 && r->neu == 2 && r->taps == 15) {
+    SmallBank<30> bank;
+    for (int i = 0; i < 30; ++i) bank.k[i] = r->h_kt[i];
     if (s16)
       resample_small_kernel<short, 1, 2, 15, R><<<small_grid(2), kRsThreads, 0, st>>>(
-          static_cast<const short*>(in_dev), io, oo, r->d_kt, r->width, out_dev);
+          static_cast<const short*>(in_dev), io, oo, bank, r->width, out_dev);
     else
       resample_small_kernel<float, 1, 2, 15, R><<<small_grid(2), kRsThreads, 0, st>>>(
-          static_cast<const float*>(in_dev), io, oo, r->d_kt, r->width, out_dev);
+          static_cast<const float*>(in_dev), io, oo, bank, r->width, out_dev);
     EVF_CUDA(cudaGetLastError());
     return EVF_OK;
   }
@@ -451,8 +493,7 @@ int evf_audio_absmax(const float* x_dev, const int64_t* offsets_dev, int32_t n_u
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   EVF_CUDA(cudaMemsetAsync(absmax_dev, 0, (size_t)n_utts * sizeof(float), st));
   if (max_len == 0) return EVF_OK;
-  long long gx = (max_len + 256 * 8 - 1) / (256 * 8);
-  if (gx < 1) gx = 1;
+  const long long gx = (max_len + 256 * kStreamItems - 1) / (256 * kStreamItems);
   absmax_kernel<<<dim3((unsigned)gx, (unsigned)n_utts), 256, 0, st>>>(
       x_dev, reinterpret_cast<const long long*>(offsets_dev), reinterpret_cast<unsigned*>(absmax_dev));
   EVF_CUDA(cudaGetLastError());
@@ -471,7 +512,7 @@ int evf_audio_finalize(const float* x_dev, const int64_t* src_offsets_dev, const
     set_error("evf_audio_finalize: null pointer");
     return EVF_ERR_INVALID_ARGUMENT;
   }
-  long long gx = (max_kept_len + 256 * 8 - 1) / (256 * 8);
+  const long long gx = (max_kept_len + 256 * kStreamItems - 1) / (256 * kStreamItems);
   finalize_kernel<<<dim3((unsigned)gx, (unsigned)n_utts), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x_dev, reinterpret_cast<const long long*>(src_offsets_dev), reinterpret_cast<const long long*>(dst_offsets_dev),
       absmax_dev, out_f32_dev, reinterpret_cast<short*>(out_s16_dev));
