@@ -705,3 +705,81 @@ def test_config5_rank_shard_of_100h_corpus(cuda_device):
     assert abs(float(normed.double().mean())) < 1e-4 and abs(float(normed.double().std()) - 1.0) < 1e-4
     back = normed * st["std"] + st["mean"]
     assert float((back - feats.energy).abs().max()) <= 1e-4 * float(feats.energy.abs().max())
+
+
+@pytest.mark.parametrize("variant", ["x1", "x2"])
+def test_nan_and_inf_samples_stay_local(cuda_device, monkeypatch, variant):
+    """A NaN / Inf sample poisons the frames whose window covers it (like torch.stft does) plus, for n_fft 1024, the
+    partner frame of the same FFT job (frames 2j and 2j + 1 ride as real and imaginary part of one complex FFT, so a
+    non-finite value in one reaches the other in the real-FFT separation) -- and nothing else: no stale value leaks
+    between jobs, tiles, warps or the two halves of a packed register.  Documented deviation (INTEGRATION.md
+    section 5); PCM input cannot contain non-finite samples."""
+    from everyvoice_b200 import synth
+    from oracle import ev_oracle as O
+
+    monkeypatch.setenv("EVF_FEATURES_VARIANT", variant)
+    tf, hop = _transform("A", "mel")
+    otf, _ = _oracle_transform("A", "mel")
+    xs = [synth.speech_like(hop * n, 22050, seed=300 + i) for i, n in enumerate((70, 33, 95, 40))]
+    xs[0][hop * 20 + 7] = np.nan
+    xs[2][hop * 64 + 100] = np.inf       # second tile of the utterance, a job of the packed kernel's B half
+    xs[2][5] = -np.inf                    # inside the reflected left margin: mirrored into frame 0 twice
+    packed, off = synth.pack_ragged(xs)
+    feats = tf.features_ragged(torch.from_numpy(packed).to(cuda_device), off)
+    n_bad = 0
+    for b, x in enumerate(xs):
+        o_spec, o_energy, _ = O.features_one(torch.from_numpy(x), otf, hop)
+        spec, energy = feats.utterance(b).cpu(), feats.utterance_energy(b).cpu()
+        bad_o = ~torch.isfinite(o_spec).all(dim=0)
+        bad = ~torch.isfinite(spec).all(dim=0)
+        allowed = bad_o.clone()           # the reference's frames, widened to whole (2j, 2j + 1) pairs
+        T = len(bad_o)
+        for t in bad_o.nonzero().flatten().tolist():
+            allowed[min(t ^ 1, T - 1)] = True
+        assert bool((bad >= bad_o).all()) and bool((bad <= allowed).all()), (b, bad.nonzero().flatten().tolist())
+        assert torch.equal(~torch.isfinite(energy), bad)
+        good = ~bad
+        assert float((spec[:, good] - o_spec[:, good]).abs().max()) <= ATOL_LOG
+        assert float((energy[good] - o_energy[good]).abs().max()) <= ATOL_LOG
+        n_bad += int(bad.sum())
+    assert 11 <= n_bad <= 16 and int((~torch.isfinite(feats.spec).all(dim=1)).sum()) == n_bad
+    # n_fft 2048: one frame per FFT job, so the locality is exactly the reference's
+    tfB, hopB = _transform("B", "mel")
+    otfB, _ = _oracle_transform("B", "mel")
+    y = synth.speech_like(hopB * 40, 44100, seed=310)
+    y[hopB * 17 + 3] = np.nan
+    fB = tfB.features_ragged(torch.from_numpy(y).to(cuda_device), np.array([0, len(y)]))
+    o_spec, _, _ = O.features_one(torch.from_numpy(y), otfB, hopB)
+    assert torch.equal(~torch.isfinite(fB.utterance(0).cpu()).all(dim=0), ~torch.isfinite(o_spec).all(dim=0))
+
+
+def test_packed_buffer_beyond_2_31_samples(cuda_device):
+    """Maximum sizes: a packed int16 batch of 2.3e9 samples (4.6 GB; 64-bit sample and output offsets).  The last
+    utterances start beyond the 2^31-th sample and must equal the same utterances processed alone, bit for bit."""
+    from everyvoice_b200 import synth
+
+    tf, hop = _transform("A", "mel")
+    filler, n_fill = 10_000_128, 230                     # 230 x 7.6 minutes
+    tail = [synth.speech_like(hop * n, 22050, seed=400 + i) for i, n in enumerate((50, 123))]
+    tail_pcm = [np.clip(np.rint(t * 32767.0), -32768, 32767).astype(np.int16) for t in tail]
+    lens = np.array([filler] * n_fill + [len(t) for t in tail_pcm], dtype=np.int64)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    assert off[n_fill] > 2**31
+    x = torch.empty(int(off[-1]), dtype=torch.int16, device=cuda_device)
+    g = torch.Generator(device=cuda_device)
+    g.manual_seed(7)
+    chunk = 2**27
+    for s in range(0, int(off[n_fill]), chunk):          # seeded filler, generated in place
+        e = min(s + chunk, int(off[n_fill]))
+        x[s:e] = torch.randint(-20000, 20000, (e - s,), generator=g, device=cuda_device, dtype=torch.int16)
+    for i, t in enumerate(tail_pcm):
+        x[int(off[n_fill + i]) : int(off[n_fill + i + 1])] = torch.from_numpy(t).to(cuda_device)
+    feats = tf.features_ragged(x, off)
+    assert np.array_equal(np.diff(feats.frame_offsets), lens // hop)
+    assert feats.spec.shape[0] == int((lens // hop).sum()) and feats.spec.shape[0] * 80 > 2**29
+    for i, t in enumerate(tail_pcm):
+        single = tf.features_ragged(torch.from_numpy(t).to(cuda_device), np.array([0, len(t)]))
+        assert torch.equal(single.spec, feats.utterance(n_fill + i).transpose(0, 1))
+        assert torch.equal(single.energy, feats.utterance_energy(n_fill + i))
+    mid = feats.utterance(117)                           # a filler utterance in the middle: finite, above the floor
+    assert bool(torch.isfinite(mid).all()) and float(mid.min()) >= np.log(1e-5) - 1e-6
