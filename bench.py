@@ -299,9 +299,19 @@ def run_ours(args, w, wname):
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version banner to stdout; stdout carries exactly ONE JSON line (bench contract)
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner on the C-level stdout when the communicator is created; stdout carries
+        # exactly ONE JSON line (bench contract), so file descriptor 1 points at stderr while NCCL comes up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize(device)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     # CPU baseline first (rank 0, N == 1 only), before the GPU gets busy
     cpu_base = None
