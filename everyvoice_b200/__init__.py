@@ -7,6 +7,7 @@ All numerics run in ``libevfeat.so`` (hand-written CUDA, C ABI in ``include/evfe
 importing this package never falls back to a CPU implementation.
 """
 
+from .artefacts import ArtefactWriter, create_path, load_ragged  # noqa: F401
 from .audio import AudioFrontEnd, ProcessedAudio, Resampler, loudness_batch  # noqa: F401
 from .config import AudioConfig, AudioSpecTypeEnum, ConfigError  # noqa: F401
 from .heavy import (  # noqa: F401
@@ -24,4 +25,5 @@ __all__ = [
     "AudioConfig", "AudioSpecTypeEnum", "ConfigError", "RaggedBatch", "RaggedFeatures",
     "SpectralTransform", "dynamic_range_compression_torch", "get_spectral_transform",
     "Scaler", "Preprocessor", "CorpusPipeline", "AudioFrontEnd", "ProcessedAudio", "Resampler", "loudness_batch",
+    "ArtefactWriter", "create_path", "load_ragged",
 ]
