@@ -22,8 +22,10 @@ struct evf_resampler {
   int orig = 1, neu = 1;  // reduced by their gcd
   int width = 0;          // zero padding on the left, torchaudio's `width`
   int taps = 0;           // 2 * width + orig
-  float* d_kt = nullptr;  // [taps][neu] transposed kernel bank: consecutive output phases are consecutive words
-  std::vector<float> h_kt;  // host copy: the small-ratio kernels take the bank by value (constant bank operands)
+  float* d_kt = nullptr;  // [nk][neu] transposed, compacted kernel bank: consecutive output phases are consecutive words
+  int* d_k0 = nullptr;    // [neu] first tap of each phase's support
+  int nk = 0;             // taps kept per phase (the longest support; everything outside is exactly 0.0f)
+  std::vector<float> h_kt;  // host copy of the full [taps][neu] bank: the small-ratio kernels take it by value
 };
 
 namespace evf {
@@ -48,6 +50,10 @@ constexpr int kRsThreads = 256;
 
 // y[j] = sum_k K[j % new][k] * xpad[(j / new) * orig + k],  xpad = x shifted by `width` zeros
 // (torchaudio _apply_sinc_resample_kernel: pad (width, width + orig), conv1d with stride orig, transpose, crop).
+// torchaudio's bank has 2 * width + orig taps per phase, but the Hann window clamps the argument at
+// +-lowpass_filter_width, where it is zero: for 48 -> 22.05 kHz only ~27 of the 348 float32 taps of a phase are
+// non-zero, the rest are EXACTLY 0.0f.  The bank is stored compacted ([nk][new] from tap k0[phase] on), which skips
+// exact-zero products in the same ascending order -- bit-identical for finite input.
 // One block = 256 consecutive outputs of one utterance; their input span is staged in shared memory once
 // (coalesced), the kernel bank is read transposed so that the 32 lanes of a warp (consecutive phases) read
 // consecutive words.
@@ -55,9 +61,9 @@ template <typename SampleT>
 __global__ void __launch_bounds__(kRsThreads) resample_kernel(const SampleT* __restrict__ x,
                                                               const long long* __restrict__ in_off,
                                                               const long long* __restrict__ out_off,
-                                                              const float* __restrict__ kt, int orig, int neu,
-                                                              int width, int taps, int span_cap,
-                                                              float* __restrict__ y) {
+                                                              const float* __restrict__ kt,
+                                                              const int* __restrict__ k0, int nk, int orig, int neu,
+                                                              int width, int span_cap, float* __restrict__ y) {
   extern __shared__ float s_x[];
   const int b = blockIdx.y;
   const long long i0 = in_off[b], L = in_off[b + 1] - i0;
@@ -76,10 +82,10 @@ __global__ void __launch_bounds__(kRsThreads) resample_kernel(const SampleT* __r
   const int phase = (int)(j % neu);
   const int rel = (int)(j / neu - blk0) * orig;
   const float* kp = kt + phase;
-  const float* xp = s_x + rel;
+  const float* xp = s_x + rel + __ldg(k0 + phase);
   float acc = 0.f;
 #pragma unroll 4
-  for (int k = 0; k < taps; ++k) acc = fmaf(kp[(long long)k * neu], xp[k], acc);
+  for (int k = 0; k < nk; ++k) acc = fmaf(__ldg(kp + (long long)k * neu), xp[k], acc);
   y[o0 + j] = acc;
 }
 
@@ -402,10 +408,33 @@ int evf_resampler_create(int32_t orig_freq, int32_t new_freq, int32_t lowpass_fi
       const double sinc = (t == 0.0) ? 1.0 : std::sin(t) / t;
       kt[(size_t)k * r->neu + p] = (float)(sinc * window * scale);
     }
-  cudaError_t e = cudaMalloc(&r->d_kt, kt.size() * sizeof(float));
-  if (e == cudaSuccess) e = cudaMemcpy(r->d_kt, kt.data(), kt.size() * sizeof(float), cudaMemcpyHostToDevice);
+  // support of every phase: first / last tap that is not exactly 0.0f
+  std::vector<int> k0(r->neu, 0);
+  int nk = 1;
+  for (int p = 0; p < r->neu; ++p) {
+    int first = r->taps, last = -1;
+    for (int k = 0; k < r->taps; ++k)
+      if (kt[(size_t)k * r->neu + p] != 0.0f) {
+        if (first == r->taps) first = k;
+        last = k;
+      }
+    if (last < 0) first = last = 0;
+    k0[p] = first;
+    nk = (last - first + 1 > nk) ? last - first + 1 : nk;
+  }
+  for (int p = 0; p < r->neu; ++p)
+    if (k0[p] + nk > r->taps) k0[p] = r->taps - nk;  // keep every phase's window inside the bank (extra taps are zeros)
+  std::vector<float> kc((size_t)nk * r->neu);
+  for (int p = 0; p < r->neu; ++p)
+    for (int t = 0; t < nk; ++t) kc[(size_t)t * r->neu + p] = kt[(size_t)(k0[p] + t) * r->neu + p];
+  r->nk = nk;
+  cudaError_t e = cudaMalloc(&r->d_kt, kc.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(r->d_kt, kc.data(), kc.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&r->d_k0, k0.size() * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(r->d_k0, k0.data(), k0.size() * sizeof(int), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
     cudaFree(r->d_kt);
+    cudaFree(r->d_k0);
     delete r;
     return cuda_fail(e, "resampler kernel bank upload");
   }
@@ -418,6 +447,7 @@ int evf_resampler_destroy(evf_resampler* r) {
   if (!r) return EVF_OK;
   DeviceGuard guard(r->device);
   cudaFree(r->d_kt);
+  cudaFree(r->d_k0);
   delete r;
   return EVF_OK;
 }
@@ -481,13 +511,13 @@ int evf_audio_resample(const evf_resampler* r, const void* in_dev, int32_t in_fo
   if (s16) {
     auto k = resample_kernel<short>;
     if (smem > 48 * 1024) EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kRsThreads, smem, st>>>(static_cast<const short*>(in_dev), io, oo, r->d_kt, r->orig, r->neu, r->width,
-                                      r->taps, span, out_dev);
+    k<<<grid, kRsThreads, smem, st>>>(static_cast<const short*>(in_dev), io, oo, r->d_kt, r->d_k0, r->nk, r->orig,
+                                      r->neu, r->width, span, out_dev);
   } else {
     auto k = resample_kernel<float>;
     if (smem > 48 * 1024) EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kRsThreads, smem, st>>>(static_cast<const float*>(in_dev), io, oo, r->d_kt, r->orig, r->neu, r->width,
-                                      r->taps, span, out_dev);
+    k<<<grid, kRsThreads, smem, st>>>(static_cast<const float*>(in_dev), io, oo, r->d_kt, r->d_k0, r->nk, r->orig,
+                                      r->neu, r->width, span, out_dev);
   }
   EVF_CUDA(cudaGetLastError());
   return EVF_OK;
