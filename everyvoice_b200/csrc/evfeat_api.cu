@@ -27,6 +27,8 @@ struct evf_plan {
   float2* d_wtab = nullptr;
   unsigned* d_gtab = nullptr;
   unsigned* d_ltab = nullptr;
+  float2* d_melw = nullptr;  // per-bin {rising, falling} weights and interval index: the backward's transposed mel
+  int* d_jk = nullptr;
 };
 
 struct evf_batch {
@@ -34,6 +36,7 @@ struct evf_batch {
   int n_utts = 0;
   int n_tiles = 0;
   int64_t total_frames = 0;
+  int64_t max_len = 0;             // longest utterance in samples
   std::vector<int64_t> frame_off;  // host copy
   std::vector<int> tile_start;     // [n_utts + 1] first tile of every utterance
   long long* d_sample_off = nullptr;
@@ -209,6 +212,8 @@ void free_plan_tables(evf_plan* p) {
   cudaFree(p->d_wtab);
   cudaFree(p->d_gtab);
   cudaFree(p->d_ltab);
+  cudaFree(p->d_melw);
+  cudaFree(p->d_jk);
 }
 
 }  // namespace
@@ -347,6 +352,11 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   if (rc == EVF_OK) rc = upload(t.wtab, &p->d_wtab);
   if (rc == EVF_OK) rc = upload(t.gtab, &p->d_gtab);
   if (rc == EVF_OK) rc = upload(t.ltab, &p->d_ltab);
+  if (rc == EVF_OK && mel) {
+    rc = upload(t.melw, &p->d_melw);
+    std::vector<int> jk(t.jk.begin(), t.jk.begin() + t.k_used);
+    if (rc == EVF_OK) rc = upload(jk, &p->d_jk);
+  }
   if (rc != EVF_OK) {
     free_plan_tables(p);
     delete p;
@@ -433,6 +443,10 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
   bt->n_utts = n_utts;
   bt->n_tiles = (int)tiles.size();
   bt->total_frames = f_off[n_utts];
+  for (int b = 0; b < n_utts; ++b) {
+    const int64_t L = sample_offsets_host[b + 1] - sample_offsets_host[b];
+    bt->max_len = L > bt->max_len ? L : bt->max_len;
+  }
   bt->frame_off.assign(f_off.begin(), f_off.end());
   bt->tile_start.swap(tile_start);
   // one device block, one copy: [sample offsets | frame offsets | tile descriptors]
@@ -595,6 +609,62 @@ int evf_log_compress(const float* in_dev, float* out_dev, int64_t n, float c, fl
     return EVF_ERR_INVALID_ARGUMENT;
   }
   return launch_log_compress(in_dev, out_dev, n, c, clip_val, static_cast<cudaStream_t>(stream));
+}
+
+int evf_log_compress_backward(const float* in_dev, const float* grad_out_dev, float* grad_in_dev, int64_t n,
+                              float clip_val, void* stream) {
+  if (n < 0 || (n > 0 && (!in_dev || !grad_out_dev || !grad_in_dev))) {
+    set_error("evf_log_compress_backward: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_log_compress_backward(in_dev, grad_out_dev, grad_in_dev, n, clip_val,
+                                      static_cast<cudaStream_t>(stream));
+}
+
+int64_t evf_features_backward_scratch_floats(const evf_plan* plan, const evf_batch* batch) {
+  if (!plan || !batch) return -1;
+  return batch->total_frames * (int64_t)plan->cfg.n_fft;
+}
+
+int evf_features_backward(const evf_plan* plan, const evf_batch* batch, const float* samples_dev,
+                          const float* grad_spec_dev, float* scratch_dev, float* grad_samples_dev, void* stream) {
+  if (!plan || !batch || batch->device != plan->device) {
+    set_error("evf_features_backward: invalid plan / batch");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (plan->cfg.n_fft != 1024 || plan->cfg.sample_format != EVF_SAMPLES_F32 || plan->cfg.apply_log ||
+      plan->cfg.spec_type == EVF_SPEC_RAW) {
+    set_error("evf_features_backward: needs n_fft == 1024, float32 samples, a linear-domain plan (apply_log = 0; the "
+              "log has its own backward, evf_log_compress_backward) and a real spec_type");
+    return EVF_ERR_UNSUPPORTED;
+  }
+  if (batch->n_tiles == 0) return EVF_OK;
+  if (!samples_dev || !grad_spec_dev || !scratch_dev || !grad_samples_dev) {
+    set_error("evf_features_backward: null pointer");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  DeviceGuard guard(plan->device);
+  BwdParams p{};
+  p.samples = samples_dev;
+  p.tiles = batch->d_tiles;
+  p.n_tiles = batch->n_tiles;
+  p.grad_spec = grad_spec_dev;
+  p.frame_grad = scratch_dev;
+  p.grad_samples = grad_samples_dev;
+  p.window = plan->d_window;
+  p.tw4 = plan->d_tw4;
+  p.melw = plan->d_melw;
+  p.jk = plan->d_jk;
+  p.sample_off = batch->d_sample_off;
+  p.frame_off = batch->d_frame_off;
+  p.n_utts = batch->n_utts;
+  p.max_len = batch->max_len;
+  p.hop = plan->cfg.hop_length;
+  p.n_mels = plan->cfg.n_mels;
+  p.k_used = plan->k_used;
+  p.row_floats = plan->row_floats;
+  p.spec_type = plan->cfg.spec_type;
+  return features_backward_launch(p, static_cast<cudaStream_t>(stream));
 }
 
 int evf_segment_mean(const float* values_dev, const int64_t* value_offsets_dev,

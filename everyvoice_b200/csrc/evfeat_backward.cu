@@ -1,0 +1,259 @@
+// Backward of the spectral transform (sm_100a): d loss / d audio from d loss / d spectrogram, for the training-time
+// use of get_spectral_transform: HiFiGAN recomputes the mel spectrogram of the
+// GENERATED audio every step and back-propagates through it,
+//   everyvoice/model/vocoder/HiFiGAN_iSTFT_lightning/hfgl/model.py:581-590, 719-721, 812-814
+//   everyvoice/utils/heavy.py:47-113 (the transform), :39-40 (the log compression, evfeat_aux.cu)
+//
+// The forward is  x -> reflect pad -> frames -> window -> rFFT -> |X|^2 (-> sqrt(. + 1e-9)) -> mel basis.  Its
+// transpose, per FFT job (two frames ride as real and imaginary part of one complex FFT, like the forward kernel):
+//   1. recompute X_a, X_b of the two frames (same loads, window-fused butterflies, 32x32 four-step FFT, real-FFT
+//      separation as evfeat_features.cu);
+//   2. g_P[k] = rise[k] * g_mel[j(k)] + fall[k] * g_mel[j(k) - 1]   (each bin feeds two adjacent filters; the
+//      transposed mel projection needs no reduction at all),  G[k] = dL/dX[k] = 2 g_P[k] X[k];
+//   3. dL/d(windowed frame)[n] = Re sum_{k=0}^{N/2} G[k] e^{+2 pi i k n / N}: the one-sided spectra of both frames are
+//      Hermitian-extended and packed as C = C_a + i C_b, whose unnormalised inverse DFT is r_a + i r_b; the inverse
+//      runs through the SAME forward FFT code with real and imaginary parts swapped on the way in and out;
+//   4. times the window -> one row of 1024 frame gradients per frame (scratch);
+// then overlap_add_kernel gathers, for every sample, the <= n_fft / hop frame rows that cover it, plus the rows that
+// cover its mirror images in the reflect padding.  No atomics; the result is deterministic.
+#include "evfeat_fft.cuh"
+#include "evfeat_internal.h"
+
+namespace evf {
+
+namespace {
+
+#include "evfeat_device.cuh"
+
+constexpr int kBwdWarps = 16;
+constexpr int kGmStride = 128;  // n_mels <= 128 gradient values per frame in shared memory
+
+template <int SPEC>
+__global__ void __launch_bounds__(kBwdWarps * 32, 1) features_backward_kernel(const BwdParams p) {
+  constexpr int NFFT = 1024;
+  constexpr bool kMel = (SPEC == EVF_SPEC_MEL || SPEC == EVF_SPEC_MEL_LIBROSA);
+  extern __shared__ __align__(16) float smem[];
+  float* s_win = smem;                                              // [16][32] pairs, pre-scaled by 1/2
+  float4* s_tw4 = reinterpret_cast<float4*>(smem + NFFT);           // [16][32]
+  float* s_warp = smem + NFFT + 2 * kFftSize;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* scr = s_warp + warp * (32 * kScrStride + 2 * kGmStride);
+  float* gm = scr + 32 * kScrStride;                                 // [2][kGmStride] mel gradients of frames a, b
+
+  for (int i = tid; i < NFFT; i += kBwdWarps * 32) s_win[i] = p.window[i];
+  for (int i = tid; i < kFftSize / 2; i += kBwdWarps * 32) s_tw4[i] = p.tw4[i];
+  for (int i = tid; i < kBwdWarps * (32 * kScrStride + 2 * kGmStride); i += kBwdWarps * 32) s_warp[i] = 0.f;
+  __syncthreads();
+
+  const TileDesc ti = p.tiles[blockIdx.x];
+  const int fa = 2 * warp;
+  if (fa >= ti.nvalid) return;
+  const bool b_valid = fa + 1 < ti.nvalid;
+  const int hop = p.hop;
+  const float* xs = p.samples + ti.s_off;
+  const long long frame_a = ti.out_frame0 + fa;
+
+  // ---- forward recomputation: samples -> window-fused first stage -> FFT ------------------------------
+  float re[32], im[32];
+  {
+    const int ua = ti.start + fa * hop + lane, ub = ua + hop;
+    const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const float2 w = wv[32 * r];
+      const int i = bitrev5(r);
+      win_head(re[i], re[i + 1], __ldg(xs + reflect_index(ua + 32 * r, ti.L)), w.x,
+               __ldg(xs + reflect_index(ua + 32 * (r + 16), ti.L)), w.y);
+      win_head(im[i], im[i + 1], __ldg(xs + reflect_index(ub + 32 * r, ti.L)), w.x,
+               __ldg(xs + reflect_index(ub + 32 * (r + 16), ti.L)), w.y);
+    }
+  }
+  warp_fft1024_tail(re, im, s_tw4, scr, lane);
+
+  // ---- mel gradients of the two frames -> shared memory --------------------------------------------------
+  if constexpr (kMel) {
+    const float* ga = p.grad_spec + frame_a * p.row_floats;
+    for (int m = lane; m < p.n_mels; m += 32) {
+      gm[m] = __ldg(ga + m);
+      gm[kGmStride + m] = b_valid ? __ldg(ga + p.row_floats + m) : 0.f;
+    }
+    __syncwarp();
+  }
+
+  // ---- G/2 = g_P X per bin, Hermitian extension, packing C = C_a + i C_b ---------------------------------
+  // element e = lane + 32 q of C; ck: this lane's bins k = lane + 32 j (j <= 15, and k = 512 for lane 0);
+  // cm: the mirror elements 1024 - k, fetched by the lane that owns them
+  float ck_r[17], ck_i[17], cm_r[17], cm_i[17];
+  const int src_lane = (32 - lane) & 31;
+#pragma unroll
+  for (int j = 0; j <= 16; ++j) {
+    const int k = lane + 32 * j;
+    float zr, zi, pr, pi;
+    if (j < 16) {
+      zr = re[j];
+      zi = im[j];
+      const float sr = (lane == 0) ? re[(32 - j) & 31] : re[31 - j];
+      const float si = (lane == 0) ? im[(32 - j) & 31] : im[31 - j];
+      pr = __shfl_sync(0xffffffffu, sr, src_lane);
+      pi = __shfl_sync(0xffffffffu, si, src_lane);
+    } else {
+      zr = pr = re[16];
+      zi = pi = im[16];
+    }
+    // window was pre-scaled by 1/2: X_a = Z[k] + conj(Z[N-k]), X_b = (Z[k] - conj(Z[N-k])) / i
+    const float ar = zr + pr, ai = zi - pi;
+    const float br = zi + pi, bi = pr - zr;
+    float gpa = 0.f, gpb = 0.f;
+    const bool own = (j < 16) || (lane == 0);
+    if (own) {
+      if constexpr (kMel) {
+        if (k < p.k_used) {
+          const float2 w = __ldg(p.melw + k);   // {rising weight -> filter j(k), falling weight -> filter j(k) - 1}
+          const int jj = __ldg(p.jk + k);
+          const int m_r = min(jj, p.n_mels - 1), m_f = max(jj - 1, 0);
+          const float wr = (jj < p.n_mels) ? w.x : 0.f, wf = (jj >= 1) ? w.y : 0.f;
+          gpa = fmaf(wr, gm[m_r], wf * gm[m_f]);
+          gpb = fmaf(wr, gm[kGmStride + m_r], wf * gm[kGmStride + m_f]);
+        }
+        if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
+          // mel = basis @ sqrt(P + 1e-9):  dM/dP = 1 / (2 sqrt(P + 1e-9))
+          gpa *= 0.5f * rsqrtf(fmaf(ar, ar, ai * ai) + 1e-9f);
+          gpb *= 0.5f * rsqrtf(fmaf(br, br, bi * bi) + 1e-9f);
+        }
+      } else {
+        const float* ga = p.grad_spec + frame_a * p.row_floats;
+        gpa = __ldg(ga + k);
+        gpb = b_valid ? __ldg(ga + p.row_floats + k) : 0.f;
+      }
+    }
+    const float ur = gpa * ar, ui = gpa * ai, vr = gpb * br, vi = gpb * bi;  // u = G_a / 2, v = G_b / 2
+    if (j == 16 || (j == 0 && lane == 0)) {
+      // k = 0 and k = N/2: the spectrum is real there; C = Re G_a + i Re G_b, no mirror
+      ck_r[j] = 2.f * ur;
+      ck_i[j] = 2.f * vr;
+      cm_r[j] = ck_r[j];  // (only read for j == 16 by lane 0: element 512 is its own mirror)
+      cm_i[j] = ck_i[j];
+    } else {
+      ck_r[j] = ur - vi;  // u + i v
+      ck_i[j] = ui + vr;
+      cm_r[j] = ur + vi;  // conj(u) + i conj(v)
+      cm_i[j] = vr - ui;
+    }
+  }
+
+  // ---- inverse DFT through the forward FFT: swap real and imaginary parts on the way in and out -------------
+  // position bitrev5(q) of the DIT arrays holds element q
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    re[bitrev5(q)] = ck_i[q];
+    im[bitrev5(q)] = ck_r[q];
+  }
+#pragma unroll
+  for (int q = 16; q < 32; ++q) {
+    // element lane + 32 q > 512 (or == 512 for lane 0, q == 16): the mirror of bin 1024 - e, owned by src_lane
+    const float sr = (lane == 0) ? cm_r[(32 - q) & 31] : cm_r[31 - q];
+    const float si = (lane == 0) ? cm_i[(32 - q) & 31] : cm_i[31 - q];
+    re[bitrev5(q)] = __shfl_sync(0xffffffffu, si, src_lane);
+    im[bitrev5(q)] = __shfl_sync(0xffffffffu, sr, src_lane);
+  }
+  dft32_dit_head(re, im);
+  warp_fft1024_tail(re, im, s_tw4, scr, lane);
+  // FFT(swap(C)) = swap(r_a + i r_b): r_a = im, r_b = re; element n = lane + 32 k2
+
+  // ---- times the (true) window -> frame-gradient rows --------------------------------------------------------
+  float* fg_a = p.frame_grad + frame_a * NFFT;
+  const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
+#pragma unroll
+  for (int k2 = 0; k2 < 32; ++k2) {
+    const float2 wp = wv[32 * (k2 & 15)];
+    const float w = 2.f * ((k2 < 16) ? wp.x : wp.y);
+    fg_a[lane + 32 * k2] = w * im[k2];
+    if (b_valid) fg_a[NFFT + lane + 32 * k2] = w * re[k2];
+  }
+}
+
+// d loss / d x[s] = sum over the padded positions that read x[s] (itself and its mirror images in the reflect
+// padding, torch.stft(center=True, pad_mode="reflect")) of the frame-gradient rows covering that position.
+__global__ void __launch_bounds__(256) overlap_add_kernel(const float* __restrict__ frame_grad,
+                                                          const long long* __restrict__ sample_off,
+                                                          const long long* __restrict__ frame_off, int n_fft, int hop,
+                                                          float* __restrict__ grad_x) {
+  const int b = blockIdx.y;
+  const long long s0 = sample_off[b], L = sample_off[b + 1] - s0;
+  const long long f0 = frame_off[b], T = frame_off[b + 1] - f0;
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= L) return;
+  const long long H = n_fft / 2;
+  long long pos[3];
+  int n_pos = 0;
+  pos[n_pos++] = s + H;
+  if (s >= 1 && s <= H) pos[n_pos++] = H - s;
+  if (s <= L - 2 && s >= L - 1 - H) pos[n_pos++] = H + 2 * (L - 1) - s;
+  float g = 0.f;
+  for (int i = 0; i < n_pos; ++i) {
+    const long long pp = pos[i];
+    long long t_hi = pp / hop;
+    if (t_hi > T - 1) t_hi = T - 1;
+    long long t_lo = (pp - n_fft + hop) / hop;  // ceil((pp - n_fft + 1) / hop) for pp - n_fft + 1 > 0
+    if (pp - n_fft + 1 <= 0) t_lo = 0;
+    for (long long t = t_lo; t <= t_hi; ++t) g += __ldg(frame_grad + (f0 + t) * n_fft + (pp - t * hop));
+  }
+  grad_x[s0 + s] = g;
+}
+
+// d/dx log(clamp(x, min = clip) * C) = 1 / x where the clamp passes (x >= clip), else 0   (utils/heavy.py:39-40)
+__global__ void __launch_bounds__(256) log_compress_backward_kernel(const float* __restrict__ x,
+                                                                    const float* __restrict__ g, float* __restrict__ out,
+                                                                    long long n, float clip) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    out[i] = (v >= clip) ? g[i] / v : ((v != v) ? v : 0.f);
+  }
+}
+
+template <int SPEC>
+int launch_bwd(const BwdParams& p, int smem, cudaStream_t st) {
+  auto k = features_backward_kernel<SPEC>;
+  EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k<<<p.n_tiles, kBwdWarps * 32, smem, st>>>(p);
+  EVF_CUDA(cudaGetLastError());
+  return EVF_OK;
+}
+
+}  // namespace
+
+int features_backward_launch(const BwdParams& p, cudaStream_t st) {
+  if (p.n_tiles == 0 || p.n_utts == 0) return EVF_OK;
+  if (p.n_mels > kGmStride) {
+    set_error("evf_features_backward: more than 128 mel filters are not supported");
+    return EVF_ERR_UNSUPPORTED;
+  }
+  const int smem = (1024 + 2 * kFftSize + kBwdWarps * (32 * kScrStride + 2 * kGmStride)) * (int)sizeof(float);
+  int rc;
+  switch (p.spec_type) {
+    case EVF_SPEC_MEL: rc = launch_bwd<EVF_SPEC_MEL>(p, smem, st); break;
+    case EVF_SPEC_MEL_LIBROSA: rc = launch_bwd<EVF_SPEC_MEL_LIBROSA>(p, smem, st); break;
+    case EVF_SPEC_LINEAR: rc = launch_bwd<EVF_SPEC_LINEAR>(p, smem, st); break;
+    default:
+      set_error("evf_features_backward: spec_type has no backward (raw is complex)");
+      return EVF_ERR_UNSUPPORTED;
+  }
+  if (rc != EVF_OK) return rc;
+  if (p.max_len > 0) {
+    const dim3 grid((unsigned)((p.max_len + 255) / 256), (unsigned)p.n_utts);
+    overlap_add_kernel<<<grid, 256, 0, st>>>(p.frame_grad, p.sample_off, p.frame_off, 1024, p.hop, p.grad_samples);
+    EVF_CUDA(cudaGetLastError());
+  }
+  return EVF_OK;
+}
+
+int launch_log_compress_backward(const float* x, const float* g, float* out, int64_t n, float clip, cudaStream_t s) {
+  if (n == 0) return EVF_OK;
+  long long blocks = (n + 256 * 4 - 1) / (256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  log_compress_backward_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, g, out, n, clip);
+  EVF_CUDA(cudaGetLastError());
+  return EVF_OK;
+}
+
+}  // namespace evf

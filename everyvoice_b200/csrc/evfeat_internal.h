@@ -99,6 +99,27 @@ int features_launch(int mode, int spec_type, int sample_format, const FeatParams
 int features_x2_dispatch(int spec_type, int sample_format, const FeatParams& p, int grid, int smem_bytes,
                          cudaStream_t stream, bool configure_only);
 
+// evfeat_backward.cu
+struct BwdParams {
+  const float* samples;          // packed float32 audio
+  const TileDesc* tiles;
+  int n_tiles;
+  const float* grad_spec;        // [total_frames][row_floats] d loss / d (linear-domain) spectrogram, time-major
+  float* frame_grad;             // scratch [total_frames][n_fft]
+  float* grad_samples;           // out, packed like samples
+  const float* window;           // plan tables (MODE_PACK2 layouts)
+  const float4* tw4;
+  const float2* melw;            // [k_used] {rising weight -> filter j(k), falling weight -> filter j(k) - 1}
+  const int* jk;                 // [k_used] interval index j(k)
+  const long long* sample_off;   // [n_utts + 1]
+  const long long* frame_off;    // [n_utts + 1]
+  int n_utts;
+  long long max_len;             // longest utterance (grid sizing)
+  int hop, n_mels, k_used, row_floats, spec_type;
+};
+int features_backward_launch(const BwdParams& p, cudaStream_t stream);
+int launch_log_compress_backward(const float* x, const float* g, float* out, int64_t n, float clip, cudaStream_t s);
+
 // evfeat_aux.cu
 int launch_energy_from_spec(const float* spec, int64_t n_frames, int row, float* out, cudaStream_t s);
 int launch_segment_mean(const float* values, const int64_t* value_off, const int64_t* durations,

@@ -152,6 +152,63 @@ class RaggedFeatures:
         return self.energy[self.frame_offsets[b] : self.frame_offsets[b + 1]]
 
 
+class _SpectralFn(torch.autograd.Function):
+    """Differentiable linear-domain transform for training through the spectrogram (HiFiGAN's mel loss on generated
+    audio, hfgl/model.py:581-590, 719-721).  Forward: the fused feature kernel; backward: ``evf_features_backward``
+    (transposed mel projection, inverse FFT through the forward FFT code, windowed overlap-add with the reflect
+    padding folded back)."""
+
+    @staticmethod
+    def forward(ctx, x2d: torch.Tensor, tf: "SpectralTransform", keep_last: bool):
+        B, L = x2d.shape
+        offsets = np.arange(B + 1, dtype=np.int64) * L
+        batch = tf.make_batch(offsets, x2d.device, apply_log=False, keep_last=keep_last)
+        spec, _ = tf.run(batch, x2d.reshape(-1), want_energy=False)
+        T = tf.num_frames(L, keep_last)
+        ctx.save_for_backward(x2d)
+        ctx.batch, ctx.dims = batch, (B, L, T)
+        return spec.view(B, T, tf.n_rows).transpose(1, 2)
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        (x2d,) = ctx.saved_tensors
+        batch, (B, L, T) = ctx.batch, ctx.dims
+        plan = batch.plan
+        g = grad_out.transpose(1, 2).to(torch.float32).contiguous().view(B * T, -1)
+        lib = plan._lib
+        n = int(lib.evf_features_backward_scratch_floats(plan.handle, batch.handle))
+        scratch = torch.empty(max(n, 1), dtype=torch.float32, device=x2d.device)
+        gx = torch.empty_like(x2d)
+        with torch.cuda.device(x2d.device):
+            _lib.check(lib.evf_features_backward(plan.handle, batch.handle, _ptr(x2d), _ptr(g), _ptr(scratch), _ptr(gx),
+                                                 _stream_ptr(x2d.device)))
+        return gx, None, None
+
+
+class _LogCompressFn(torch.autograd.Function):
+    """``log(clamp(x, min=clip) * C)`` with its gradient ``1 / x`` where the clamp passes (utils/heavy.py:39-40)."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, C: float, clip_val: float):
+        out = torch.empty_like(x)
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.evf_log_compress(_ptr(x), _ptr(out), x.numel(), float(C), float(clip_val), _stream_ptr(x.device)))
+        ctx.save_for_backward(x)
+        ctx.clip = float(clip_val)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        (x,) = ctx.saved_tensors
+        g = grad_out.to(torch.float32).contiguous()
+        gi = torch.empty_like(x)
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            _lib.check(lib.evf_log_compress_backward(_ptr(x), _ptr(g), _ptr(gi), x.numel(), ctx.clip, _stream_ptr(x.device)))
+        return gi, None, None
+
+
 class SpectralTransform:
     """The object ``get_spectral_transform`` returns.  ``t(x)`` mirrors the torchaudio
     transform the reference builds (linear-domain output, all ``1 + L//hop`` frames);
@@ -265,6 +322,15 @@ class SpectralTransform:
         L = x.shape[-1]
         lead = tuple(x.shape[:-1])
         B = int(np.prod(lead)) if lead else 1
+        if x.requires_grad and torch.is_grad_enabled():
+            # training through the transform: custom autograd functions over the same kernels
+            if self.is_complex:
+                raise NotImplementedError("the complex ('raw') transform has no backward")
+            out = _SpectralFn.apply(xd.view(B, L), self, bool(keep_last))     # [B, F, T], linear domain
+            if normalize:
+                out = _LogCompressFn.apply(out.contiguous(), 1.0, 1e-5)
+            out = out.reshape(*lead, self.n_rows, out.shape[-1])
+            return out if src_device == device else out.to(src_device)
         offsets = np.arange(B + 1, dtype=np.int64) * L
         batch = self.make_batch(offsets, device, apply_log=normalize and not self.is_complex, keep_last=keep_last)
         spec, _ = self.run(batch, xd.view(-1), want_energy=False)
@@ -306,6 +372,9 @@ def dynamic_range_compression_torch(x: torch.Tensor, C=1, clip_val=1e-5) -> torc
     as a stand-alone operator (the fused kernels do this in their epilogue)."""
     device = x.device if x.is_cuda else _require_cuda(None)
     xd = x.to(device=device, dtype=torch.float32).contiguous()
+    if x.requires_grad and torch.is_grad_enabled():
+        out = _LogCompressFn.apply(xd, float(C), float(clip_val))
+        return out if x.is_cuda else out.to(x.device)
     out = torch.empty_like(xd)
     lib = _lib.load()
     with torch.cuda.device(device):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define EVF_ABI_VERSION 4
+#define EVF_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define EVF_API __attribute__((visibility("default")))
@@ -183,6 +183,21 @@ EVF_API int evf_stats_merge(const double* parts_dev, int32_t n_parts, int32_t st
                     void* stream);
 EVF_API int evf_normalize_by_gathered_stats(float* values_dev, int64_t n, const double* parts_dev, int32_t n_parts,
                                     int32_t stride_doubles, void* stream);
+
+/* ---- backward of the transform: HiFiGAN trains through the mel spectrogram of the
+ * generated audio, everyvoice/model/vocoder/HiFiGAN_iSTFT_lightning/hfgl/model.py:581-590, 719-721 -------------
+ * grad_spec_dev: d loss / d spectrogram in the layout evf_features_run writes ([total_frames][row_floats],
+ * linear domain: the plan must have apply_log == 0); grad_samples_dev: d loss / d samples, packed like the samples;
+ * scratch_dev: evf_features_backward_scratch_floats(plan, batch) float32.  n_fft == 1024, float32 samples, spec types
+ * mel / mel-librosa / linear.  Deterministic (no atomics). */
+EVF_API int64_t evf_features_backward_scratch_floats(const evf_plan* plan, const evf_batch* batch);
+EVF_API int evf_features_backward(const evf_plan* plan, const evf_batch* batch, const float* samples_dev,
+                                  const float* grad_spec_dev, float* scratch_dev, float* grad_samples_dev,
+                                  void* stream);
+/* backward of dynamic_range_compression_torch (utils/heavy.py:39-40): grad_in = grad_out / x where x >= clip_val,
+ * else 0 (the clamp blocks the gradient) */
+EVF_API int evf_log_compress_backward(const float* in_dev, const float* grad_out_dev, float* grad_in_dev, int64_t n,
+                                      float clip_val, void* stream);
 
 /* ---- audio front-end: the numerics of Preprocessor.process_audio ----------------
  * everyvoice/preprocessor/preprocessor.py:131-218.  Ragged batches: utterance b owns [offsets[b], offsets[b+1])
