@@ -632,10 +632,9 @@ int evf_features_backward(const evf_plan* plan, const evf_batch* batch, const fl
     set_error("evf_features_backward: invalid plan / batch");
     return EVF_ERR_INVALID_ARGUMENT;
   }
-  if (plan->cfg.n_fft != 1024 || plan->cfg.sample_format != EVF_SAMPLES_F32 || plan->cfg.apply_log ||
-      plan->cfg.spec_type == EVF_SPEC_RAW) {
-    set_error("evf_features_backward: needs n_fft == 1024, float32 samples, a linear-domain plan (apply_log = 0; the "
-              "log has its own backward, evf_log_compress_backward) and a real spec_type");
+  if (plan->cfg.sample_format != EVF_SAMPLES_F32 || plan->cfg.apply_log || plan->cfg.spec_type == EVF_SPEC_RAW) {
+    set_error("evf_features_backward: needs float32 samples, a linear-domain plan (apply_log = 0; the log has its own "
+              "backward, evf_log_compress_backward) and a real spec_type");
     return EVF_ERR_UNSUPPORTED;
   }
   if (batch->n_tiles == 0) return EVF_OK;
@@ -653,6 +652,8 @@ int evf_features_backward(const evf_plan* plan, const evf_batch* batch, const fl
   p.grad_samples = grad_samples_dev;
   p.window = plan->d_window;
   p.tw4 = plan->d_tw4;
+  p.wpost = plan->d_wpost;
+  p.n_fft = plan->cfg.n_fft;
   p.melw = plan->d_melw;
   p.jk = plan->d_jk;
   p.sample_off = batch->d_sample_off;

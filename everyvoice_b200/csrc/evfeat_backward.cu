@@ -28,34 +28,44 @@ namespace {
 constexpr int kBwdWarps = 16;
 constexpr int kGmStride = 128;  // n_mels <= 128 gradient values per frame in shared memory
 
-template <int SPEC>
+// MODE_PACK2 (n_fft 1024): two frames per job as real / imaginary part.  MODE_HALF (n_fft 2048): one frame per job as
+// 1024 complex points z[m] = v[2m] + i v[2m + 1]; the transpose of its real-FFT split is the classic half-size
+// inverse: with Y = G / 2 (Y_0 = Re G_0, Y_1024 = Re G_1024),  A[k] = Y[k] + conj(Y[M - k]),
+// B[k] = (Y[k] - conj(Y[M - k])) e^{+2 pi i k / 2048},  Zin[k] = A[k] + i B[k] (k < M = 1024; Zin[M - k] =
+// conj(A[k]) + i conj(B[k])), and the unnormalised inverse DFT of Zin is  g_v[2m] + i g_v[2m + 1].
+template <int MODE, int SPEC>
 __global__ void __launch_bounds__(kBwdWarps * 32, 1) features_backward_kernel(const BwdParams p) {
-  constexpr int NFFT = 1024;
+  constexpr bool kHalf = (MODE == MODE_HALF);
+  constexpr int NFFT = kHalf ? 2048 : 1024;
+  constexpr int FPJ = kHalf ? 1 : 2;
   constexpr bool kMel = (SPEC == EVF_SPEC_MEL || SPEC == EVF_SPEC_MEL_LIBROSA);
   extern __shared__ __align__(16) float smem[];
-  float* s_win = smem;                                              // [16][32] pairs, pre-scaled by 1/2
+  float* s_win = smem;                                              // forward layout of the mode, pre-scaled by 1/2
   float4* s_tw4 = reinterpret_cast<float4*>(smem + NFFT);           // [16][32]
-  float* s_warp = smem + NFFT + 2 * kFftSize;
+  float2* s_wpost = reinterpret_cast<float2*>(smem + NFFT + 2 * kFftSize);   // MODE_HALF: (cos, -sin)(2 pi k / 2048)
+  float* s_warp = smem + NFFT + 2 * kFftSize + (kHalf ? 1028 : 0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* scr = s_warp + warp * (32 * kScrStride + 2 * kGmStride);
   float* gm = scr + 32 * kScrStride;                                 // [2][kGmStride] mel gradients of frames a, b
 
   for (int i = tid; i < NFFT; i += kBwdWarps * 32) s_win[i] = p.window[i];
   for (int i = tid; i < kFftSize / 2; i += kBwdWarps * 32) s_tw4[i] = p.tw4[i];
+  if constexpr (kHalf)
+    for (int i = tid; i <= 512; i += kBwdWarps * 32) s_wpost[i] = p.wpost[i];
   for (int i = tid; i < kBwdWarps * (32 * kScrStride + 2 * kGmStride); i += kBwdWarps * 32) s_warp[i] = 0.f;
   __syncthreads();
 
   const TileDesc ti = p.tiles[blockIdx.x];
-  const int fa = 2 * warp;
+  const int fa = FPJ * warp;
   if (fa >= ti.nvalid) return;
-  const bool b_valid = fa + 1 < ti.nvalid;
+  const bool b_valid = !kHalf && (fa + 1 < ti.nvalid);
   const int hop = p.hop;
   const float* xs = p.samples + ti.s_off;
   const long long frame_a = ti.out_frame0 + fa;
 
   // ---- forward recomputation: samples -> window-fused first stage -> FFT ------------------------------
   float re[32], im[32];
-  {
+  if constexpr (!kHalf) {
     const int ua = ti.start + fa * hop + lane, ub = ua + hop;
     const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
 #pragma unroll
@@ -67,22 +77,52 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) features_backward_kernel(co
       win_head(im[i], im[i + 1], __ldg(xs + reflect_index(ub + 32 * r, ti.L)), w.x,
                __ldg(xs + reflect_index(ub + 32 * (r + 16), ti.L)), w.y);
     }
+  } else {
+    const int u0 = ti.start + fa * hop + 2 * lane;
+    const float2* w2 = reinterpret_cast<const float2*>(s_win) + lane;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const float2 wa = w2[32 * r], wb = w2[32 * (r + 16)];
+      const int ia = u0 + 64 * r, ib = u0 + 64 * (r + 16);
+      const int i = bitrev5(r);
+      win_head(re[i], re[i + 1], __ldg(xs + reflect_index(ia, ti.L)), wa.x, __ldg(xs + reflect_index(ib, ti.L)), wb.x);
+      win_head(im[i], im[i + 1], __ldg(xs + reflect_index(ia + 1, ti.L)), wa.y,
+               __ldg(xs + reflect_index(ib + 1, ti.L)), wb.y);
+    }
   }
   warp_fft1024_tail(re, im, s_tw4, scr, lane);
 
-  // ---- mel gradients of the two frames -> shared memory --------------------------------------------------
+  // ---- mel gradients of the frame(s) -> shared memory ----------------------------------------------------
+  const float* ga = p.grad_spec + frame_a * p.row_floats;
   if constexpr (kMel) {
-    const float* ga = p.grad_spec + frame_a * p.row_floats;
     for (int m = lane; m < p.n_mels; m += 32) {
       gm[m] = __ldg(ga + m);
       gm[kGmStride + m] = b_valid ? __ldg(ga + p.row_floats + m) : 0.f;
     }
     __syncwarp();
   }
+  // transposed mel projection for bin k of frame f (0 = a, 1 = b): a bin feeds two adjacent filters
+  auto g_power = [&](int k, int f) -> float {
+    if constexpr (kMel) {
+      if (k >= p.k_used) return 0.f;
+      const float2 w = __ldg(p.melw + k);   // {rising weight -> filter j(k), falling weight -> filter j(k) - 1}
+      const int jj = __ldg(p.jk + k);
+      const int m_r = min(jj, p.n_mels - 1), m_f = max(jj - 1, 0);
+      const float wr = (jj < p.n_mels) ? w.x : 0.f, wf = (jj >= 1) ? w.y : 0.f;
+      return fmaf(wr, gm[f * kGmStride + m_r], wf * gm[f * kGmStride + m_f]);
+    } else {
+      return (f == 0 || b_valid) ? __ldg(ga + f * p.row_floats + k) : 0.f;
+    }
+  };
+  // mel-librosa: mel = basis @ sqrt(P + 1e-9), dM/dP = 1 / (2 sqrt(P + 1e-9))
+  auto librosa = [&](float g, float xr, float xi) -> float {
+    if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) return g * 0.5f * rsqrtf(fmaf(xr, xr, xi * xi) + 1e-9f);
+    return g;
+  };
 
-  // ---- G/2 = g_P X per bin, Hermitian extension, packing C = C_a + i C_b ---------------------------------
-  // element e = lane + 32 q of C; ck: this lane's bins k = lane + 32 j (j <= 15, and k = 512 for lane 0);
-  // cm: the mirror elements 1024 - k, fetched by the lane that owns them
+  // ---- spectrum gradients per bin, extension to the full complex input of the inverse ------------------------
+  // element e = lane + 32 q; ck: this lane's elements k = lane + 32 j (j <= 15, and k = 512 for lane 0);
+  // cm: the mirror elements 1024 - k, fetched below by the lane that owns them
   float ck_r[17], ck_i[17], cm_r[17], cm_i[17];
   const int src_lane = (32 - lane) & 31;
 #pragma unroll
@@ -100,44 +140,62 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) features_backward_kernel(co
       zr = pr = re[16];
       zi = pi = im[16];
     }
-    // window was pre-scaled by 1/2: X_a = Z[k] + conj(Z[N-k]), X_b = (Z[k] - conj(Z[N-k])) / i
-    const float ar = zr + pr, ai = zi - pi;
-    const float br = zi + pi, bi = pr - zr;
-    float gpa = 0.f, gpb = 0.f;
     const bool own = (j < 16) || (lane == 0);
-    if (own) {
-      if constexpr (kMel) {
-        if (k < p.k_used) {
-          const float2 w = __ldg(p.melw + k);   // {rising weight -> filter j(k), falling weight -> filter j(k) - 1}
-          const int jj = __ldg(p.jk + k);
-          const int m_r = min(jj, p.n_mels - 1), m_f = max(jj - 1, 0);
-          const float wr = (jj < p.n_mels) ? w.x : 0.f, wf = (jj >= 1) ? w.y : 0.f;
-          gpa = fmaf(wr, gm[m_r], wf * gm[m_f]);
-          gpb = fmaf(wr, gm[kGmStride + m_r], wf * gm[kGmStride + m_f]);
-        }
-        if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
-          // mel = basis @ sqrt(P + 1e-9):  dM/dP = 1 / (2 sqrt(P + 1e-9))
-          gpa *= 0.5f * rsqrtf(fmaf(ar, ar, ai * ai) + 1e-9f);
-          gpb *= 0.5f * rsqrtf(fmaf(br, br, bi * bi) + 1e-9f);
-        }
+    if constexpr (!kHalf) {
+      // window was pre-scaled by 1/2: X_a = Z[k] + conj(Z[N-k]), X_b = (Z[k] - conj(Z[N-k])) / i
+      const float ar = zr + pr, ai = zi - pi;
+      const float br = zi + pi, bi = pr - zr;
+      const float gpa = own ? librosa(g_power(k, 0), ar, ai) : 0.f;
+      const float gpb = own ? librosa(g_power(k, 1), br, bi) : 0.f;
+      const float ur = gpa * ar, ui = gpa * ai, vr = gpb * br, vi = gpb * bi;  // u = G_a / 2, v = G_b / 2
+      if (j == 16 || (j == 0 && lane == 0)) {
+        // k = 0 and k = N/2: the spectrum is real there; C = Re G_a + i Re G_b, no mirror
+        ck_r[j] = 2.f * ur;
+        ck_i[j] = 2.f * vr;
+        cm_r[j] = ck_r[j];  // (only read for j == 16 by lane 0: element 512 is its own mirror)
+        cm_i[j] = ck_i[j];
       } else {
-        const float* ga = p.grad_spec + frame_a * p.row_floats;
-        gpa = __ldg(ga + k);
-        gpb = b_valid ? __ldg(ga + p.row_floats + k) : 0.f;
+        ck_r[j] = ur - vi;  // u + i v
+        ck_i[j] = ui + vr;
+        cm_r[j] = ur + vi;  // conj(u) + i conj(v)
+        cm_i[j] = vr - ui;
       }
-    }
-    const float ur = gpa * ar, ui = gpa * ai, vr = gpb * br, vi = gpb * bi;  // u = G_a / 2, v = G_b / 2
-    if (j == 16 || (j == 0 && lane == 0)) {
-      // k = 0 and k = N/2: the spectrum is real there; C = Re G_a + i Re G_b, no mirror
-      ck_r[j] = 2.f * ur;
-      ck_i[j] = 2.f * vr;
-      cm_r[j] = ck_r[j];  // (only read for j == 16 by lane 0: element 512 is its own mirror)
-      cm_i[j] = ck_i[j];
     } else {
-      ck_r[j] = ur - vi;  // u + i v
-      ck_i[j] = ui + vr;
-      cm_r[j] = ur + vi;  // conj(u) + i conj(v)
-      cm_i[j] = vr - ui;
+      // forward split: X[k] = E - T, X[M - k] = conj(E + T), E = Z[k] + conj(Z[M - k]),
+      // T = i w_k (Z[k] - conj(Z[M - k])), w_k = e^{-2 pi i k / 2048}
+      const float er = zr + pr, ei = zi - pi;
+      const float orr = zr - pr, oi = zi + pi;
+      const float2 w = s_wpost[own ? k : 0];
+      const float tr = -fmaf(w.x, oi, w.y * orr);
+      const float tq = fmaf(w.x, orr, -w.y * oi);
+      const float x0r = er - tr, x0i = ei - tq;      // bin k
+      const float x1r = er + tr, x1i = -(ei + tq);   // bin 1024 - k
+      const float g0 = own ? librosa(g_power(k, 0), x0r, x0i) : 0.f;
+      const float g1 = own ? librosa(g_power(1024 - k, 0), x1r, x1i) : 0.f;
+      float y0r = g0 * x0r, y0i = g0 * x0i;          // Y[k]     = G[k] / 2
+      float y1r = g1 * x1r, y1i = g1 * x1i;          // Y[M - k] = G[M - k] / 2
+      if (j == 0 && lane == 0) {                     // bins 0 and 1024: real, not halved
+        y0r *= 2.f;
+        y0i = 0.f;
+        y1r *= 2.f;
+        y1i = 0.f;
+      }
+      if (j == 16) {                                 // k = 512 is its own mirror
+        y1r = y0r;
+        y1i = y0i;
+      }
+      const float Ar = y0r + y1r, Ai = y0i - y1i;     // A = Y[k] + conj(Y[M - k])
+      const float dr = y0r - y1r, di = y0i + y1i;     // Y[k] - conj(Y[M - k])
+      const float Br = fmaf(dr, w.x, di * w.y);       // times e^{+2 pi i k / 2048} = (w.x, -w.y)
+      const float Bi = fmaf(di, w.x, -dr * w.y);
+      ck_r[j] = Ar - Bi;  // A + i B
+      ck_i[j] = Ai + Br;
+      cm_r[j] = Ar + Bi;  // conj(A) + i conj(B)
+      cm_i[j] = Br - Ai;
+      if (j == 16) {      // element 512 (lane 0) is read through the mirror path below
+        cm_r[j] = ck_r[j];
+        cm_i[j] = ck_i[j];
+      }
     }
   }
 
@@ -150,7 +208,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) features_backward_kernel(co
   }
 #pragma unroll
   for (int q = 16; q < 32; ++q) {
-    // element lane + 32 q > 512 (or == 512 for lane 0, q == 16): the mirror of bin 1024 - e, owned by src_lane
+    // element lane + 32 q > 512 (or == 512 for lane 0, q == 16): the mirror of element 1024 - e, owned by src_lane
     const float sr = (lane == 0) ? cm_r[(32 - q) & 31] : cm_r[31 - q];
     const float si = (lane == 0) ? cm_i[(32 - q) & 31] : cm_i[31 - q];
     re[bitrev5(q)] = __shfl_sync(0xffffffffu, si, src_lane);
@@ -158,17 +216,26 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) features_backward_kernel(co
   }
   dft32_dit_head(re, im);
   warp_fft1024_tail(re, im, s_tw4, scr, lane);
-  // FFT(swap(C)) = swap(r_a + i r_b): r_a = im, r_b = re; element n = lane + 32 k2
+  // FFT(swap(C)) = swap(y): real part of the inverse = im, imaginary part = re; element n = lane + 32 k2
 
   // ---- times the (true) window -> frame-gradient rows --------------------------------------------------------
   float* fg_a = p.frame_grad + frame_a * NFFT;
-  const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
+  if constexpr (!kHalf) {
+    const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
 #pragma unroll
-  for (int k2 = 0; k2 < 32; ++k2) {
-    const float2 wp = wv[32 * (k2 & 15)];
-    const float w = 2.f * ((k2 < 16) ? wp.x : wp.y);
-    fg_a[lane + 32 * k2] = w * im[k2];
-    if (b_valid) fg_a[NFFT + lane + 32 * k2] = w * re[k2];
+    for (int k2 = 0; k2 < 32; ++k2) {
+      const float2 wp = wv[32 * (k2 & 15)];
+      const float w = 2.f * ((k2 < 16) ? wp.x : wp.y);
+      fg_a[lane + 32 * k2] = w * im[k2];
+      if (b_valid) fg_a[NFFT + lane + 32 * k2] = w * re[k2];
+    }
+  } else {
+    const float2* w2 = reinterpret_cast<const float2*>(s_win) + lane;
+#pragma unroll
+    for (int k2 = 0; k2 < 32; ++k2) {
+      const float2 w = w2[32 * k2];  // {w[2m], w[2m + 1]} / 2, m = lane + 32 k2
+      reinterpret_cast<float2*>(fg_a)[lane + 32 * k2] = make_float2(2.f * w.x * im[k2], 2.f * w.y * re[k2]);
+    }
   }
 }
 
@@ -211,13 +278,17 @@ __global__ void __launch_bounds__(256) log_compress_backward_kernel(const float*
   }
 }
 
-template <int SPEC>
-int launch_bwd(const BwdParams& p, int smem, cudaStream_t st) {
-  auto k = features_backward_kernel<SPEC>;
+template <int MODE, int SPEC>
+int launch_bwd_t(const BwdParams& p, int smem, cudaStream_t st) {
+  auto k = features_backward_kernel<MODE, SPEC>;
   EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   k<<<p.n_tiles, kBwdWarps * 32, smem, st>>>(p);
   EVF_CUDA(cudaGetLastError());
   return EVF_OK;
+}
+template <int SPEC>
+int launch_bwd(const BwdParams& p, int smem, cudaStream_t st) {
+  return p.n_fft == 2048 ? launch_bwd_t<MODE_HALF, SPEC>(p, smem, st) : launch_bwd_t<MODE_PACK2, SPEC>(p, smem, st);
 }
 
 }  // namespace
@@ -228,7 +299,8 @@ int features_backward_launch(const BwdParams& p, cudaStream_t st) {
     set_error("evf_features_backward: more than 128 mel filters are not supported");
     return EVF_ERR_UNSUPPORTED;
   }
-  const int smem = (1024 + 2 * kFftSize + kBwdWarps * (32 * kScrStride + 2 * kGmStride)) * (int)sizeof(float);
+  const int smem = (p.n_fft + 2 * kFftSize + (p.n_fft == 2048 ? 1028 : 0) +
+                    kBwdWarps * (32 * kScrStride + 2 * kGmStride)) * (int)sizeof(float);
   int rc;
   switch (p.spec_type) {
     case EVF_SPEC_MEL: rc = launch_bwd<EVF_SPEC_MEL>(p, smem, st); break;
@@ -241,7 +313,7 @@ int features_backward_launch(const BwdParams& p, cudaStream_t st) {
   if (rc != EVF_OK) return rc;
   if (p.max_len > 0) {
     const dim3 grid((unsigned)((p.max_len + 255) / 256), (unsigned)p.n_utts);
-    overlap_add_kernel<<<grid, 256, 0, st>>>(p.frame_grad, p.sample_off, p.frame_off, 1024, p.hop, p.grad_samples);
+    overlap_add_kernel<<<grid, 256, 0, st>>>(p.frame_grad, p.sample_off, p.frame_off, p.n_fft, p.hop, p.grad_samples);
     EVF_CUDA(cudaGetLastError());
   }
   return EVF_OK;

@@ -109,13 +109,14 @@ struct BwdParams {
   float* grad_samples;           // out, packed like samples
   const float* window;           // plan tables (MODE_PACK2 layouts)
   const float4* tw4;
+  const float2* wpost;           // MODE_HALF
   const float2* melw;            // [k_used] {rising weight -> filter j(k), falling weight -> filter j(k) - 1}
   const int* jk;                 // [k_used] interval index j(k)
   const long long* sample_off;   // [n_utts + 1]
   const long long* frame_off;    // [n_utts + 1]
   int n_utts;
   long long max_len;             // longest utterance (grid sizing)
-  int hop, n_mels, k_used, row_floats, spec_type;
+  int hop, n_mels, k_used, row_floats, spec_type, n_fft;
 };
 int features_backward_launch(const BwdParams& p, cudaStream_t stream);
 int launch_log_compress_backward(const float* x, const float* g, float* out, int64_t n, float clip, cudaStream_t s);

@@ -188,8 +188,8 @@ EVF_API int evf_normalize_by_gathered_stats(float* values_dev, int64_t n, const 
  * generated audio, everyvoice/model/vocoder/HiFiGAN_iSTFT_lightning/hfgl/model.py:581-590, 719-721 -------------
  * grad_spec_dev: d loss / d spectrogram in the layout evf_features_run writes ([total_frames][row_floats],
  * linear domain: the plan must have apply_log == 0); grad_samples_dev: d loss / d samples, packed like the samples;
- * scratch_dev: evf_features_backward_scratch_floats(plan, batch) float32.  n_fft == 1024, float32 samples, spec types
- * mel / mel-librosa / linear.  Deterministic (no atomics). */
+ * scratch_dev: evf_features_backward_scratch_floats(plan, batch) float32.  float32 samples, spec types mel /
+ * mel-librosa / linear (raw is complex: unsupported).  Deterministic (no atomics). */
 EVF_API int64_t evf_features_backward_scratch_floats(const evf_plan* plan, const evf_batch* batch);
 EVF_API int evf_features_backward(const evf_plan* plan, const evf_batch* batch, const float* samples_dev,
                                   const float* grad_spec_dev, float* scratch_dev, float* grad_samples_dev,

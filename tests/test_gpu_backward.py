@@ -28,10 +28,11 @@ def _inputs(B, L, seed):
 
 @pytest.mark.parametrize("spec_type", ["mel", "mel-librosa", "linear"])
 @pytest.mark.parametrize("B,L", [(3, 8192), (2, 5000 + 13), (1, 700)])
-def test_linear_domain_backward_matches_autograd(cuda_device, spec_type, B, L):
+@pytest.mark.parametrize("win,hop", [(1024, 256), (800, 200)])
+def test_linear_domain_backward_matches_autograd(cuda_device, spec_type, B, L, win, hop):
     """d/dx of sum(R * transform(x)) for a random R: exactly J^T R, no dependence on loss non-smoothness.  L = 8192
     is HiFiGAN's segment; 5013 is not a multiple of the hop; 700 has both reflect margins inside every frame."""
-    tf, otf = _pair(spec_type)
+    tf, otf = _pair(spec_type, win, hop)
     x = _inputs(B, L, 700)
     xr = torch.tensor(x, requires_grad=True)
     y_ref = otf(xr)
@@ -39,7 +40,7 @@ def test_linear_domain_backward_matches_autograd(cuda_device, spec_type, B, L):
     (y_ref * R).sum().backward()
     xg = torch.tensor(x, device=cuda_device, requires_grad=True)
     y = tf(xg)
-    assert tuple(y.shape) == tuple(y_ref.shape) == (B, y_ref.shape[1], L // 256 + 1)
+    assert tuple(y.shape) == tuple(y_ref.shape) == (B, y_ref.shape[1], L // hop + 1)
     (y * R.to(cuda_device)).sum().backward()
     scale = float(xr.grad.abs().max())
     err = float((xg.grad.cpu() - xr.grad).abs().max())
@@ -100,6 +101,28 @@ def test_backward_is_deterministic_and_rejects_unsupported(cuda_device):
     raw, _ = _pair("raw")
     with pytest.raises(NotImplementedError):
         raw(x.clone().requires_grad_(True))
-    big = ev.get_spectral_transform("mel", 2048, 2048, 512, 44100, 128, 0, 8000)
-    with pytest.raises(ev._lib.EvfError):
-        big(torch.zeros(1, 8192, device=cuda_device, requires_grad=True)).sum().backward()
+
+
+@pytest.mark.parametrize("spec_type", ["mel", "mel-librosa", "linear"])
+@pytest.mark.parametrize("win,hop,f_max", [(2048, 512, 8000), (2048, 512, 22050), (1200, 300, 8000)])
+def test_n_fft_2048_backward_matches_autograd(cuda_device, spec_type, win, hop, f_max):
+    """44.1 kHz vocoder configuration (BASELINE configs[2]): one frame per FFT job, half-size inverse; also a window
+    shorter than n_fft with a hop that is not a power of two."""
+    import everyvoice_b200 as ev
+    from everyvoice_b200 import synth
+    from oracle import ev_oracle as O
+
+    args = (spec_type, 2048, win, hop, 44100, 128, 0, f_max)
+    tf, otf = ev.get_spectral_transform(*args), O.get_spectral_transform(*args)
+    B, L = 2, 16384 + 77
+    x = np.stack([synth.speech_like(L, 44100, seed=950 + b) * np.float32(0.6) for b in range(B)])
+    xr = torch.tensor(x, requires_grad=True)
+    y_ref = otf(xr)
+    R = torch.from_numpy(np.random.default_rng(hop).normal(size=tuple(y_ref.shape)).astype(np.float32))
+    (y_ref * R).sum().backward()
+    xg = torch.tensor(x, device=cuda_device, requires_grad=True)
+    y = tf(xg)
+    assert tuple(y.shape) == tuple(y_ref.shape)
+    (y * R.to(cuda_device)).sum().backward()
+    scale = float(xr.grad.abs().max())
+    assert float((xg.grad.cpu() - xr.grad).abs().max()) <= RTOL_GRAD * scale
