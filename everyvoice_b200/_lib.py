@@ -28,7 +28,7 @@ EVF_ERR_OUT_OF_MEMORY = 7
 SPEC_TYPES = {"mel": 0, "mel-librosa": 1, "linear": 2, "raw": 3}
 SAMPLES_F32, SAMPLES_S16 = 0, 1
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class evf_config(C.Structure):
@@ -76,6 +76,7 @@ PROTOTYPES = {
     "evf_features_backward_scratch_floats": (C.c_int64, [_P, _P]),
     "evf_features_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "evf_log_compress_backward": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, _P]),
+    "evf_pitch_fill_unvoiced": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     # audio front-end (process_audio numerics)
     "evf_resampler_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.POINTER(_P)]),
     "evf_resampler_destroy": (C.c_int, [_P]),

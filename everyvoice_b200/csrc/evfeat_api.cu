@@ -611,6 +611,15 @@ int evf_log_compress(const float* in_dev, float* out_dev, int64_t n, float c, fl
   return launch_log_compress(in_dev, out_dev, n, c, clip_val, static_cast<cudaStream_t>(stream));
 }
 
+int evf_pitch_fill_unvoiced(const double* pitch_dev, const int64_t* offsets_dev, int32_t n_utts, float* out_dev,
+                            void* stream) {
+  if (n_utts < 0 || (n_utts > 0 && (!pitch_dev || !offsets_dev || !out_dev))) {
+    set_error("evf_pitch_fill_unvoiced: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_pitch_fill_unvoiced(pitch_dev, offsets_dev, n_utts, out_dev, static_cast<cudaStream_t>(stream));
+}
+
 int evf_log_compress_backward(const float* in_dev, const float* grad_out_dev, float* grad_in_dev, int64_t n,
                               float clip_val, void* stream) {
   if (n < 0 || (n > 0 && (!in_dev || !grad_out_dev || !grad_in_dev))) {

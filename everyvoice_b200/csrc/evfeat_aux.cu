@@ -308,6 +308,50 @@ int launch_stats_merge(const double* parts, int n_parts, int stride, double* out
   return EVF_OK;
 }
 
+// Pitch post-processing of Preprocessor.extract_pitch (preprocessor.py:278-285): pitch[pitch == 0] = NaN, the NaNs
+// are filled by np.interp over the frame index (linear between the neighbouring voiced frames, constant beyond the
+// first / last voiced frame), an utterance without any voiced frame becomes all zeros; float64 in (what pyworld
+// returns), float32 out (torch.tensor(pitch).float()).  One thread per utterance: a pitch track has at most a few
+// thousand frames and the fill is a sequential walk over runs; np.interp's arithmetic is mirrored operation by
+// operation in double precision (slope * (x - x0) + y0 without contraction).
+__global__ void __launch_bounds__(64) pitch_fill_unvoiced_kernel(const double* __restrict__ pitch,
+                                                                 const long long* __restrict__ off, int n_utts,
+                                                                 float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_utts) return;
+  const double* x = pitch + off[b];
+  float* y = out + off[b];
+  const long long T = off[b + 1] - off[b];
+  auto voiced = [](double v) { return v != 0.0 && v == v; };  // 0 -> NaN by the reference; a NaN from the tracker is a gap too
+  long long prev = -1;  // last voiced frame seen
+  for (long long t = 0; t < T; ++t) {
+    const double v = x[t];
+    if (!voiced(v)) continue;
+    if (prev < 0) {
+      for (long long u = 0; u < t; ++u) y[u] = (float)v;  // np.interp: left of the first point -> its value
+    } else if (t - prev > 1) {
+      const double y0 = x[prev], slope = __ddiv_rn(__dsub_rn(v, y0), (double)(t - prev));
+      for (long long u = prev + 1; u < t; ++u) y[u] = (float)__dadd_rn(__dmul_rn(slope, (double)(u - prev)), y0);
+    }
+    y[t] = (float)v;
+    prev = t;
+  }
+  if (prev < 0) {
+    for (long long u = 0; u < T; ++u) y[u] = 0.f;  // ValueError branch: pitch-less sample -> zeros
+  } else {
+    const float last = (float)x[prev];
+    for (long long u = prev + 1; u < T; ++u) y[u] = last;  // right of the last point -> its value
+  }
+}
+
+int launch_pitch_fill_unvoiced(const double* pitch, const int64_t* offsets, int n_utts, float* out, cudaStream_t s) {
+  if (n_utts == 0) return EVF_OK;
+  pitch_fill_unvoiced_kernel<<<(n_utts + 63) / 64, 64, 0, s>>>(pitch, reinterpret_cast<const long long*>(offsets),
+                                                              n_utts, out);
+  EVF_CUDA(cudaGetLastError());
+  return EVF_OK;
+}
+
 int launch_log_compress(const float* in, float* out, int64_t n, float c, float clip, cudaStream_t s) {
   if (n == 0) return EVF_OK;
   log_compress_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, s>>>(in, out, n, c, clip);

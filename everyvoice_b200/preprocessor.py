@@ -121,6 +121,40 @@ class Preprocessor:
         return res.utterance(0).cpu(), res.sr
 
     # ------------------------------------------------------------------------------------------
+    # Pitch (preprocessor.py:236-285): DIO / StoneMask stay with pyworld on the CPU like in the reference;
+    # everything after them runs on the device
+    # ------------------------------------------------------------------------------------------
+    def postprocess_pitch_batch(self, tracks):
+        """``tracks``: list of float64 pitch tracks as pyworld returns them (0 = unvoiced).  Unvoiced frames are
+        filled by linear interpolation over the frame index (``_interpolate`` / np.interp, :236-242, :278-283), a
+        track without a voiced frame becomes zeros, float32 out.  Returns ``(packed device tensor, offsets)``."""
+        device = _require_cuda(self.device)
+        arrs = [np.ascontiguousarray(t.detach().cpu().numpy() if torch.is_tensor(t) else t, dtype=np.float64).reshape(-1)
+                for t in tracks]
+        lens = np.array([len(a) for a in arrs], dtype=np.int64)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        packed = torch.from_numpy(np.concatenate(arrs) if arrs else np.zeros(0)).to(device)
+        out = torch.empty(int(off[-1]), dtype=torch.float32, device=device)
+        d_off = torch.from_numpy(off).to(device)
+        lib = _lib.load()
+        with torch.cuda.device(device):
+            _lib.check(lib.evf_pitch_fill_unvoiced(_ptr(packed), _ptr(d_off), len(arrs), _ptr(out), _stream_ptr(device)))
+        return out, off
+
+    def extract_pitch(self, audio_tensor: torch.Tensor):
+        """Reference: preprocessor.py:244-285, same argument and result (``[T]`` float32 CPU tensor).  pyworld's
+        ``dio`` (``speed=4``, ``frame_period = hop / sr * 1000``) and ``stonemask`` run on the CPU exactly as in the
+        reference (third-party C++; ImportError if pyworld is missing); the rest is ``postprocess_pitch_batch``."""
+        import pyworld as pw
+
+        x = audio_tensor.squeeze(0).detach().cpu().numpy().astype(np.float64)
+        pitch, t = pw.dio(x, self.input_sampling_rate,
+                          frame_period=self.audio_config.fft_hop_size / self.input_sampling_rate * 1000, speed=4)
+        pitch = pw.stonemask(x, pitch, t, self.input_sampling_rate)
+        out, _ = self.postprocess_pitch_batch([pitch])
+        return out.cpu()
+
+    # ------------------------------------------------------------------------------------------
     # The reference's per-utterance operators
     # ------------------------------------------------------------------------------------------
     def extract_spectral_features(self, audio_tensor: torch.Tensor, transform, normalize=True):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define EVF_ABI_VERSION 5
+#define EVF_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define EVF_API __attribute__((visibility("default")))
@@ -183,6 +183,13 @@ EVF_API int evf_stats_merge(const double* parts_dev, int32_t n_parts, int32_t st
                     void* stream);
 EVF_API int evf_normalize_by_gathered_stats(float* values_dev, int64_t n, const double* parts_dev, int32_t n_parts,
                                     int32_t stride_doubles, void* stream);
+
+/* Pitch post-processing of Preprocessor.extract_pitch, everyvoice/preprocessor/preprocessor.py:278-285 (everything
+ * after pyworld's dio / stonemask, which stay on the CPU with the reference): zeros (unvoiced) are filled by linear
+ * interpolation over the frame index like np.interp, constant beyond the first / last voiced frame; an utterance
+ * without a voiced frame becomes zeros.  pitch_dev: packed float64 tracks; out_dev: packed float32. */
+EVF_API int evf_pitch_fill_unvoiced(const double* pitch_dev, const int64_t* offsets_dev, int32_t n_utts, float* out_dev,
+                                    void* stream);
 
 /* ---- backward of the transform: HiFiGAN trains through the mel spectrogram of the
  * generated audio, everyvoice/model/vocoder/HiFiGAN_iSTFT_lightning/hfgl/model.py:581-590, 719-721 -------------

@@ -514,3 +514,21 @@ def process_audio_tensor(audio: np.ndarray, sr: int, *, normalize=True, resample
         raise ValueError("We must know the hop size for processing audio because EveryVoice enforces that the "
                          "number of samples is evenly divisible by the hop size")
     return x[: (len(x) // hop_size) * hop_size], sr
+
+
+# ------------------------------------------------------------------------------------------------
+# pitch post-processing: everything in Preprocessor.extract_pitch after pyworld's dio / stonemask
+# (everyvoice/preprocessor/preprocessor.py:236-285).  Pinned against the live reference (with a stub pyworld that
+# returns seeded tracks) by oracle/make_golden_pitch.py -> tests/golden/pitch.npz.
+# ------------------------------------------------------------------------------------------------
+def postprocess_pitch(pitch: np.ndarray) -> np.ndarray:
+    """``pitch[pitch == 0] = nan``; NaNs filled by ``np.interp`` over the frame index (preprocessor.py:236-242);
+    nothing voiced (``ValueError`` from np.interp on an empty array) -> zeros; ``torch.tensor(pitch).float()``."""
+    x = np.array(pitch, dtype=np.float64, copy=True)
+    x[x == 0] = np.nan
+    nans = np.isnan(x)
+    try:
+        x[nans] = np.interp(nans.nonzero()[0], (~nans).nonzero()[0], x[~nans])
+    except ValueError:
+        x[np.isnan(x)] = 0
+    return x.astype(np.float32)

@@ -147,3 +147,40 @@ def test_process_audio_file_mirror(cuda_device, tmp_path):
     pre2 = _pre(cuda_device, min_audio_length=2.0)
     assert pre2.process_audio(path, hop_size=256) == (None, None)
     assert pre2.counters["audio_too_short"] == 1
+
+
+def test_pitch_postprocessing_bit_exact_and_variance_flow(cuda_device, golden_dir):
+    """Everything after pyworld in extract_pitch (preprocessor.py:278-285) on the device, then the same path energy
+    takes: phone-level averaging by durations (:662-669) and Scaler statistics / normalisation (:453-490)."""
+    import everyvoice_b200 as ev
+    from everyvoice_b200 import synth
+    from oracle import ev_oracle as O
+    from oracle.make_golden_pitch import pitch_tracks
+
+    golden = np.load(golden_dir / "pitch.npz")
+    tracks = pitch_tracks()
+    names = sorted(tracks)
+    pre = _pre(cuda_device)
+    out, off = pre.postprocess_pitch_batch([tracks[n] for n in names])
+    assert out.dtype == torch.float32 and int(off[-1]) == sum(len(tracks[n]) for n in names)
+    for b, n in enumerate(names):
+        got = out[int(off[b]) : int(off[b + 1])].cpu().numpy()
+        assert np.array_equal(got, golden[n]), n                      # np.interp mirrored operation by operation
+    # phone-level pitch + corpus statistics, against the oracle's per-utterance flow
+    durs = [synth.synthetic_durations(len(tracks[n]), seed=70 + b) for b, n in enumerate(names)]
+    d_packed, p_off = synth.pack_ragged(durs)
+    phone = pre.average_data_by_durations_ragged(out, off, torch.from_numpy(d_packed), p_off)
+    o_scaler = O.Scaler()
+    for b, n in enumerate(names):
+        want = O.average_data_by_durations(torch.from_numpy(golden[n]), torch.from_numpy(durs[b]))
+        got = phone[int(p_off[b]) : int(p_off[b + 1])].cpu()
+        nan = torch.isnan(want)
+        assert torch.equal(torch.isnan(got), nan)
+        assert float((got[~nan] - want[~nan]).abs().max()) <= 1e-3 if bool((~nan).any()) else True
+        o_scaler.append(want)
+    _, p_scaler = pre.compute_stats(pitch=phone, n_pitch_files=len(names))
+    stats = pre.normalize_stats(None, p_scaler, distributed=False)["pitch"]
+    ref = o_scaler.calculate_stats()
+    assert stats["sample_size"] == ref["sample_size"] == len(names)
+    for k in ("min", "max", "mean", "std"):
+        assert stats[k] == pytest.approx(ref[k], rel=1e-5), k
