@@ -161,8 +161,7 @@ class _SpectralFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x2d: torch.Tensor, tf: "SpectralTransform", keep_last: bool):
         B, L = x2d.shape
-        offsets = np.arange(B + 1, dtype=np.int64) * L
-        batch = tf.make_batch(offsets, x2d.device, apply_log=False, keep_last=keep_last)
+        batch = tf.uniform_batch(B, L, x2d.device, apply_log=False, keep_last=keep_last)
         spec, _ = tf.run(batch, x2d.reshape(-1), want_energy=False)
         T = tf.num_frames(L, keep_last)
         ctx.save_for_backward(x2d)
@@ -269,6 +268,20 @@ class SpectralTransform:
                    sample_dtype=torch.float32) -> RaggedBatch:
         fmt = _lib.SAMPLES_S16 if sample_dtype == torch.int16 else _lib.SAMPLES_F32
         return RaggedBatch(self.plan(device, apply_log, keep_last, fmt), sample_offsets)
+
+    def uniform_batch(self, B: int, L: int, device=None, apply_log=True, keep_last=False) -> RaggedBatch:
+        """The batch of ``B`` equal-length utterances (training segments).  Cached: a training loop calls the
+        transform with the same shape every step, and building a batch costs a host pass over the tile list, a
+        device allocation and a copy."""
+        device = _require_cuda(device if device is not None else self._device)
+        key = (device.index, int(B), int(L), bool(apply_log), bool(keep_last))
+        cache = self.__dict__.setdefault("_uniform_batches", {})
+        batch = cache.get(key)
+        if batch is None:
+            if len(cache) >= 8:
+                cache.pop(next(iter(cache)))
+            batch = cache[key] = self.make_batch(np.arange(B + 1, dtype=np.int64) * int(L), device, apply_log, keep_last)
+        return batch
 
     def run(self, batch: RaggedBatch, samples: torch.Tensor, spec_out: torch.Tensor | None = None,
             energy_out: torch.Tensor | None = None, want_energy=True):
