@@ -113,7 +113,7 @@ class ArtefactWriter:
     def write_pitch(self, items, values, offsets):
         self.write_ragged(items, values, offsets, "pitch", "pitch.pt")
 
-    def write_audio(self, items, processed, kept_only: bool = True):
+    def write_audio(self, items, processed):
         """``processed``: the ``ProcessedAudio`` of ``process_audio_batch(out_dtype=torch.int16)``; items are
         indexed like its INPUT list (skipped utterances get no file, like the reference)."""
         if processed.samples.dtype != torch.int16:

@@ -59,18 +59,6 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 namespace {
 
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = false;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    ok = (cudaSetDevice(dev) == cudaSuccess);
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
-
 template <typename T>
 int upload(const std::vector<T>& h, T** d) {
   *d = nullptr;

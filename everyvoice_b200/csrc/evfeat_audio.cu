@@ -31,18 +31,6 @@ struct evf_resampler {
 namespace evf {
 namespace {
 
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = true;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
-
 __device__ __forceinline__ float sample_to_float(float v) { return v; }
 __device__ __forceinline__ float sample_to_float(short v) { return (float)v * (1.0f / 32768.0f); }
 

@@ -251,13 +251,13 @@ __global__ void __launch_bounds__(256) overlap_add_kernel(const float* __restric
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= L) return;
   const long long H = n_fft / 2;
-  long long pos[3];
-  int n_pos = 0;
-  pos[n_pos++] = s + H;
-  if (s >= 1 && s <= H) pos[n_pos++] = H - s;
-  if (s <= L - 2 && s >= L - 1 - H) pos[n_pos++] = H + 2 * (L - 1) - s;
+  // the padded positions that read x[s]: itself, and its mirror images in the left / right reflect margin
+  const long long pos[3] = {s + H, H - s, H + 2 * (L - 1) - s};
+  const bool use[3] = {true, s >= 1 && s <= H, s <= L - 2 && s >= L - 1 - H};
   float g = 0.f;
-  for (int i = 0; i < n_pos; ++i) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (!use[i]) continue;
     const long long pp = pos[i];
     long long t_hi = pp / hop;
     if (t_hi > T - 1) t_hi = T - 1;

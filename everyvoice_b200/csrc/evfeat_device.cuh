@@ -156,3 +156,47 @@ __device__ __forceinline__ int reflect_index(int j, int L) {
   return (j < 0) ? 0 : j;  // only reachable for frames beyond the last valid one
 }
 
+// ---- tile descriptors and input staging shared by the feature kernels -----------------------------------------
+// Tile descriptors are host-built (no dependent loads) and fetched two tiles ahead, as two 16-byte words.
+__device__ __forceinline__ TileDesc load_tile_desc(const TileDesc* tiles, int tile) {
+  const int4* q = reinterpret_cast<const int4*>(tiles + tile);
+  const int4 a = __ldg(q), b = __ldg(q + 1);
+  TileDesc ti;
+  ti.s_off = ((long long)(unsigned)a.x) | ((long long)a.y << 32);
+  ti.out_frame0 = ((long long)(unsigned)a.z) | ((long long)a.w << 32);
+  ti.L = b.x;
+  ti.start = b.y;
+  ti.nvalid = b.z;
+  ti.span = b.w;
+  return ti;
+}
+
+// Stage one tile into `buf`.  NT threads (a warp in the steady state, the CTA in the prologue) store the words the
+// bulk copy cannot take -- reflected margins, a 16-byte-misaligned span -- then a leader arms the mbarrier and issues
+// one bulk copy for the aligned in-range part [a_lo, a_hi) (evf_stage_bulk).  The caller orders the manual stores before
+// the leader's arrive (__syncwarp / __syncthreads).
+template <typename SampleT>
+__device__ __forceinline__ void evf_stage_manual(const SampleT* __restrict__ samples, const TileDesc& ti, SampleT* buf,
+                                             int t, int nt, int& a_lo, int& a_hi) {
+  constexpr int kAlign = 16 / (int)sizeof(SampleT);  // samples per 16 bytes (bulk-copy granularity)
+  const int lo = max(0, -ti.start);                   // first tile word inside the utterance
+  const int hi = min(ti.span, ti.L - ti.start);       // one past the last
+  a_lo = lo;
+  a_hi = lo;
+  // tile word i <-> packed sample s_off + start + i ; both sides must be 16-byte aligned
+  if ((((ti.s_off + ti.start + lo) | lo) & (kAlign - 1)) == 0 && hi > lo) a_hi = lo + ((hi - lo) & ~(kAlign - 1));
+  const int total = a_lo + (ti.span - a_hi);
+  const SampleT* src = samples + ti.s_off;
+  for (int e = t; e < total; e += nt) {
+    const int w = (e < a_lo) ? e : a_hi + (e - a_lo);
+    buf[w] = __ldg(src + reflect_index(ti.start + w, ti.L));
+  }
+}
+template <typename SampleT>
+__device__ __forceinline__ void evf_stage_bulk(const SampleT* __restrict__ samples, const TileDesc& ti, SampleT* buf,
+                                           uint64_t* bar, int a_lo, int a_hi) {
+  const uint32_t bytes = (uint32_t)(a_hi - a_lo) * (uint32_t)sizeof(SampleT);
+  fence_proxy_async();  // generic-proxy accesses to the buffer (reads of the previous tile) before the async write
+  mbar_arrive_expect_tx(bar, bytes);
+  if (bytes) bulk_g2s(buf + a_lo, samples + ti.s_off + ti.start + a_lo, bytes, bar);
+}

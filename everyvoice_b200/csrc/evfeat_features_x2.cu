@@ -92,7 +92,6 @@ __global__ void __launch_bounds__(kX2Warps * 32, 1) features_kernel_x2(const Fea
   constexpr int kThreads = WARPS * 32;
   constexpr int NFFT = 1024;
   constexpr bool kMel = (SPEC == EVF_SPEC_MEL || SPEC == EVF_SPEC_MEL_LIBROSA);
-  constexpr int kAlign = 16 / (int)sizeof(SampleT);
 
   extern __shared__ __align__(16) float smem[];
   float* s_win = smem + p.off_win;
@@ -134,36 +133,12 @@ __global__ void __launch_bounds__(kX2Warps * 32, 1) features_kernel_x2(const Fea
   const SampleT* __restrict__ samples = static_cast<const SampleT*>(p.samples);
   const int G = gridDim.x;
 
-  auto tile_info = [&](int tile) {
-    const int4* q = reinterpret_cast<const int4*>(p.tiles + tile);
-    const int4 a = __ldg(q), b = __ldg(q + 1);
-    TileInfo ti;
-    ti.s_off = ((long long)(unsigned)a.x) | ((long long)a.y << 32);
-    ti.out_frame0 = ((long long)(unsigned)a.z) | ((long long)a.w << 32);
-    ti.L = b.x;
-    ti.start = b.y;
-    ti.nvalid = b.z;
-    ti.span = b.w;
-    return ti;
-  };
+  auto tile_info = [&](int tile) { return load_tile_desc(p.tiles, tile); };
   auto stage_manual = [&](const TileInfo& ti, SampleT* buf, int t, int nt, int& a_lo, int& a_hi) {
-    const int lo = max(0, -ti.start);
-    const int hi = min(ti.span, ti.L - ti.start);
-    a_lo = lo;
-    a_hi = lo;
-    if ((((ti.s_off + ti.start + lo) | lo) & (kAlign - 1)) == 0 && hi > lo) a_hi = lo + ((hi - lo) & ~(kAlign - 1));
-    const int total = a_lo + (ti.span - a_hi);
-    const SampleT* src = samples + ti.s_off;
-    for (int e = t; e < total; e += nt) {
-      const int w = (e < a_lo) ? e : a_hi + (e - a_lo);
-      buf[w] = __ldg(src + reflect_index(ti.start + w, ti.L));
-    }
+    evf_stage_manual(samples, ti, buf, t, nt, a_lo, a_hi);
   };
   auto stage_bulk = [&](const TileInfo& ti, SampleT* buf, uint64_t* bar, int a_lo, int a_hi) {
-    const uint32_t bytes = (uint32_t)(a_hi - a_lo) * (uint32_t)sizeof(SampleT);
-    fence_proxy_async();
-    mbar_arrive_expect_tx(bar, bytes);
-    if (bytes) bulk_g2s(buf + a_lo, samples + ti.s_off + ti.start + a_lo, bytes, bar);
+    evf_stage_bulk(samples, ti, buf, bar, a_lo, a_hi);
   };
   auto in_buf = [&](int b) { return reinterpret_cast<SampleT*>(smem + (b ? p.off_in2 : p.off_in)); };
 

@@ -80,6 +80,21 @@ struct PlanTables {
   int k_used = 0, n_chunk = 1, n_heads = 0, m_pad = 32, n_slots = 34;
 };
 
+// Makes `dev` the current device for the lifetime of the guard and restores the previous one.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
 #define EVF_CUDA(call)                                          \
