@@ -301,6 +301,10 @@ def run_ours(args, w, wname):
     _lib.load()
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # staging buffers on the GPU's own NUMA node (matters for the end-to-end leg at N > 2)
+    from everyvoice_b200.distributed import bind_to_gpu_numa_node
+
+    numa_cpus = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner on the C-level stdout when the communicator is created; stdout carries
@@ -517,6 +521,8 @@ def run_ours(args, w, wname):
             "e2e": None if not e2e_ok else {"value": e2e_f32, "unit": UNIT, "h2d_bytes_per_step": int(info_f32["h2d"]),
                     "d2h_bytes_per_step": int(info_f32["d2h"]), "steps": e2e_steps, "input_format": "float32, pinned host",
                     "chunks": info_f32["chunks"], "gpu_launches_per_step": info_f32["launches"],
+                    "host_affinity": (f"rank 0 bound to the {len(numa_cpus)} cores NVML reports local to its GPU"
+                                      if numa_cpus else "not bound"),
                     "api": "Preprocessor.make_corpus_pipeline(...).run(host buffers): batch planning + chunked "
                            "H2D / kernels / D2H on three streams, every step",
                     "pcm16_input": {"value": e2e_s16, "unit": UNIT, "h2d_bytes_per_step": int(info_s16["h2d"]),

@@ -90,3 +90,35 @@ def finalize_stats(stats5, sample_size: int) -> dict:
         "mean": f32(mean32),
         "std": f32(std32),
     }
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> list[int] | None:
+    """Pin this process to the CPU cores NVML reports as local to GPU ``local_rank`` (its NUMA node / PCIe root).
+    Call it BEFORE allocating pinned host buffers: page-locked memory is placed by first touch, and a rank whose
+    staging buffers sit on the other socket pushes every H2D / D2H byte over the inter-socket link -- with 4-8 ranks
+    per box that link, not PCIe, bounds the end-to-end rate.  Returns the CPU list, or ``None`` if NVML or the
+    affinity call is unavailable (nothing is changed then)."""
+    import os
+
+    try:
+        import pynvml
+        import torch
+
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(local_rank)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(
+                f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0".encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1 and 64 * i + b < n_cpu]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
