@@ -2,7 +2,7 @@
 bucketed by the exact log-power (run on the GPU box)."""
 import sys
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 import numpy as np, torch
 import everyvoice_b200 as ev
 from everyvoice_b200 import synth

@@ -1,7 +1,6 @@
 """Timing of the differentiable transform (forward + backward) on one B200, next to the
 same graph in plain torch on the same GPU (torch.stft through cuFFT + mel-basis matmul + log: what the reference's
-HiFiGAN training executes, hfgl/model.py:581-590, 719-721) -- here built from the oracle's transform moved to CUDA,
-as a measured baseline only.
+HiFiGAN training executes, hfgl/model.py:581-590, 719-721), as a measured baseline only.
 
     python tools/backward_bench.py > profiles/rNN_backward_bench.json"""
 import json
@@ -14,7 +13,7 @@ import torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import everyvoice_b200 as ev  # noqa: E402
-from oracle import ev_oracle as O  # noqa: E402  (baseline leg of a measurement tool, like bench.py's cpu_baseline)
+from everyvoice_b200 import filterbanks  # noqa: E402
 
 
 def timed(fn, reps):
@@ -35,8 +34,7 @@ def timed(fn, reps):
 def main():
     dev = torch.device("cuda", 0)
     tf = ev.get_spectral_transform("mel", 1024, 1024, 256, 22050, 80, 0, 8000).to(dev)
-    fb = O.torchaudio_melscale_fbanks(513, 0.0, 8000.0, 80, 22050, "slaney", "htk")
-    fb = (fb if torch.is_tensor(fb) else torch.from_numpy(np.asarray(fb))).to(dev, torch.float32)
+    fb = filterbanks.melscale_fbanks_htk_slaney(513, 0.0, 8000.0, 80, 22050).to(dev, torch.float32)
     win = torch.hann_window(1024, device=dev)
 
     def otf(x):  # T.MelSpectrogram's graph on the GPU: torch.stft (cuFFT) -> |.|^2 -> (spec^T @ fb)^T
@@ -62,7 +60,7 @@ def main():
 
         def torch_gpu():
             xg = x.detach().requires_grad_(True)
-            y = O.dynamic_range_compression_torch(otf(xg))
+            y = torch.log(torch.clamp(otf(xg), min=1e-5))
             (torch.nn.functional.l1_loss(y, target) * 45).backward()
             return xg.grad
 
@@ -71,7 +69,7 @@ def main():
             g2 = torch_gpu()
             rel = float((g1 - g2).abs().max() / g2.abs().max())
             t_ref = timed(torch_gpu, reps)
-        except Exception as e:  # the oracle's transform may hold CPU buffers
+        except Exception as e:
             rel, t_ref = None, (None, None)
             out.setdefault("torch_gpu_error", repr(e)[:200])
         t_ours = timed(ours, reps)
