@@ -24,7 +24,7 @@ def assert_log_spec_close(ours: torch.Tensor, ref: torch.Tensor, truth: np.ndarr
 
     For the 513/1025-bin ``linear`` type only: weak bins (log-power below about -3) of a frame
     whose strongest bins are ~1e9 stronger are at the fp32 FFT round-off floor.  Measured on the
-    B200 (tools/err_stats.py, profiles/accuracy_r01.txt): against the exact float64 value the
+    B200 (tests/tools/err_stats.py): against the exact float64 value the
     reference's own CPU fp32 result is off by up to 7.4e-3 there and the CUDA path by up to
     6.8e-3, with equal RMS error -- two correct fp32 FFTs cannot agree to 1e-3 on those bins.
     The bar for ``linear`` is therefore:
