@@ -236,28 +236,29 @@ __global__ void __launch_bounds__(32) loudness_partial_kernel(const float* __res
   const Biquad s = P.shelf, h = P.highpass;
   float acc = 0.f;
   const int total = 2 * P.step;
+  // Software pipeline: the 64 loads of tile c + 1 are issued before the recursion runs over tile c (they sit in
+  // registers until the tile buffer is free), so the DRAM round trip hides behind 64 x ~22 dependent instructions.
+  float v[32][kLdTile / 32];
+  auto load_tile = [&](int c0) {
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {  // row r = the stream of lane r
+      const long long tb = (q0 + r + 1) * P.step - 2 * (long long)P.step + c0;
+#pragma unroll
+      for (int hh = 0; hh < kLdTile / 32; ++hh) {
+        const long long t = tb + 32 * hh + lane;
+        v[r][hh] = (t >= 0 && t < L) ? __ldg(xs + t) : 0.f;
+      }
+    }
+  };
+  load_tile(0);
   for (int c0 = 0; c0 < total; c0 += kLdTile) {
     __syncwarp();
-    // row r = the stream of lane r.  All 64 loads of a tile are issued before the first store (two batches of 16
-    // rows): one DRAM latency per batch instead of one per four rows.
 #pragma unroll
-    for (int rb = 0; rb < 32; rb += 16) {
-      float v[16][kLdTile / 32];
+    for (int r = 0; r < 32; ++r)
 #pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const long long tb = (q0 + rb + r + 1) * P.step - 2 * (long long)P.step + c0;
-#pragma unroll
-        for (int hh = 0; hh < kLdTile / 32; ++hh) {
-          const long long t = tb + 32 * hh + lane;
-          v[r][hh] = (t >= 0 && t < L) ? __ldg(xs + t) : 0.f;
-        }
-      }
-#pragma unroll
-      for (int r = 0; r < 16; ++r)
-#pragma unroll
-        for (int hh = 0; hh < kLdTile / 32; ++hh) tile[rb + r][32 * hh + lane] = v[r][hh];
-    }
+      for (int hh = 0; hh < kLdTile / 32; ++hh) tile[r][32 * hh + lane] = v[r][hh];
     __syncwarp();
+    if (c0 + kLdTile < total) load_tile(c0 + kLdTile);
     const int n_it = min(kLdTile, total - c0);
     for (int i = 0; i < n_it; ++i) {
       const float x0 = tile[lane][i];
