@@ -204,8 +204,8 @@ struct LoudnessParams {
   int gate, step;  // gate == 4 * step
 };
 
-// Pass 1, one thread per 100 ms step of one utterance: the two K-weighting biquads (direct form I; torchaudio's
-// lfilter(clamp=True) clamps each filter's OUTPUT to [-1, 1], the recursion itself runs on the unclamped state),
+// Pass 1, one thread per 100 ms step of one utterance: the two K-weighting biquads (torchaudio's lfilter(clamp=True)
+// clamps each filter's OUTPUT to [-1, 1], the recursion itself runs on the unclamped state),
 // squared and summed over the step.  The recursion is sequential in time, so every thread starts one step early
 // from a zero state: the slowest pole of the 38 Hz high-pass (a double pole at 1 - 2*pi*38/sr) has decayed to
 // n * r^n < 1e-7 after one step at every sampling rate, i.e. below float32 resolution of the running state.
@@ -231,8 +231,8 @@ __global__ void __launch_bounds__(32) loudness_partial_kernel(const float* __res
   const long long t_end = (q + 1) * P.step;
   const long long t_begin = t_end - 2 * (long long)P.step;  // may be negative for q == 0
   const long long t_acc = t_end - P.step;
-  float x1 = 0.f, x2 = 0.f, u1 = 0.f, u2 = 0.f;   // shelf: inputs and unclamped outputs
-  float c1 = 0.f, c2 = 0.f, v1 = 0.f, v2 = 0.f;   // high-pass: (clamped) inputs and unclamped outputs
+  float s1a = 0.f, s2a = 0.f;   // shelf state
+  float s1b = 0.f, s2b = 0.f;   // high-pass state (its input is the CLAMPED shelf output, like lfilter(clamp=True))
   const Biquad s = P.shelf, h = P.highpass;
   float acc = 0.f;
   const int total = 2 * P.step;
@@ -261,20 +261,16 @@ __global__ void __launch_bounds__(32) loudness_partial_kernel(const float* __res
     if (c0 + kLdTile < total) load_tile(c0 + kLdTile);
     const int n_it = min(kLdTile, total - c0);
     for (int i = 0; i < n_it; ++i) {
+      // transposed direct form II: two state words per biquad, 5 dependent-free-ish FMAs each (the same transfer
+      // function as torchaudio's direct form I; rounding differs at the 1e-7 level, far inside the LKFS tolerance)
       const float x0 = tile[lane][i];
-      float u0 = fmaf(s.b0, x0, fmaf(s.b1, x1, s.b2 * x2));
-      u0 = fmaf(-s.a1, u1, fmaf(-s.a2, u2, u0));
-      x2 = x1;
-      x1 = x0;
-      u2 = u1;
-      u1 = u0;
+      const float u0 = fmaf(s.b0, x0, s1a);
+      s1a = fmaf(s.b1, x0, fmaf(-s.a1, u0, s2a));
+      s2a = fmaf(s.b2, x0, -s.a2 * u0);
       const float cc = fminf(fmaxf(u0, -1.f), 1.f);
-      float v0 = fmaf(h.b0, cc, fmaf(h.b1, c1, h.b2 * c2));
-      v0 = fmaf(-h.a1, v1, fmaf(-h.a2, v2, v0));
-      c2 = c1;
-      c1 = cc;
-      v2 = v1;
-      v1 = v0;
+      const float v0 = fmaf(h.b0, cc, s1b);
+      s1b = fmaf(h.b1, cc, fmaf(-h.a1, v0, s2b));
+      s2b = fmaf(h.b2, cc, -h.a2 * v0);
       const float z = fminf(fmaxf(v0, -1.f), 1.f);
       if (t_begin + c0 + i >= t_acc) acc = fmaf(z, z, acc);
     }
