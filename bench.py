@@ -282,6 +282,53 @@ def run_reference_arm(args, w, wname):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def measure_preprocess_flow(pre, samples, sample_offsets, d_packed, phone_offsets, sr, hop, device, steps=4):
+    """The whole numeric flow behind `everyvoice preprocess` for one batch, host to host, every step:
+    loaded float32 waveforms (pinned host) -> process_audio (gates, loudness, peak normalisation, truncation, PCM16)
+    -> process_spec -> process_energy (phone-level) -> compute_stats / normalize_stats -> log-spectrogram, energy and
+    normalised phone values back in pinned host memory.  An extra, informative key of the bench line (N = 1 only)."""
+    import torch
+
+    n = len(sample_offsets) - 1
+    host_all = torch.empty(int(sample_offsets[-1]), dtype=torch.float32).pin_memory()
+    host_all.copy_(samples)
+    host_list = [host_all[int(sample_offsets[b]):int(sample_offsets[b + 1])] for b in range(n)]
+    durs = torch.from_numpy(d_packed.astype(np.int64)).to(device)
+    out = {}
+
+    def step():
+        audio = pre.process_audio_batch(host_list, sr, resample_rate=sr, hop_size=hop, out_dtype=torch.int16)
+        feats = pre.process_spec_batch(audio.samples, audio.offsets)
+        if len(audio.kept) == n:
+            phone, p_off = pre.process_energy_batch(feats, durs, phone_offsets)
+        else:  # a gate dropped something: frame-level energy keeps the step well defined
+            phone, p_off = pre.process_energy_batch(feats)
+        e_scaler, _ = pre.compute_stats(energy=phone, n_energy_files=len(audio.kept))
+        stats = pre.normalize_stats(e_scaler, None, distributed=False)
+        if "spec" not in out:
+            out["spec"] = torch.empty(tuple(feats.spec.shape), dtype=torch.float32).pin_memory()
+            out["energy"] = torch.empty(tuple(feats.energy.shape), dtype=torch.float32).pin_memory()
+            out["phone"] = torch.empty(tuple(phone.shape), dtype=torch.float32).pin_memory()
+        out["spec"].copy_(feats.spec, non_blocking=True)
+        out["energy"].copy_(feats.energy, non_blocking=True)
+        out["phone"].copy_(phone, non_blocking=True)
+        torch.cuda.synchronize(device)
+        out["kept"], out["mean"] = len(audio.kept), stats["energy"]["mean"]
+
+    for _ in range(2):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    audio_s = float(sample_offsets[-1]) / sr
+    return {"value": audio_s / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "utterances_kept": out["kept"],
+            "h2d_bytes_per_step": int(sample_offsets[-1]) * 4,
+            "d2h_bytes_per_step": int(out["spec"].numel() + out["energy"].numel() + out["phone"].numel()) * 4,
+            "api": "process_audio_batch -> process_spec_batch -> process_energy_batch -> compute_stats -> "
+                   "normalize_stats, host float32 waveforms in, host log-mel / energy / phone values out"}
+
+
 def run_ours(args, w, wname):
     import torch
     import torch.distributed as dist
@@ -482,6 +529,13 @@ def run_ours(args, w, wname):
         e2e_f32, e2e_steps, info_f32 = e2e_measure(torch.float32)
         e2e_s16, _, info_s16 = e2e_measure(torch.int16)
 
+    flow = None
+    if world == 1 and e2e_ok and spec_type in ("mel", "mel-librosa") and not corpus:
+        try:
+            flow = measure_preprocess_flow(pre, samples, sample_offsets, d_packed, phone_offsets, sr, hop, device)
+        except Exception as e:  # informative extra: never costs the bench line
+            flow = {"error": repr(e)[:300]}
+
     if rank == 0:
         bpf = algorithmic_bytes_per_frame(spec_type, hop, n_mels, n_fft)
         peaks_path = ROOT / "MEASURED_PEAKS.json"
@@ -529,6 +583,7 @@ def run_ours(args, w, wname):
                                     "d2h_bytes_per_step": int(info_s16["d2h"]),
                                     "note": "same call fed int16 PCM (the on-disk format process_audio writes); "
                                             "converted in the kernel, bit-identical to float input"}},
+            "preprocess_flow": flow,
             "gpu_launches": launches,
             "clocks": clock_info,
         }
