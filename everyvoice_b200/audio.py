@@ -120,6 +120,19 @@ def loudness_batch(samples: torch.Tensor, offsets, sample_rate: int) -> torch.Te
     return out
 
 
+def _consecutive_views(waves) -> bool:
+    """True if the 1-D float32 CPU tensors are contiguous views that follow one another in ONE storage."""
+    if not waves or any(w.device.type != "cpu" or w.dtype != torch.float32 or not w.is_contiguous() for w in waves):
+        return False
+    base = waves[0].untyped_storage().data_ptr()
+    nxt = waves[0].storage_offset()
+    for w in waves:
+        if w.untyped_storage().data_ptr() != base or w.storage_offset() != nxt:
+            return False
+        nxt += w.numel()
+    return True
+
+
 class AudioFrontEnd:
     """Batched ``process_audio``.  One instance per (device, audio config); resamplers are cached per rate pair."""
 
@@ -181,8 +194,14 @@ class AudioFrontEnd:
         off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
         # one device buffer, one asynchronous copy per utterance (pinned host tensors overlap; no host-side concat)
         x = torch.empty(int(off[-1]), dtype=torch.float32, device=dev)
-        for j, w in enumerate(waves):
-            x[int(off[j]) : int(off[j + 1])].copy_(w, non_blocking=True)
+        if _consecutive_views(waves):
+            # the utterances already sit back to back in one host buffer (e.g. a memory-mapped corpus): one copy
+            whole = torch.empty(0, dtype=torch.float32).set_(waves[0].untyped_storage(), waves[0].storage_offset(),
+                                                              (int(off[-1]),))
+            x.copy_(whole, non_blocking=True)
+        else:
+            for j, w in enumerate(waves):
+                x[int(off[j]) : int(off[j + 1])].copy_(w, non_blocking=True)
         # ---- loudness gate (:177-186) -----------------------------------------------------------
         lk = loudness_batch(x, off, sr).cpu().numpy()
         loud[cand] = lk
