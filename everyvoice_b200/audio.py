@@ -98,8 +98,17 @@ class Resampler:
         return out, out_off
 
 
+def _fmt(t: torch.Tensor) -> int:
+    if t.dtype == torch.int16:
+        return _lib.SAMPLES_S16
+    if t.dtype == torch.float32:
+        return _lib.SAMPLES_F32
+    raise ValueError("samples must be float32 or int16 PCM")
+
+
 def loudness_batch(samples: torch.Tensor, offsets, sample_rate: int) -> torch.Tensor:
-    """``torchaudio.transforms.Loudness(sr)`` of every mono utterance of a packed float32 device batch."""
+    """``torchaudio.transforms.Loudness(sr)`` of every mono utterance of a packed float32 / int16 PCM device batch
+    (int16 is ``s / 32768``, what ``torchaudio.load`` returns for a PCM16 wav)."""
     lib = _lib.load()
     device = samples.device
     offsets = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
@@ -114,15 +123,16 @@ def loudness_batch(samples: torch.Tensor, offsets, sample_rate: int) -> torch.Te
     out = torch.empty(len(lens), dtype=torch.float32, device=device)
     d_off, d_soff = torch.from_numpy(offsets).to(device), torch.from_numpy(s_off).to(device)
     with torch.cuda.device(device):
-        _lib.check(lib.evf_audio_loudness(_ptr(samples), _ptr(d_off), len(lens), int(lens.max()) if len(lens) else 0,
+        _lib.check(lib.evf_audio_loudness(_ptr(samples), _fmt(samples), _ptr(d_off), len(lens),
+                                          int(lens.max()) if len(lens) else 0,
                                           int(sample_rate), _ptr(scratch),
                                           _ptr(d_soff), _ptr(out), _stream_ptr(device)))
     return out
 
 
 def _consecutive_views(waves) -> bool:
-    """True if the 1-D float32 CPU tensors are contiguous views that follow one another in ONE storage."""
-    if not waves or any(w.device.type != "cpu" or w.dtype != torch.float32 or not w.is_contiguous() for w in waves):
+    """True if the 1-D CPU tensors (one dtype) are contiguous views that follow one another in ONE storage."""
+    if not waves or any(w.device.type != "cpu" or w.dtype != waves[0].dtype or not w.is_contiguous() for w in waves):
         return False
     base = waves[0].untyped_storage().data_ptr()
     nxt = waves[0].storage_offset()
@@ -152,7 +162,9 @@ class AudioFrontEnd:
     def process_audio_batch(self, audios, sr: int, normalize=True, resample_rate=None, hop_size=None,
                             out_dtype=torch.float32, update_counters=True, names=None) -> ProcessedAudio:
         """``audios``: list of ``[L]`` / ``[C, L]`` float32 tensors or arrays as ``load_audio`` returns them, all at
-        sampling rate ``sr``.  Mirrors process_audio's order of gates and operations (preprocessor.py:148-218)."""
+        sampling rate ``sr`` -- or, all of them, the int16 PCM samples of the wav files themselves (converted on the
+        device as ``s / 32768``, bit-identical to loading them as float; half the host-to-device bytes).  Mirrors
+        process_audio's order of gates and operations (preprocessor.py:148-218)."""
         if hop_size is None:
             raise ValueError(
                 "We must know the hop size for processing audio because EveryVoice enforces that the number of "
@@ -184,7 +196,7 @@ class AudioFrontEnd:
                 raise NotImplementedError("process_audio_batch handles mono input; downmix stereo first "
                                           "(the reference does it through its sox effects)")
             cand.append(i)
-            waves.append(t[0].to(torch.float32))
+            waves.append(t[0] if t.dtype == torch.int16 else t[0].to(torch.float32))
         loud = np.full(len(audios), np.nan, dtype=np.float32)
         if not cand:
             self._count(skipped, 0.0, 0, update_counters)
@@ -193,11 +205,14 @@ class AudioFrontEnd:
         lens = np.array([w.numel() for w in waves], dtype=np.int64)
         off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
         # one device buffer, one asynchronous copy per utterance (pinned host tensors overlap; no host-side concat)
-        x = torch.empty(int(off[-1]), dtype=torch.float32, device=dev)
+        in_dtype = torch.int16 if all(w.dtype == torch.int16 for w in waves) else torch.float32
+        if in_dtype == torch.float32:
+            waves = [w.to(torch.float32) for w in waves]
+        x = torch.empty(int(off[-1]), dtype=in_dtype, device=dev)
         if _consecutive_views(waves):
             # the utterances already sit back to back in one host buffer (e.g. a memory-mapped corpus): one copy
-            whole = torch.empty(0, dtype=torch.float32).set_(waves[0].untyped_storage(), waves[0].storage_offset(),
-                                                              (int(off[-1]),))
+            whole = torch.empty(0, dtype=in_dtype).set_(waves[0].untyped_storage(), waves[0].storage_offset(),
+                                                         (int(off[-1]),))
             x.copy_(whole, non_blocking=True)
         else:
             for j, w in enumerate(waves):
@@ -221,7 +236,7 @@ class AudioFrontEnd:
         if normalize:
             absmax = torch.empty(len(cand), dtype=torch.float32, device=dev)
             with torch.cuda.device(dev):
-                _lib.check(lib.evf_audio_absmax(_ptr(x), _ptr(d_off), len(cand), int(full.max()), _ptr(absmax),
+                _lib.check(lib.evf_audio_absmax(_ptr(x), _fmt(x), _ptr(d_off), len(cand), int(full.max()), _ptr(absmax),
                                                 _stream_ptr(dev)))
         kept_len = np.where(ok, (full // int(hop_size)) * int(hop_size), 0).astype(np.int64)
         dst = np.concatenate([[0], np.cumsum(kept_len)]).astype(np.int64)
@@ -229,7 +244,7 @@ class AudioFrontEnd:
         out = torch.empty(int(dst[-1]), dtype=out_dtype, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.evf_audio_finalize(
-                _ptr(x), _ptr(d_off), _ptr(d_dst), len(cand), int(kept_len.max()), _ptr(absmax),
+                _ptr(x), _fmt(x), _ptr(d_off), _ptr(d_dst), len(cand), int(kept_len.max()), _ptr(absmax),
                 _ptr(out) if out_dtype == torch.float32 else None, _ptr(out) if out_dtype == torch.int16 else None,
                 _stream_ptr(dev)))
         kept = [i for j, i in enumerate(cand) if ok[j]]

@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(kRsThreads) resample_small_kernel(const Sample
 // max |x| per utterance (NaN-propagating like torch.max(torch.abs(.)): a NaN sample yields NaN).  A block owns 2048
 // consecutive samples of one utterance; the 8 loads of a thread are independent (64 KB in flight per SM).
 constexpr int kStreamItems = 8;
-__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, const long long* __restrict__ off,
+template <typename SampleT>
+__global__ void __launch_bounds__(256) absmax_kernel(const SampleT* __restrict__ x, const long long* __restrict__ off,
                                                      unsigned* __restrict__ out_bits) {
   const int b = blockIdx.y;
   const long long o0 = off[b], L = off[b + 1] - o0;
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
 #pragma unroll
   for (int i = 0; i < kStreamItems; ++i) {
     const long long j = j0 + i * 256;
-    v[i] = (j < L) ? fabsf(__ldg(x + o0 + j)) : 0.f;
+    v[i] = (j < L) ? fabsf(sample_to_float(__ldg(x + o0 + j))) : 0.f;
   }
   float m = 0.f;
   bool nan = false;
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
 
 // out = (x / max) * 0.95 (two roundings, exactly `audio /= max; audio *= 0.95` in fp32), truncated to the kept
 // length, as float32 and / or PCM16 (round to nearest even of x * 32768, clipped: ffmpeg swresample flt -> s16)
-__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ x,
+template <typename SampleT>
+__global__ void __launch_bounds__(256) finalize_kernel(const SampleT* __restrict__ x,
                                                        const long long* __restrict__ src_off,
                                                        const long long* __restrict__ dst_off,
                                                        const float* __restrict__ absmax, float* __restrict__ out_f32,
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__
 #pragma unroll
   for (int i = 0; i < kStreamItems; ++i) {
     const long long j = j0 + i * 256;
-    v[i] = (j < n) ? __ldg(x + s0 + j) : 0.f;
+    v[i] = (j < n) ? sample_to_float(__ldg(x + s0 + j)) : 0.f;
   }
 #pragma unroll
   for (int i = 0; i < kStreamItems; ++i) {
@@ -212,13 +214,14 @@ struct LoudnessParams {
 // A block is ONE warp owning 32 consecutive steps; the 32 sample streams advance together in tiles of 64 samples
 // that the warp loads row by row (coalesced) into a padded shared-memory tile and each lane then reads along its row.
 constexpr int kLdTile = 64;
-__global__ void __launch_bounds__(32) loudness_partial_kernel(const float* __restrict__ x,
+template <typename SampleT>
+__global__ void __launch_bounds__(32) loudness_partial_kernel(const SampleT* __restrict__ x,
                                                               const long long* __restrict__ off, LoudnessParams P,
                                                               float* __restrict__ scratch,
                                                               const long long* __restrict__ scratch_off) {
   __shared__ float tile[32][kLdTile + 1];
   const int b = blockIdx.y;
-  const float* xs = x + off[b];
+  const SampleT* xs = x + off[b];
   const long long L = off[b + 1] - off[b];
   const long long n_sub = L / P.step;
   const long long q0 = (long long)blockIdx.x * 32;
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(32) loudness_partial_kernel(const float* __res
 #pragma unroll
       for (int hh = 0; hh < kLdTile / 32; ++hh) {
         const long long t = tb + 32 * hh + lane;
-        v[r][hh] = (t >= 0 && t < L) ? __ldg(xs + t) : 0.f;
+        v[r][hh] = (t >= 0 && t < L) ? sample_to_float(__ldg(xs + t)) : 0.f;
       }
     }
   };
@@ -508,9 +511,10 @@ int evf_audio_resample(const evf_resampler* r, const void* in_dev, int32_t in_fo
   return EVF_OK;
 }
 
-int evf_audio_absmax(const float* x_dev, const int64_t* offsets_dev, int32_t n_utts, int64_t max_len,
+int evf_audio_absmax(const void* x_dev, int32_t x_format, const int64_t* offsets_dev, int32_t n_utts, int64_t max_len,
                      float* absmax_dev, void* stream) {
-  if (n_utts < 0 || max_len < 0 || (n_utts > 0 && (!x_dev || !offsets_dev || !absmax_dev))) {
+  if (n_utts < 0 || max_len < 0 || (x_format != EVF_SAMPLES_F32 && x_format != EVF_SAMPLES_S16) ||
+      (n_utts > 0 && (!x_dev || !offsets_dev || !absmax_dev))) {
     set_error("evf_audio_absmax: invalid argument");
     return EVF_ERR_INVALID_ARGUMENT;
   }
@@ -519,16 +523,21 @@ int evf_audio_absmax(const float* x_dev, const int64_t* offsets_dev, int32_t n_u
   EVF_CUDA(cudaMemsetAsync(absmax_dev, 0, (size_t)n_utts * sizeof(float), st));
   if (max_len == 0) return EVF_OK;
   const long long gx = (max_len + 256 * kStreamItems - 1) / (256 * kStreamItems);
-  absmax_kernel<<<dim3((unsigned)gx, (unsigned)n_utts), 256, 0, st>>>(
-      x_dev, reinterpret_cast<const long long*>(offsets_dev), reinterpret_cast<unsigned*>(absmax_dev));
+  const dim3 grid((unsigned)gx, (unsigned)n_utts);
+  const long long* off = reinterpret_cast<const long long*>(offsets_dev);
+  unsigned* out = reinterpret_cast<unsigned*>(absmax_dev);
+  if (x_format == EVF_SAMPLES_S16)
+    absmax_kernel<short><<<grid, 256, 0, st>>>(static_cast<const short*>(x_dev), off, out);
+  else
+    absmax_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x_dev), off, out);
   EVF_CUDA(cudaGetLastError());
   return EVF_OK;
 }
 
-int evf_audio_finalize(const float* x_dev, const int64_t* src_offsets_dev, const int64_t* dst_offsets_dev,
-                       int32_t n_utts, int64_t max_kept_len, const float* absmax_dev, float* out_f32_dev,
-                       int16_t* out_s16_dev, void* stream) {
-  if (n_utts < 0 || max_kept_len < 0) {
+int evf_audio_finalize(const void* x_dev, int32_t x_format, const int64_t* src_offsets_dev,
+                       const int64_t* dst_offsets_dev, int32_t n_utts, int64_t max_kept_len, const float* absmax_dev,
+                       float* out_f32_dev, int16_t* out_s16_dev, void* stream) {
+  if (n_utts < 0 || max_kept_len < 0 || (x_format != EVF_SAMPLES_F32 && x_format != EVF_SAMPLES_S16)) {
     set_error("evf_audio_finalize: invalid argument");
     return EVF_ERR_INVALID_ARGUMENT;
   }
@@ -538,9 +547,15 @@ int evf_audio_finalize(const float* x_dev, const int64_t* src_offsets_dev, const
     return EVF_ERR_INVALID_ARGUMENT;
   }
   const long long gx = (max_kept_len + 256 * kStreamItems - 1) / (256 * kStreamItems);
-  finalize_kernel<<<dim3((unsigned)gx, (unsigned)n_utts), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x_dev, reinterpret_cast<const long long*>(src_offsets_dev), reinterpret_cast<const long long*>(dst_offsets_dev),
-      absmax_dev, out_f32_dev, reinterpret_cast<short*>(out_s16_dev));
+  const dim3 grid((unsigned)gx, (unsigned)n_utts);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long* so = reinterpret_cast<const long long*>(src_offsets_dev);
+  const long long* dd = reinterpret_cast<const long long*>(dst_offsets_dev);
+  short* o16 = reinterpret_cast<short*>(out_s16_dev);
+  if (x_format == EVF_SAMPLES_S16)
+    finalize_kernel<short><<<grid, 256, 0, st>>>(static_cast<const short*>(x_dev), so, dd, absmax_dev, out_f32_dev, o16);
+  else
+    finalize_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x_dev), so, dd, absmax_dev, out_f32_dev, o16);
   EVF_CUDA(cudaGetLastError());
   return EVF_OK;
 }
@@ -553,10 +568,10 @@ int64_t evf_audio_loudness_scratch_floats(int32_t sample_rate, int64_t n_samples
   return n_samples / step + 4;  // one partial sum per 100 ms step; the block energies read up to 3 past their index
 }
 
-int evf_audio_loudness(const float* x_dev, const int64_t* offsets_dev, int32_t n_utts, int64_t max_len,
-                       int32_t sample_rate, float* scratch_dev, const int64_t* scratch_offsets_dev, float* lkfs_dev,
-                       void* stream) {
-  if (n_utts < 0 || sample_rate < 1 || max_len < 0 || (n_utts > 0 && (!x_dev || !offsets_dev || !scratch_dev || !scratch_offsets_dev || !lkfs_dev))) {
+int evf_audio_loudness(const void* x_dev, int32_t x_format, const int64_t* offsets_dev, int32_t n_utts,
+                       int64_t max_len, int32_t sample_rate, float* scratch_dev, const int64_t* scratch_offsets_dev,
+                       float* lkfs_dev, void* stream) {
+  if (n_utts < 0 || sample_rate < 1 || max_len < 0 || (x_format != EVF_SAMPLES_F32 && x_format != EVF_SAMPLES_S16) || (n_utts > 0 && (!x_dev || !offsets_dev || !scratch_dev || !scratch_offsets_dev || !lkfs_dev))) {
     set_error("evf_audio_loudness: invalid argument");
     return EVF_ERR_INVALID_ARGUMENT;
   }
@@ -576,8 +591,11 @@ int evf_audio_loudness(const float* x_dev, const int64_t* offsets_dev, int32_t n
   const long long* soff = reinterpret_cast<const long long*>(scratch_offsets_dev);
   const long long max_sub = max_len / P.step;
   if (max_sub > 0) {
-    loudness_partial_kernel<<<dim3((unsigned)((max_sub + 31) / 32), (unsigned)n_utts), 32, 0, st>>>(
-        x_dev, off, P, scratch_dev, soff);
+    const dim3 grid((unsigned)((max_sub + 31) / 32), (unsigned)n_utts);
+    if (x_format == EVF_SAMPLES_S16)
+      loudness_partial_kernel<short><<<grid, 32, 0, st>>>(static_cast<const short*>(x_dev), off, P, scratch_dev, soff);
+    else
+      loudness_partial_kernel<float><<<grid, 32, 0, st>>>(static_cast<const float*>(x_dev), off, P, scratch_dev, soff);
     EVF_CUDA(cudaGetLastError());
   }
   loudness_gate_kernel<<<(n_utts + 63) / 64, 64, 0, st>>>(off, n_utts, P, scratch_dev, soff, lkfs_dev);

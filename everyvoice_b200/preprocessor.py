@@ -106,14 +106,14 @@ class Preprocessor:
             sr, ch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
             raw = w.readframes(n)
         if width == 2:
-            a = np.frombuffer(raw, dtype="<i2").astype(np.float32) / 32768.0
+            a = np.frombuffer(raw, dtype="<i2").copy()  # stays int16: converted on the device as s / 32768 (torchaudio.load)
         elif width == 4:
             a = (np.frombuffer(raw, dtype="<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
         elif width == 1:
             a = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
         else:
             raise ValueError(f"unsupported PCM sample width {width}")
-        audio = torch.from_numpy(np.ascontiguousarray(a.reshape(-1, ch).T))
+        audio = torch.from_numpy(np.ascontiguousarray(a.reshape(-1, ch).T))  # [C, L]
         res = self.process_audio_batch([audio], sr, normalize, resample_rate, hop_size, torch.float32,
                                        update_counters, [wav_path])
         if not res.kept:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define EVF_ABI_VERSION 6
+#define EVF_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define EVF_API __attribute__((visibility("default")))
@@ -208,7 +208,8 @@ EVF_API int evf_log_compress_backward(const float* in_dev, const float* grad_out
 
 /* ---- audio front-end: the numerics of Preprocessor.process_audio ----------------
  * everyvoice/preprocessor/preprocessor.py:131-218.  Ragged batches: utterance b owns [offsets[b], offsets[b+1])
- * of a packed buffer; every offsets array has n_utts + 1 entries. */
+ * of a packed buffer; every offsets array has n_utts + 1 entries.  `x_dev` buffers are float32 or int16 PCM
+ * (`x_format`, evf_sample_format; int16 is s / 32768 like torchaudio.load of a PCM16 wav). */
 typedef struct evf_resampler evf_resampler;
 
 /* torchaudio.functional.resample(audio, orig_freq, new_freq) as process_audio calls it (preprocessor.py:196-198):
@@ -226,24 +227,24 @@ EVF_API int evf_audio_resample(const evf_resampler* resampler, const void* in_de
                                const int64_t* in_offsets_dev, const int64_t* out_offsets_dev, int32_t n_utts,
                                int64_t max_out_len, float* out_dev, void* stream);
 /* absmax_dev[b] = max |x| of utterance b (NaN if it holds a NaN): torch.max(torch.abs(audio)), preprocessor.py:200 */
-EVF_API int evf_audio_absmax(const float* x_dev, const int64_t* offsets_dev, int32_t n_utts, int64_t max_len,
-                             float* absmax_dev, void* stream);
+EVF_API int evf_audio_absmax(const void* x_dev, int32_t x_format, const int64_t* offsets_dev, int32_t n_utts,
+                             int64_t max_len, float* absmax_dev, void* stream);
 /* Peak normalisation + truncation + output format in one pass (preprocessor.py:199-201, 216-218; helpers.py:31-44):
  * for j < dst length: v = x[src_offsets[b] + j]; if absmax_dev: v = (v / absmax[b]) * 0.95f (two roundings, as the
  * reference's two in-place ops); written as float32 (out_f32_dev) and / or PCM16 (out_s16_dev: round-half-even of
  * v * 32768, clipped) at dst_offsets[b] + j.  dst lengths are the kept lengths (L // hop) * hop <= src lengths. */
-EVF_API int evf_audio_finalize(const float* x_dev, const int64_t* src_offsets_dev, const int64_t* dst_offsets_dev,
-                               int32_t n_utts, int64_t max_kept_len, const float* absmax_dev, float* out_f32_dev,
-                               int16_t* out_s16_dev, void* stream);
+EVF_API int evf_audio_finalize(const void* x_dev, int32_t x_format, const int64_t* src_offsets_dev,
+                               const int64_t* dst_offsets_dev, int32_t n_utts, int64_t max_kept_len,
+                               const float* absmax_dev, float* out_f32_dev, int16_t* out_s16_dev, void* stream);
 /* torchaudio.transforms.Loudness(sr)(audio) for mono utterances (preprocessor.py:177-186: skipped when NaN or
  * < -36): ITU-R BS.1770-4 K-weighting, 400 ms blocks with 75 % overlap, absolute (-70) and relative (-10) gates.
  * scratch_dev: float32, evf_audio_loudness_scratch_floats(sr, L_b) entries per utterance at scratch_offsets_dev;
  * max_len = the longest utterance (grid sizing).  The filters' recursion is restarted every 100 ms with a 100 ms
  * run-in (state error < 1e-7 relative), so all steps of all utterances run in parallel. */
 EVF_API int64_t evf_audio_loudness_scratch_floats(int32_t sample_rate, int64_t n_samples);
-EVF_API int evf_audio_loudness(const float* x_dev, const int64_t* offsets_dev, int32_t n_utts, int64_t max_len,
-                               int32_t sample_rate, float* scratch_dev, const int64_t* scratch_offsets_dev,
-                               float* lkfs_dev, void* stream);
+EVF_API int evf_audio_loudness(const void* x_dev, int32_t x_format, const int64_t* offsets_dev, int32_t n_utts,
+                               int64_t max_len, int32_t sample_rate, float* scratch_dev,
+                               const int64_t* scratch_offsets_dev, float* lkfs_dev, void* stream);
 
 #ifdef __cplusplus
 }

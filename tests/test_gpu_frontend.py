@@ -184,3 +184,30 @@ def test_pitch_postprocessing_bit_exact_and_variance_flow(cuda_device, golden_di
     assert stats["sample_size"] == ref["sample_size"] == len(names)
     for k in ("min", "max", "mean", "std"):
         assert stats[k] == pytest.approx(ref[k], rel=1e-5), k
+
+
+def test_int16_waveforms_equal_float_waveforms_bitwise(cuda_device):
+    """The PCM16 samples of the wav files themselves can be handed over: s / 32768 happens on the device, every
+    kernel of the front-end (loudness, resampling, peak, finalisation) gives the bits of the float path."""
+    from everyvoice_b200 import synth
+    from oracle import ev_oracle as O
+
+    pre = _pre(cuda_device)
+    pcm = [O.pcm16(synth.speech_like(int(44100 * s) + 5, 44100, seed=120 + i) * np.float32(g))
+           for i, (s, g) in enumerate(((0.7, 0.5), (1.3, 0.9), (0.5, 0.003), (0.9, 0.2)))]
+    as_f32 = [torch.from_numpy(p.astype(np.float32) / 32768.0) for p in pcm]
+    as_i16 = [torch.from_numpy(p) for p in pcm]
+    for rs in (22050, 44100):
+        for out_dtype in (torch.float32, torch.int16):
+            a = pre.process_audio_batch(as_f32, 44100, resample_rate=rs, hop_size=256, out_dtype=out_dtype)
+            b = pre.process_audio_batch(as_i16, 44100, resample_rate=rs, hop_size=256, out_dtype=out_dtype)
+            assert a.kept == b.kept == [0, 1, 3] and a.skipped == b.skipped == {2: "audio_empty"}
+            assert np.array_equal(a.offsets, b.offsets) and torch.equal(a.samples, b.samples)
+            assert np.array_equal(a.loudness, b.loudness, equal_nan=True)
+    # consecutive views of one int16 host buffer take the single-copy path
+    buf = torch.from_numpy(np.concatenate(pcm))
+    cuts = np.concatenate([[0], np.cumsum([len(p) for p in pcm])])
+    views = [buf[int(cuts[i]):int(cuts[i + 1])] for i in range(len(pcm))]
+    c = pre.process_audio_batch(views, 44100, resample_rate=22050, hop_size=256, out_dtype=torch.int16)
+    d = pre.process_audio_batch(as_i16, 44100, resample_rate=22050, hop_size=256, out_dtype=torch.int16)
+    assert torch.equal(c.samples, d.samples)

@@ -70,7 +70,7 @@ def main():
     scratch = torch.empty(int(s_off[-1]), dtype=torch.float32, device=dev)
     lk = torch.empty(n, dtype=torch.float32, device=dev)
     rec("loudness (partial + gate)",
-        timed(lambda: _lib.check(lib.evf_audio_loudness(_ptr(x), _ptr(d_off), n, int(lens.max()), sr_in, _ptr(scratch),
+        timed(lambda: _lib.check(lib.evf_audio_loudness(_ptr(x), _lib.SAMPLES_F32, _ptr(d_off), n, int(lens.max()), sr_in, _ptr(scratch),
                                                         _ptr(d_soff), _ptr(lk), st))), 4 * int(off[-1]))
     rs = ev.Resampler(sr_in, sr_out, dev)
     y, y_off = rs(x, off)
@@ -79,14 +79,14 @@ def main():
         4 * int(off[-1]) + 4 * int(y_off[-1]))
     full = np.diff(y_off)
     absmax = torch.empty(n, dtype=torch.float32, device=dev)
-    rec("absmax", timed(lambda: _lib.check(lib.evf_audio_absmax(_ptr(y), _ptr(d_yoff), n, int(full.max()), _ptr(absmax), st))),
+    rec("absmax", timed(lambda: _lib.check(lib.evf_audio_absmax(_ptr(y), _lib.SAMPLES_F32, _ptr(d_yoff), n, int(full.max()), _ptr(absmax), st))),
         4 * int(y_off[-1]))
     kept = (full // hop) * hop
     dst = np.concatenate([[0], np.cumsum(kept)]).astype(np.int64)
     d_dst = torch.from_numpy(dst).to(dev)
     o16 = torch.empty(int(dst[-1]), dtype=torch.int16, device=dev)
     rec("finalize (normalise + truncate + PCM16)",
-        timed(lambda: _lib.check(lib.evf_audio_finalize(_ptr(y), _ptr(d_yoff), _ptr(d_dst), n, int(kept.max()), _ptr(absmax),
+        timed(lambda: _lib.check(lib.evf_audio_finalize(_ptr(y), _lib.SAMPLES_F32, _ptr(d_yoff), _ptr(d_dst), n, int(kept.max()), _ptr(absmax),
                                                         None, _ptr(o16), st))), 6 * int(dst[-1]))
     total_ms = sum(k["ms"] for k in out["kernels"].values())
     out["device_total_ms"] = total_ms
