@@ -282,7 +282,8 @@ def run_reference_arm(args, w, wname):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def measure_preprocess_flow(pre, samples, sample_offsets, d_packed, phone_offsets, sr, hop, device, steps=4):
+def measure_preprocess_flow(pre, samples, sample_offsets, d_packed, phone_offsets, sr, hop, device, steps=4,
+                            pcm16=False):
     """The whole numeric flow behind `everyvoice preprocess` for one batch, host to host, every step:
     loaded float32 waveforms (pinned host) -> process_audio (gates, loudness, peak normalisation, truncation, PCM16)
     -> process_spec -> process_energy (phone-level) -> compute_stats / normalize_stats -> log-spectrogram, energy and
@@ -290,8 +291,12 @@ def measure_preprocess_flow(pre, samples, sample_offsets, d_packed, phone_offset
     import torch
 
     n = len(sample_offsets) - 1
-    host_all = torch.empty(int(sample_offsets[-1]), dtype=torch.float32).pin_memory()
-    host_all.copy_(samples)
+    if pcm16:  # the wav files' own samples
+        host_all = torch.empty(int(sample_offsets[-1]), dtype=torch.int16).pin_memory()
+        host_all.copy_((samples * 32767.0).round().to(torch.int16))
+    else:      # what load_audio returns
+        host_all = torch.empty(int(sample_offsets[-1]), dtype=torch.float32).pin_memory()
+        host_all.copy_(samples)
     host_list = [host_all[int(sample_offsets[b]):int(sample_offsets[b + 1])] for b in range(n)]
     durs = torch.from_numpy(d_packed.astype(np.int64)).to(device)
     out = {}
@@ -323,7 +328,7 @@ def measure_preprocess_flow(pre, samples, sample_offsets, d_packed, phone_offset
     dt = (time.perf_counter() - t0) / steps
     audio_s = float(sample_offsets[-1]) / sr
     return {"value": audio_s / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "utterances_kept": out["kept"],
-            "h2d_bytes_per_step": int(sample_offsets[-1]) * 4,
+            "h2d_bytes_per_step": int(sample_offsets[-1]) * (2 if pcm16 else 4),
             "d2h_bytes_per_step": int(out["spec"].numel() + out["energy"].numel() + out["phone"].numel()) * 4,
             "api": "process_audio_batch -> process_spec_batch -> process_energy_batch -> compute_stats -> "
                    "normalize_stats, host float32 waveforms in, host log-mel / energy / phone values out"}
@@ -533,6 +538,9 @@ def run_ours(args, w, wname):
     if world == 1 and e2e_ok and spec_type in ("mel", "mel-librosa") and not corpus:
         try:
             flow = measure_preprocess_flow(pre, samples, sample_offsets, d_packed, phone_offsets, sr, hop, device)
+            f16 = measure_preprocess_flow(pre, samples, sample_offsets, d_packed, phone_offsets, sr, hop, device,
+                                          pcm16=True)
+            flow["pcm16_input"] = {k: f16[k] for k in ("value", "unit", "ms_per_step", "h2d_bytes_per_step")}
         except Exception as e:  # informative extra: never costs the bench line
             flow = {"error": repr(e)[:300]}
 
