@@ -113,10 +113,9 @@ def loudness_batch(samples: torch.Tensor, offsets, sample_rate: int) -> torch.Te
     device = samples.device
     offsets = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
     lens = np.diff(offsets)
-    one = int(lib.evf_audio_loudness_scratch_floats(int(sample_rate), int(sample_rate)))  # floats per second + 4
-    if one < 0:
+    step = int(lib.evf_audio_loudness_step(int(sample_rate)))   # the 100 ms step in samples, as the library rounds it
+    if step < 1:
         raise ValueError("unsupported sampling rate for the loudness measurement")
-    step = int(sample_rate) // (one - 4)  # the 100 ms step in samples
     per = lens // step + 4                # == evf_audio_loudness_scratch_floats(sr, n) for every n
     s_off = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
     scratch = torch.empty(int(s_off[-1]), dtype=torch.float32, device=device)
@@ -206,8 +205,8 @@ class AudioFrontEnd:
         off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
         # one device buffer, one asynchronous copy per utterance (pinned host tensors overlap; no host-side concat)
         in_dtype = torch.int16 if all(w.dtype == torch.int16 for w in waves) else torch.float32
-        if in_dtype == torch.float32:
-            waves = [w.to(torch.float32) for w in waves]
+        if in_dtype == torch.float32:  # a mixed batch: PCM promoted to float is s / 32768 (torchaudio.load), not the integer
+            waves = [w.to(torch.float32) * (1.0 / 32768.0) if w.dtype == torch.int16 else w for w in waves]
         x = torch.empty(int(off[-1]), dtype=in_dtype, device=dev)
         if _consecutive_views(waves):
             # the utterances already sit back to back in one host buffer (e.g. a memory-mapped corpus): one copy

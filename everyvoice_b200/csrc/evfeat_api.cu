@@ -272,14 +272,8 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   p->cfg = *cfg;
   p->device = device;
   p->mode = (cfg->n_fft == 1024) ? MODE_PACK2 : MODE_HALF;
-  if (p->mode == MODE_PACK2) {
-    // A/B switch (tools/kbench.py, tests): the packed two-jobs-per-warp kernel computes the same bits
-    // (evfeat_features_x2.cu; not the default, DESIGN.md section 4.1 has the counters)
-    const char* v = std::getenv("EVF_FEATURES_VARIANT");
-    if (v && std::strcmp(v, "x2") == 0) p->mode = MODE_PACK2X2;
-  }
   p->n_freq = cfg->n_fft / 2 + 1;
-  p->warps = (p->mode == MODE_PACK2X2) ? kX2Warps : kMaxWarps;  // one CTA per SM
+  p->warps = kMaxWarps;  // one CTA per SM
   p->frames_per_tile = (p->mode == MODE_HALF) ? p->warps : 32;     // 16 jobs of two frames (n_fft 1024)
   p->num_sms = prop.multiProcessorCount;
   p->row_floats = mel ? cfg->n_mels : (cfg->spec_type == EVF_SPEC_RAW ? 2 * p->n_freq : p->n_freq);

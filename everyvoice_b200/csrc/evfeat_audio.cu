@@ -35,6 +35,7 @@ __device__ __forceinline__ float sample_to_float(float v) { return v; }
 __device__ __forceinline__ float sample_to_float(short v) { return (float)v * (1.0f / 32768.0f); }
 
 constexpr int kRsThreads = 256;
+constexpr int kMaxGridY = 65535;  // gridDim.y limit: ragged (chunk, utterance) grids are launched in slices of utterances
 
 // y[j] = sum_k K[j % new][k] * xpad[(j / new) * orig + k],  xpad = x shifted by `width` zeros
 // (torchaudio _apply_sinc_resample_kernel: pad (width, width + orig), conv1d with stride orig, transpose, crop).
@@ -461,32 +462,38 @@ int evf_audio_resample(const evf_resampler* r, const void* in_dev, int32_t in_fo
   const bool s16 = (in_format == EVF_SAMPLES_S16);
   // register-window kernels for the two common ratios (lowpass_filter_width 6, rolloff 0.99: 28 resp. 15 taps)
   constexpr int R = 4;
-  auto small_grid = [&](int neu) {
+  auto small_grid = [&](int neu, int ny) {
     const long long blocks_in = (max_out_len + neu - 1) / neu;  // input blocks of the longest utterance
-    return dim3((unsigned)((blocks_in + (long long)R * kRsThreads - 1) / ((long long)R * kRsThreads)), (unsigned)n_utts);
+    return dim3((unsigned)((blocks_in + (long long)R * kRsThreads - 1) / ((long long)R * kRsThreads)), (unsigned)ny);
   };
   if (r->orig == 2 && r->neu == 1 && r->taps == 28) {
     SmallBank<28> bank;
     for (int i = 0; i < 28; ++i) bank.k[i] = r->h_kt[i];
-    if (s16)
-      resample_small_kernel<short, 2, 1, 28, R><<<small_grid(1), kRsThreads, 0, st>>>(
-          static_cast<const short*>(in_dev), io, oo, bank, r->width, out_dev);
-    else
-      resample_small_kernel<float, 2, 1, 28, R><<<small_grid(1), kRsThreads, 0, st>>>(
-          static_cast<const float*>(in_dev), io, oo, bank, r->width, out_dev);
-    EVF_CUDA(cudaGetLastError());
+    for (int y0 = 0; y0 < n_utts; y0 += kMaxGridY) {
+      const int ny = n_utts - y0 < kMaxGridY ? n_utts - y0 : kMaxGridY;
+      if (s16)
+        resample_small_kernel<short, 2, 1, 28, R><<<small_grid(1, ny), kRsThreads, 0, st>>>(
+            static_cast<const short*>(in_dev), io + y0, oo + y0, bank, r->width, out_dev);
+      else
+        resample_small_kernel<float, 2, 1, 28, R><<<small_grid(1, ny), kRsThreads, 0, st>>>(
+            static_cast<const float*>(in_dev), io + y0, oo + y0, bank, r->width, out_dev);
+      EVF_CUDA(cudaGetLastError());
+    }
     return EVF_OK;
   }
   if (r->orig == 1 && r->neu == 2 && r->taps == 15) {
     SmallBank<30> bank;
     for (int i = 0; i < 30; ++i) bank.k[i] = r->h_kt[i];
-    if (s16)
-      resample_small_kernel<short, 1, 2, 15, R><<<small_grid(2), kRsThreads, 0, st>>>(
-          static_cast<const short*>(in_dev), io, oo, bank, r->width, out_dev);
-    else
-      resample_small_kernel<float, 1, 2, 15, R><<<small_grid(2), kRsThreads, 0, st>>>(
-          static_cast<const float*>(in_dev), io, oo, bank, r->width, out_dev);
-    EVF_CUDA(cudaGetLastError());
+    for (int y0 = 0; y0 < n_utts; y0 += kMaxGridY) {
+      const int ny = n_utts - y0 < kMaxGridY ? n_utts - y0 : kMaxGridY;
+      if (s16)
+        resample_small_kernel<short, 1, 2, 15, R><<<small_grid(2, ny), kRsThreads, 0, st>>>(
+            static_cast<const short*>(in_dev), io + y0, oo + y0, bank, r->width, out_dev);
+      else
+        resample_small_kernel<float, 1, 2, 15, R><<<small_grid(2, ny), kRsThreads, 0, st>>>(
+            static_cast<const float*>(in_dev), io + y0, oo + y0, bank, r->width, out_dev);
+      EVF_CUDA(cudaGetLastError());
+    }
     return EVF_OK;
   }
   const int span = ((kRsThreads - 1) / r->neu + 2) * r->orig + r->taps;
@@ -495,19 +502,22 @@ int evf_audio_resample(const evf_resampler* r, const void* in_dev, int32_t in_fo
     set_error("evf_audio_resample: rate ratio needs more than 200 KB of shared memory per block");
     return EVF_ERR_UNSUPPORTED;
   }
-  const dim3 grid((unsigned)((max_out_len + kRsThreads - 1) / kRsThreads), (unsigned)n_utts);
-  if (s16) {
-    auto k = resample_kernel<short>;
-    if (smem > 48 * 1024) EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kRsThreads, smem, st>>>(static_cast<const short*>(in_dev), io, oo, r->d_kt, r->d_k0, r->nk, r->orig,
-                                      r->neu, r->width, span, out_dev);
-  } else {
-    auto k = resample_kernel<float>;
-    if (smem > 48 * 1024) EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, kRsThreads, smem, st>>>(static_cast<const float*>(in_dev), io, oo, r->d_kt, r->d_k0, r->nk, r->orig,
-                                      r->neu, r->width, span, out_dev);
+  for (int y0 = 0; y0 < n_utts; y0 += kMaxGridY) {
+    const int ny = n_utts - y0 < kMaxGridY ? n_utts - y0 : kMaxGridY;
+    const dim3 grid((unsigned)((max_out_len + kRsThreads - 1) / kRsThreads), (unsigned)ny);
+    if (s16) {
+      auto k = resample_kernel<short>;
+      if (smem > 48 * 1024) EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, kRsThreads, smem, st>>>(static_cast<const short*>(in_dev), io + y0, oo + y0, r->d_kt, r->d_k0, r->nk,
+                                        r->orig, r->neu, r->width, span, out_dev);
+    } else {
+      auto k = resample_kernel<float>;
+      if (smem > 48 * 1024) EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, kRsThreads, smem, st>>>(static_cast<const float*>(in_dev), io + y0, oo + y0, r->d_kt, r->d_k0, r->nk,
+                                        r->orig, r->neu, r->width, span, out_dev);
+    }
+    EVF_CUDA(cudaGetLastError());
   }
-  EVF_CUDA(cudaGetLastError());
   return EVF_OK;
 }
 
@@ -523,14 +533,16 @@ int evf_audio_absmax(const void* x_dev, int32_t x_format, const int64_t* offsets
   EVF_CUDA(cudaMemsetAsync(absmax_dev, 0, (size_t)n_utts * sizeof(float), st));
   if (max_len == 0) return EVF_OK;
   const long long gx = (max_len + 256 * kStreamItems - 1) / (256 * kStreamItems);
-  const dim3 grid((unsigned)gx, (unsigned)n_utts);
   const long long* off = reinterpret_cast<const long long*>(offsets_dev);
   unsigned* out = reinterpret_cast<unsigned*>(absmax_dev);
-  if (x_format == EVF_SAMPLES_S16)
-    absmax_kernel<short><<<grid, 256, 0, st>>>(static_cast<const short*>(x_dev), off, out);
-  else
-    absmax_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x_dev), off, out);
-  EVF_CUDA(cudaGetLastError());
+  for (int y0 = 0; y0 < n_utts; y0 += kMaxGridY) {
+    const dim3 grid((unsigned)gx, (unsigned)(n_utts - y0 < kMaxGridY ? n_utts - y0 : kMaxGridY));
+    if (x_format == EVF_SAMPLES_S16)
+      absmax_kernel<short><<<grid, 256, 0, st>>>(static_cast<const short*>(x_dev), off + y0, out + y0);
+    else
+      absmax_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x_dev), off + y0, out + y0);
+    EVF_CUDA(cudaGetLastError());
+  }
   return EVF_OK;
 }
 
@@ -547,24 +559,32 @@ int evf_audio_finalize(const void* x_dev, int32_t x_format, const int64_t* src_o
     return EVF_ERR_INVALID_ARGUMENT;
   }
   const long long gx = (max_kept_len + 256 * kStreamItems - 1) / (256 * kStreamItems);
-  const dim3 grid((unsigned)gx, (unsigned)n_utts);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long* so = reinterpret_cast<const long long*>(src_offsets_dev);
   const long long* dd = reinterpret_cast<const long long*>(dst_offsets_dev);
   short* o16 = reinterpret_cast<short*>(out_s16_dev);
-  if (x_format == EVF_SAMPLES_S16)
-    finalize_kernel<short><<<grid, 256, 0, st>>>(static_cast<const short*>(x_dev), so, dd, absmax_dev, out_f32_dev, o16);
-  else
-    finalize_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x_dev), so, dd, absmax_dev, out_f32_dev, o16);
-  EVF_CUDA(cudaGetLastError());
+  for (int y0 = 0; y0 < n_utts; y0 += kMaxGridY) {
+    const dim3 grid((unsigned)gx, (unsigned)(n_utts - y0 < kMaxGridY ? n_utts - y0 : kMaxGridY));
+    const float* am = absmax_dev ? absmax_dev + y0 : nullptr;
+    if (x_format == EVF_SAMPLES_S16)
+      finalize_kernel<short><<<grid, 256, 0, st>>>(static_cast<const short*>(x_dev), so + y0, dd + y0, am, out_f32_dev, o16);
+    else
+      finalize_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x_dev), so + y0, dd + y0, am, out_f32_dev, o16);
+    EVF_CUDA(cudaGetLastError());
+  }
   return EVF_OK;
 }
 
-int64_t evf_audio_loudness_scratch_floats(int32_t sample_rate, int64_t n_samples) {
-  if (sample_rate < 1 || n_samples < 0) return -1;
+int32_t evf_audio_loudness_step(int32_t sample_rate) {
+  if (sample_rate < 1) return -1;
   const long long gate = (long long)std::nearbyint(0.4 * (double)sample_rate);
   const long long step = (long long)std::nearbyint((double)gate * (1.0 - 0.75));
-  if (step < 1) return -1;
+  return step < 1 ? -1 : (int32_t)step;
+}
+
+int64_t evf_audio_loudness_scratch_floats(int32_t sample_rate, int64_t n_samples) {
+  const long long step = evf_audio_loudness_step(sample_rate);
+  if (step < 1 || n_samples < 0) return -1;
   return n_samples / step + 4;  // one partial sum per 100 ms step; the block energies read up to 3 past their index
 }
 
@@ -591,12 +611,16 @@ int evf_audio_loudness(const void* x_dev, int32_t x_format, const int64_t* offse
   const long long* soff = reinterpret_cast<const long long*>(scratch_offsets_dev);
   const long long max_sub = max_len / P.step;
   if (max_sub > 0) {
-    const dim3 grid((unsigned)((max_sub + 31) / 32), (unsigned)n_utts);
-    if (x_format == EVF_SAMPLES_S16)
-      loudness_partial_kernel<short><<<grid, 32, 0, st>>>(static_cast<const short*>(x_dev), off, P, scratch_dev, soff);
-    else
-      loudness_partial_kernel<float><<<grid, 32, 0, st>>>(static_cast<const float*>(x_dev), off, P, scratch_dev, soff);
-    EVF_CUDA(cudaGetLastError());
+    for (int y0 = 0; y0 < n_utts; y0 += kMaxGridY) {
+      const dim3 grid((unsigned)((max_sub + 31) / 32), (unsigned)(n_utts - y0 < kMaxGridY ? n_utts - y0 : kMaxGridY));
+      if (x_format == EVF_SAMPLES_S16)
+        loudness_partial_kernel<short><<<grid, 32, 0, st>>>(static_cast<const short*>(x_dev), off + y0, P, scratch_dev,
+                                                            soff + y0);
+      else
+        loudness_partial_kernel<float><<<grid, 32, 0, st>>>(static_cast<const float*>(x_dev), off + y0, P, scratch_dev,
+                                                            soff + y0);
+      EVF_CUDA(cudaGetLastError());
+    }
   }
   loudness_gate_kernel<<<(n_utts + 63) / 64, 64, 0, st>>>(off, n_utts, P, scratch_dev, soff, lkfs_dev);
   EVF_CUDA(cudaGetLastError());

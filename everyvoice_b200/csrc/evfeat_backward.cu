@@ -312,9 +312,12 @@ int features_backward_launch(const BwdParams& p, cudaStream_t st) {
   }
   if (rc != EVF_OK) return rc;
   if (p.max_len > 0) {
-    const dim3 grid((unsigned)((p.max_len + 255) / 256), (unsigned)p.n_utts);
-    overlap_add_kernel<<<grid, 256, 0, st>>>(p.frame_grad, p.sample_off, p.frame_off, p.n_fft, p.hop, p.grad_samples);
-    EVF_CUDA(cudaGetLastError());
+    for (int y0 = 0; y0 < p.n_utts; y0 += 65535) {  // gridDim.y limit: slices of utterances
+      const dim3 grid((unsigned)((p.max_len + 255) / 256), (unsigned)(p.n_utts - y0 < 65535 ? p.n_utts - y0 : 65535));
+      overlap_add_kernel<<<grid, 256, 0, st>>>(p.frame_grad, p.sample_off + y0, p.frame_off + y0, p.n_fft, p.hop,
+                                               p.grad_samples);
+      EVF_CUDA(cudaGetLastError());
+    }
   }
   return EVF_OK;
 }

@@ -183,8 +183,11 @@ __device__ __forceinline__ void evf_stage_manual(const SampleT* __restrict__ sam
   const int hi = min(ti.span, ti.L - ti.start);       // one past the last
   a_lo = lo;
   a_hi = lo;
-  // tile word i <-> packed sample s_off + start + i ; both sides must be 16-byte aligned
-  if ((((ti.s_off + ti.start + lo) | lo) & (kAlign - 1)) == 0 && hi > lo) a_hi = lo + ((hi - lo) & ~(kAlign - 1));
+  // tile word i <-> packed sample s_off + start + i ; both sides must be 16-byte aligned.  The packed buffer itself
+  // may start anywhere (a caller's view such as wav[1:]): its misalignment counts like an offset of the utterance
+  const long long base_mis = (long long)((reinterpret_cast<uintptr_t>(samples) & 15u) / sizeof(SampleT));
+  if ((((base_mis + ti.s_off + ti.start + lo) | lo) & (kAlign - 1)) == 0 && hi > lo)
+    a_hi = lo + ((hi - lo) & ~(kAlign - 1));
   const int total = a_lo + (ti.span - a_hi);
   const SampleT* src = samples + ti.s_off;
   for (int e = t; e < total; e += nt) {

@@ -455,7 +455,6 @@ int launch_m(int spec, int fmt, const FeatParams& p, int grid, int smem, cudaStr
 int dispatch(int mode, int spec, int fmt, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
   if (mode == MODE_PACK2) return launch_m<MODE_PACK2>(spec, fmt, p, grid, smem, st, cfg);
   if (mode == MODE_HALF) return launch_m<MODE_HALF>(spec, fmt, p, grid, smem, st, cfg);
-  if (mode == MODE_PACK2X2) return features_x2_dispatch(spec, fmt, p, grid, smem, st, cfg);
   set_error("unknown FFT mode");
   return EVF_ERR_UNSUPPORTED;
 }
@@ -466,8 +465,7 @@ int dispatch(int mode, int spec, int fmt, const FeatParams& p, int grid, int sme
 int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, const PlanTables& t,
                         FeatParams* c) {
   const bool mel = (spec_type == EVF_SPEC_MEL || spec_type == EVF_SPEC_MEL_LIBROSA);
-  const bool x2 = (mode == MODE_PACK2X2);           // two jobs per warp, 8-byte scratch elements, 32-byte slots
-  const int fpj = (mode == MODE_HALF) ? 1 : (x2 ? 4 : 2);  // frames per warp and tile
+  const int fpj = (mode == MODE_HALF) ? 1 : 2;  // frames per warp and tile
   const int fr = warps * fpj;
   const long long limit = 227 * 1024;  // one CTA per SM
   auto up4 = [](int w) { return (w + 3) & ~3; };
@@ -476,7 +474,7 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
   c->m_pad = t.m_pad;
   c->n_slots = t.n_slots;
   // the P column must fit into the transpose scratch it aliases
-  if (mel && t.n_chunk * 32 * fpj > 32 * kScrStride * (x2 ? 2 : 1)) return -1;
+  if (mel && t.n_chunk * 32 * fpj > 32 * kScrStride) return -1;
   // Prefer a ring of two input buffers (the refill of one overlaps the FFTs on the other); fall back
   // to one when the hop is so large that two do not fit.
   for (int nbuf = 2; nbuf >= 1; --nbuf) {
@@ -507,7 +505,7 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
       w += 32;
     }
     c->off_warp = w;
-    c->warp_words = 32 * kScrStride * (x2 ? 2 : 1) + (mel ? up4(t.n_slots * 2 * fpj) : 0);
+    c->warp_words = 32 * kScrStride + (mel ? up4(t.n_slots * 2 * fpj) : 0);
     w += warps * c->warp_words;
     const long long bytes = 4ll * w;
     if (bytes <= limit) return (int)bytes;

@@ -43,89 +43,12 @@ EVF_HD constexpr float cos32(int j) {
 }
 EVF_HD constexpr float sin32(int j) { return (j <= 8) ? cos32(8 - j) : cos32(j - 8); }
 
-// ---- value types -----------------------------------------------------------------------------
-// The butterflies are written once over a value type V with the operations below.  V = float is
-// the scalar form (one FFT per warp; also what the host-side index check runs).  V = f32x2 packs
-// the same element of TWO independent FFTs into one 64-bit register pair and maps every operation
-// to one packed instruction (FFMA2 / FADD2 / FMUL2: same lane throughput as the scalar forms, half
-// the issue slots; a scalar multiplier -- immediate twiddle, window or table value -- is broadcast
-// by the instruction itself, SASS `R.F32` / immediate operand, so nothing is duplicated).
+// The butterflies are written over a value type V with the operations below (V = float).
 EVF_HD float v_add(float a, float b) { return a + b; }
 EVF_HD float v_sub(float a, float b) { return a - b; }
 EVF_HD float v_neg(float a) { return -a; }
 EVF_HD float v_mul(float a, float s) { return a * s; }                 // a * s
 EVF_HD float v_fma(float a, float s, float c) { return fmaf(a, s, c); }  // a * s + c, s scalar
-
-// Two floats in one 64-bit register pair.  Device: the packed sm_100 instructions through inline PTX.
-// Host (tests/native/fft_host_check.cu): the same operations on the two halves, so that the packed
-// index arithmetic can be checked without a GPU.
-struct f32x2 {
-  unsigned long long v;  // low 32 bits = first element, high 32 bits = second element
-};
-EVF_HD f32x2 v_pack(float lo, float hi) {
-  f32x2 r;
-#ifdef __CUDA_ARCH__
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
-#else
-  unsigned a, b;
-  memcpy(&a, &lo, 4);
-  memcpy(&b, &hi, 4);
-  r.v = (unsigned long long)a | ((unsigned long long)b << 32);
-#endif
-  return r;
-}
-EVF_HD void v_unpack(f32x2 x, float& lo, float& hi) {
-#ifdef __CUDA_ARCH__
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x.v));
-#else
-  const unsigned a = (unsigned)x.v, b = (unsigned)(x.v >> 32);
-  memcpy(&lo, &a, 4);
-  memcpy(&hi, &b, 4);
-#endif
-}
-#ifdef __CUDA_ARCH__
-#define EVF_F32X2_OP2(name, ptx)                                              \
-  EVF_HD f32x2 name(f32x2 a, f32x2 b) {                                        \
-    f32x2 r;                                                                   \
-    asm(ptx " %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));                  \
-    return r;                                                                  \
-  }
-#else
-#define EVF_F32X2_OP2(name, ptx)                                              \
-  EVF_HD f32x2 name(f32x2 a, f32x2 b) {                                        \
-    float a0, a1, b0, b1;                                                      \
-    v_unpack(a, a0, a1);                                                       \
-    v_unpack(b, b0, b1);                                                       \
-    return v_pack(name(a0, b0), name(a1, b1));                                 \
-  }
-#endif
-EVF_F32X2_OP2(v_add, "add.rn.f32x2")
-EVF_F32X2_OP2(v_sub, "sub.rn.f32x2")
-EVF_F32X2_OP2(v_mul, "mul.rn.f32x2")  // element-wise product
-#undef EVF_F32X2_OP2
-EVF_HD f32x2 v_fma(f32x2 a, f32x2 b, f32x2 c) {  // element-wise a * b + c
-#ifdef __CUDA_ARCH__
-  f32x2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
-  return r;
-#else
-  float a0, a1, b0, b1, c0, c1;
-  v_unpack(a, a0, a1);
-  v_unpack(b, b0, b1);
-  v_unpack(c, c0, c1);
-  return v_pack(fmaf(a0, b0, c0), fmaf(a1, b1, c1));
-#endif
-}
-EVF_HD f32x2 v_neg(f32x2 a) {  // folds into the consumer's operand modifier
-  float lo, hi;
-  v_unpack(a, lo, hi);
-  return v_pack(-lo, -hi);
-}
-// scalar multiplier broadcast to both halves (SASS: immediate or `R.F32` operand, no extra instruction)
-EVF_HD f32x2 v_mul(f32x2 a, float s) { return v_mul(a, v_pack(s, s)); }
-EVF_HD f32x2 v_fma(f32x2 a, float s, f32x2 c) { return v_fma(a, v_pack(s, s), c); }
-EVF_HD f32x2 v_mul2(f32x2 a, f32x2 b) { return v_mul(a, b); }
-EVF_HD f32x2 v_fma2(f32x2 a, f32x2 b, f32x2 c) { return v_fma(a, b, c); }
 
 // One DIT butterfly on (a, b) with w = exp(-2*pi*i*J/32):  a' = a + w b,  b' = a - w b.
 template <int J, typename V>

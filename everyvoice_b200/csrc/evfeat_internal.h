@@ -11,16 +11,14 @@
 namespace evf {
 
 constexpr int kMaxWarps = 16;        // warps per CTA (one CTA per SM); one FFT job per warp per tile
-constexpr int kX2Warps = 8;          // packed kernel (evfeat_features_x2.cu): two FFT jobs per warp per tile
 constexpr int kFftSize = 1024;       // complex points per warp-level FFT
 constexpr int kScrStride = 34;       // padded row stride of the per-warp transpose scratch (even: LDS.64 rows)
 
 enum FftMode : int {
   MODE_PACK2 = 0,  // n_fft == 1024: two real frames packed as re/im of one complex FFT
   MODE_HALF = 1,   // n_fft == 2048: one real frame as a 1024-point complex FFT + split
-  MODE_PACK2X2 = 2,  // n_fft == 1024, packed f32x2 arithmetic: a warp runs two MODE_PACK2 jobs at once (opt-in variant)
 };
-inline bool mode_is_pack2(int mode) { return mode == MODE_PACK2 || mode == MODE_PACK2X2; }
+inline bool mode_is_pack2(int mode) { return mode == MODE_PACK2; }
 
 // One frame tile of one utterance; built on the host by evf_batch_create so that the kernel
 // needs no dependent loads (tile -> utterance -> offsets) to start staging a tile.
@@ -109,10 +107,6 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
 int features_configure(int mode, int spec_type, int sample_format, int smem_bytes);
 int features_launch(int mode, int spec_type, int sample_format, const FeatParams& p, int grid, int smem_bytes,
                     cudaStream_t stream);
-
-// evfeat_features_x2.cu
-int features_x2_dispatch(int spec_type, int sample_format, const FeatParams& p, int grid, int smem_bytes,
-                         cudaStream_t stream, bool configure_only);
 
 // evfeat_backward.cu
 struct BwdParams {

@@ -205,9 +205,10 @@ class CorpusPipeline:
                     stats = self._d_stats
                     if normalize_phones:
                         parts = allgather_stats(self._d_stats, group, out=self._d_gathered)
-                        if parts.dim() == 2 and parts.shape[0] > 1:
-                            self._d_gathered = parts
-                        parts = parts.contiguous()
+                        if parts.is_cuda and parts.dim() == 2 and parts.shape[0] > 1:
+                            self._d_gathered = parts       # NCCL: reuse the gather buffer next run
+                        # a gloo group gathers through host memory; the kernel below takes DEVICE pointers
+                        parts = parts.to(self.device).contiguous()
                         _lib.check(lib.evf_normalize_by_gathered_stats(
                             C.c_void_p(self._d_phone.data_ptr()), self.n_phones, C.c_void_p(parts.data_ptr()),
                             parts.shape[0], parts.shape[1], st))

@@ -30,6 +30,15 @@ from .heavy import (RaggedFeatures, SpectralTransform, _ptr, _require_cuda, _str
 from .helpers import Scaler
 
 
+def _to_sample_dtype(a: torch.Tensor, dt) -> torch.Tensor:
+    """int16 PCM promoted to float32 is ``s / 32768`` (what torchaudio.load yields), never the raw integer value."""
+    if a.dtype == dt:
+        return a
+    if a.dtype == torch.int16 and dt == torch.float32:
+        return a.to(torch.float32) * (1.0 / 32768.0)
+    return a.to(dt)
+
+
 def _as_i64_dev(x, device) -> torch.Tensor:
     if torch.is_tensor(x):
         return x.to(device=device, dtype=torch.int64).contiguous()
@@ -208,6 +217,14 @@ class Preprocessor:
         n_utts = v_off.numel() - 1
         if p_off.numel() != n_utts + 1:
             raise ValueError("value_offsets and phone_offsets must describe the same number of utterances")
+        if n_utts > 0 and not (torch.is_tensor(value_offsets) and value_offsets.is_cuda):
+            # host-side offsets: check them against the buffers before a kernel indexes with them
+            vo, po = np.asarray(value_offsets, dtype=np.int64), np.asarray(
+                phone_offsets.cpu() if torch.is_tensor(phone_offsets) else phone_offsets, dtype=np.int64)
+            if (np.diff(vo) < 0).any() or vo[0] < 0 or vo[-1] > vals.numel():
+                raise ValueError("value_offsets must be non-decreasing and end inside `values`")
+            if (np.diff(po) < 0).any() or po[0] < 0 or po[-1] > durs.numel():
+                raise ValueError("phone_offsets must be non-decreasing and end inside `durations`")
         out = torch.empty(durs.numel(), dtype=torch.float32, device=device)
         lib = _lib.load()
         with torch.cuda.device(device):
@@ -226,7 +243,8 @@ class Preprocessor:
             lens = np.array([a.numel() for a in audios], dtype=np.int64)
             sample_offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
             dt = torch.int16 if all(a.dtype == torch.int16 for a in audios) else torch.float32
-            packed = torch.cat([a.reshape(-1).to(dt) for a in audios]) if len(audios) else torch.zeros(0, dtype=dt)
+            packed = torch.cat([_to_sample_dtype(a.reshape(-1), dt) for a in audios]) if len(audios) \
+                else torch.zeros(0, dtype=dt)
         else:
             packed = audios
         if not packed.is_cuda:
@@ -291,7 +309,7 @@ class Preprocessor:
         stored value (here: in place over the scaler's device tensors, one launch each)."""
         stats = {}
         for name, scaler in (("energy", energy_scaler), ("pitch", pitch_scaler)):
-            if not scaler:
+            if scaler is None:   # an EMPTY scaler still joins the collectives (a rank whose shard was gated out)
                 continue
             n_files = getattr(scaler, "_n_files", None)
             if n_files is not None:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define EVF_ABI_VERSION 7
+#define EVF_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define EVF_API __attribute__((visibility("default")))
@@ -242,6 +242,8 @@ EVF_API int evf_audio_finalize(const void* x_dev, int32_t x_format, const int64_
  * max_len = the longest utterance (grid sizing).  The filters' recursion is restarted every 100 ms with a 100 ms
  * run-in (state error < 1e-7 relative), so all steps of all utterances run in parallel. */
 EVF_API int64_t evf_audio_loudness_scratch_floats(int32_t sample_rate, int64_t n_samples);
+/* the 100 ms step in samples as torchaudio rounds it (round(round(0.4 * sr) * 0.25), half to even); -1 on bad input */
+EVF_API int32_t evf_audio_loudness_step(int32_t sample_rate);
 EVF_API int evf_audio_loudness(const void* x_dev, int32_t x_format, const int64_t* offsets_dev, int32_t n_utts,
                                int64_t max_len, int32_t sample_rate, float* scratch_dev,
                                const int64_t* scratch_offsets_dev, float* lkfs_dev, void* stream);

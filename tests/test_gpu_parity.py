@@ -196,33 +196,6 @@ def test_batched_equals_single_bitwise(cuda_device):
         assert torch.equal(single.energy, feats.utterance_energy(b))
 
 
-@pytest.mark.parametrize("spec_type", ["mel", "mel-librosa", "linear", "raw"])
-@pytest.mark.parametrize("dtype", ["f32", "s16"])
-def test_packed_two_job_kernel_is_bit_identical(cuda_device, monkeypatch, spec_type, dtype):
-    """EVF_FEATURES_VARIANT=x2 selects features_kernel_x2 (two FFT jobs per warp in f32x2 registers) when the
-    plan is created; every half of a packed instruction is the scalar kernel's IEEE operation."""
-    from everyvoice_b200 import synth
-
-    hop = 256
-    lens = synth.utterance_lengths(7, 22050, hop, 21, 0.2, 1.7)
-    lens[2] = 3 * hop + 17  # a one-tile utterance whose second job half stays idle
-    rng = np.random.default_rng(8)
-    if dtype == "s16":
-        xs = [rng.integers(-30000, 30000, size=int(L)).astype(np.int16) for L in lens]
-    else:
-        xs = [synth.speech_like(int(L), 22050, seed=40 + i) for i, L in enumerate(lens)]
-    packed, offsets = synth.pack_ragged(xs)
-    x = torch.from_numpy(packed).to(cuda_device)
-    out = {}
-    for variant in ("x1", "x2"):
-        monkeypatch.setenv("EVF_FEATURES_VARIANT", variant)
-        tf, _ = _transform("A", spec_type)  # a fresh transform: plans are created (and the variant read) lazily
-        out[variant] = tf.features_ragged(x, offsets)
-    assert torch.equal(out["x1"].spec, out["x2"].spec)
-    if spec_type != "raw":
-        assert torch.equal(out["x1"].energy, out["x2"].energy)
-
-
 def test_leading_batch_dims_and_device_round_trip(cuda_device):
     from oracle import ev_oracle as O
 
@@ -707,22 +680,20 @@ def test_config5_rank_shard_of_100h_corpus(cuda_device):
     assert float((back - feats.energy).abs().max()) <= 1e-4 * float(feats.energy.abs().max())
 
 
-@pytest.mark.parametrize("variant", ["x1", "x2"])
-def test_nan_and_inf_samples_stay_local(cuda_device, monkeypatch, variant):
+def test_nan_and_inf_samples_stay_local(cuda_device):
     """A NaN / Inf sample poisons the frames whose window covers it (like torch.stft does) plus, for n_fft 1024, the
     partner frame of the same FFT job (frames 2j and 2j + 1 ride as real and imaginary part of one complex FFT, so a
     non-finite value in one reaches the other in the real-FFT separation) -- and nothing else: no stale value leaks
-    between jobs, tiles, warps or the two halves of a packed register.  Documented deviation (INTEGRATION.md
+    between jobs, tiles or warps.  Documented deviation (INTEGRATION.md
     section 5); PCM input cannot contain non-finite samples."""
     from everyvoice_b200 import synth
     from oracle import ev_oracle as O
 
-    monkeypatch.setenv("EVF_FEATURES_VARIANT", variant)
     tf, hop = _transform("A", "mel")
     otf, _ = _oracle_transform("A", "mel")
     xs = [synth.speech_like(hop * n, 22050, seed=300 + i) for i, n in enumerate((70, 33, 95, 40))]
     xs[0][hop * 20 + 7] = np.nan
-    xs[2][hop * 64 + 100] = np.inf       # second tile of the utterance, a job of the packed kernel's B half
+    xs[2][hop * 64 + 100] = np.inf       # second tile of the utterance
     xs[2][5] = -np.inf                    # inside the reflected left margin: mirrored into frame 0 twice
     packed, off = synth.pack_ragged(xs)
     feats = tf.features_ragged(torch.from_numpy(packed).to(cuda_device), off)
