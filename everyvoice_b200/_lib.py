@@ -27,6 +27,7 @@ EVF_ERR_OUT_OF_MEMORY = 7
 # evf_spec_type  (everyvoice/config/preprocessing_config.py:18-22)
 SPEC_TYPES = {"mel": 0, "mel-librosa": 1, "linear": 2, "raw": 3}
 SAMPLES_F32, SAMPLES_S16 = 0, 1
+FFT_AUTO, FFT_GENERIC = 0, 1
 
 ABI_VERSION = 8
 
@@ -43,6 +44,7 @@ class evf_config(C.Structure):
         ("keep_last_frame", C.c_int32),
         ("sample_format", C.c_int32),
         ("log_clip", C.c_float),
+        ("fft_path", C.c_int32),
     ]
 
 

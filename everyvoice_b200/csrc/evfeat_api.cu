@@ -29,6 +29,13 @@ struct evf_plan {
   unsigned* d_ltab = nullptr;
   float2* d_melw = nullptr;  // per-bin {rising, falling} weights and interval index: the backward's transposed mel
   int* d_jk = nullptr;
+  // MODE_GENERIC (evfeat_generic.cu)
+  evf::GenParams gen{};
+  int gen_grid_per_sm = 1;
+  float2* d_tw = nullptr;
+  double2* d_tw64 = nullptr;
+  int* d_kstart = nullptr;
+  float* d_fb_dense = nullptr;
 };
 
 struct evf_batch {
@@ -202,6 +209,82 @@ void free_plan_tables(evf_plan* p) {
   cudaFree(p->d_ltab);
   cudaFree(p->d_melw);
   cudaFree(p->d_jk);
+  cudaFree(p->d_tw);
+  cudaFree(p->d_tw64);
+  cudaFree(p->d_kstart);
+  cudaFree(p->d_fb_dense);
+}
+
+// frames of an utterance of L samples: torch.stft(center=True) yields 1 + (L + 2 * (n_fft / 2) - n_fft) / hop
+// (= 1 + L / hop for even n_fft, 1 + (L - 1) / hop for odd n_fft); process_spec keeps the first L / hop of them
+long long frames_of(const evf_config& c, long long L) {
+  if (c.keep_last_frame) return 1 + (L + 2 * (long long)(c.n_fft / 2) - c.n_fft) / c.hop_length;
+  return L / c.hop_length;
+}
+
+// Tables and launch geometry of the any-size kernel (evfeat_generic.cu).
+int create_generic_plan(evf_plan* p, const float* window_host, const float* fb_dense_host, const PlanTables& t) {
+  const evf_config& c = p->cfg;
+  const int N = c.n_fft;
+  const bool mel = (c.spec_type == EVF_SPEC_MEL || c.spec_type == EVF_SPEC_MEL_LIBROSA);
+  GenParams& g = p->gen;
+  bool needs64 = false;
+  if (generic_factorize(N, &g.st, &needs64) != EVF_OK) {
+    set_error("evf_plan_create: n_fft has more prime factors than the stage list holds");
+    return EVF_ERR_UNSUPPORTED;
+  }
+  p->smem_bytes = generic_smem_bytes(N, &g.pairs);
+  if (p->smem_bytes < 0) {
+    set_error("evf_plan_create: n_fft is too large for the shared-memory FFT (two buffers of n_fft complex points "
+              "must fit into 227 KB: n_fft <= 14 000)");
+    return EVF_ERR_UNSUPPORTED;
+  }
+  p->frames_per_tile = 2 * g.pairs;
+  g.n_fft = N;
+  g.hop = c.hop_length;
+  g.n_freq = p->n_freq;
+  g.n_mels = c.n_mels;
+  g.row_floats = p->row_floats;
+  g.apply_log = (c.spec_type == EVF_SPEC_RAW) ? 0 : c.apply_log;
+  g.log_clip = c.log_clip;
+  std::vector<float> win(N);
+  for (int i = 0; i < N; ++i) win[i] = 0.5f * window_host[i];  // exact scaling: the pair separation omits its 1/2
+  std::vector<float2> tw(N);
+  std::vector<double2> tw64(needs64 ? N : 0);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int m = 0; m < N; ++m) {
+    const double ang = -two_pi * (double)m / (double)N;
+    tw[m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    if (needs64) tw64[m] = make_double2(std::cos(ang), std::sin(ang));
+  }
+  int rc = generic_configure(c.spec_type, c.sample_format, p->smem_bytes);
+  if (rc == EVF_OK) rc = upload(win, &p->d_window);
+  if (rc == EVF_OK) rc = upload(tw, &p->d_tw);
+  if (rc == EVF_OK) rc = upload(tw64, &p->d_tw64);
+  if (rc == EVF_OK && mel) {
+    if (fb_dense_host != nullptr) {
+      std::vector<float> fb(fb_dense_host, fb_dense_host + (size_t)p->n_freq * c.n_mels);
+      rc = upload(fb, &p->d_fb_dense);
+    } else {
+      rc = upload(t.melw, &p->d_melw);
+      if (rc == EVF_OK) rc = upload(t.kstart, &p->d_kstart);
+      std::vector<int> jk(t.jk.begin(), t.jk.begin() + t.k_used);
+      if (rc == EVF_OK) rc = upload(jk, &p->d_jk);
+    }
+  }
+  if (rc != EVF_OK) return rc;
+  g.window = p->d_window;
+  g.tw = p->d_tw;
+  g.tw64 = p->d_tw64;
+  g.melw = p->d_melw;
+  g.kstart = p->d_kstart;
+  g.fb_dense = p->d_fb_dense;
+  // resident CTAs per SM: shared memory (the opt-in 227 KB) and 2048 threads
+  int per_sm = (227 * 1024) / (p->smem_bytes + 1024);
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  p->gen_grid_per_sm = per_sm;
+  return EVF_OK;
 }
 
 }  // namespace
@@ -227,18 +310,13 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
     set_error("evf_plan_create: unknown spec_type");
     return EVF_ERR_UNSUPPORTED;
   }
-  if (cfg->n_fft != 1024 && cfg->n_fft != 2048) {
-    set_error("evf_plan_create: n_fft must be 1024 or 2048");
-    return EVF_ERR_UNSUPPORTED;
-  }
-  if (cfg->hop_length < 1 || cfg->hop_length > cfg->n_fft || cfg->win_length < 1 ||
-      cfg->win_length > cfg->n_fft) {
-    set_error("evf_plan_create: need 1 <= hop_length, win_length <= n_fft");
+  if (cfg->n_fft < 1 || cfg->hop_length < 1 || cfg->win_length < 1 || cfg->win_length > cfg->n_fft) {
+    set_error("evf_plan_create: need n_fft >= 1, hop_length >= 1 and 1 <= win_length <= n_fft (torch.stft's own limits)");
     return EVF_ERR_INVALID_ARGUMENT;
   }
-  if (cfg->n_fft == 2048 && (cfg->hop_length & 1)) {
-    set_error("evf_plan_create: n_fft 2048 needs an even hop_length");
-    return EVF_ERR_UNSUPPORTED;
+  if (cfg->fft_path != EVF_FFT_AUTO && cfg->fft_path != EVF_FFT_GENERIC) {
+    set_error("evf_plan_create: unknown fft_path");
+    return EVF_ERR_INVALID_ARGUMENT;
   }
   if (cfg->sample_format != EVF_SAMPLES_F32 && cfg->sample_format != EVF_SAMPLES_S16) {
     set_error("evf_plan_create: unknown sample_format");
@@ -271,7 +349,11 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   if (!p) return EVF_ERR_OUT_OF_MEMORY;
   p->cfg = *cfg;
   p->device = device;
-  p->mode = (cfg->n_fft == 1024) ? MODE_PACK2 : MODE_HALF;
+  // the warp-per-FFT kernel covers n_fft 1024 (any hop <= n_fft) and 2048 (even hops); everything else -- and
+  // whatever does not fit its shared-memory carve-up or its triangular-bank tables -- runs in the any-size kernel
+  const bool fast_shape = cfg->fft_path == EVF_FFT_AUTO && cfg->hop_length <= cfg->n_fft &&
+                          (cfg->n_fft == 1024 || (cfg->n_fft == 2048 && (cfg->hop_length & 1) == 0));
+  p->mode = !fast_shape ? MODE_GENERIC : (cfg->n_fft == 1024 ? MODE_PACK2 : MODE_HALF);
   p->n_freq = cfg->n_fft / 2 + 1;
   p->warps = kMaxWarps;  // one CTA per SM
   p->frames_per_tile = (p->mode == MODE_HALF) ? p->warps : 32;     // 16 jobs of two frames (n_fft 1024)
@@ -279,6 +361,34 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   p->row_floats = mel ? cfg->n_mels : (cfg->spec_type == EVF_SPEC_RAW ? 2 * p->n_freq : p->n_freq);
 
   PlanTables t;
+  bool triangular = true;
+  int rc = EVF_OK;
+  if (mel) {
+    rc = compress_filterbank(mel_fb_host, p->n_freq, cfg->n_mels, &t);
+    if (rc == EVF_OK && p->mode != MODE_GENERIC) rc = build_walk_tables(cfg->n_mels, &t);
+    if (rc != EVF_OK) {  // not a bank of adjacent triangular filters (or too many of them): dense projection
+      triangular = false;
+      p->mode = MODE_GENERIC;
+      rc = EVF_OK;
+    }
+    p->k_used = t.k_used;
+  }
+  if (p->mode != MODE_GENERIC) {
+    // does the carve-up fit?  (large hops: two or even one input tile of (frames - 1) * hop + n_fft samples do not)
+    FeatParams probe{};
+    if (features_smem_bytes(p->mode, cfg->spec_type, p->warps, cfg->hop_length, cfg->n_fft, t, &probe) < 0)
+      p->mode = MODE_GENERIC;
+  }
+  if (p->mode == MODE_GENERIC) {
+    rc = create_generic_plan(p, window_host, triangular ? nullptr : mel_fb_host, t);
+    if (rc != EVF_OK) {
+      free_plan_tables(p);
+      delete p;
+      return rc;
+    }
+    *plan_out = p;
+    return EVF_OK;
+  }
   t.window.resize(cfg->n_fft);
   if (mode_is_pack2(p->mode)) {
     // pair layout for LDS.64: [r][lane] = {w[32 * r + lane], w[32 * (r + 16) + lane]}, r < 16: the two inputs of
@@ -313,13 +423,6 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
       const double ang = two_pi * (double)k / 2048.0;
       t.wpost[k] = make_float2((float)std::cos(ang), (float)(-std::sin(ang)));
     }
-  }
-  int rc = EVF_OK;
-  if (mel) {
-    rc = compress_filterbank(mel_fb_host, p->n_freq, cfg->n_mels, &t);
-    if (rc == EVF_OK) rc = build_walk_tables(cfg->n_mels, &t);
-    if (rc != EVF_OK) { delete p; return rc; }
-    p->k_used = t.k_used;
   }
   p->smem_bytes = features_smem_bytes(p->mode, cfg->spec_type, p->warps, cfg->hop_length, cfg->n_fft, t, &p->carve);
   if (p->smem_bytes < 0) {
@@ -367,7 +470,7 @@ int evf_plan_row_floats(const evf_plan* plan, int32_t* row_floats_out) {
 
 int64_t evf_plan_num_frames(const evf_plan* plan, int64_t n_samples) {
   if (!plan || n_samples < 0) return -1;
-  return n_samples / plan->cfg.hop_length + (plan->cfg.keep_last_frame ? 1 : 0);
+  return frames_of(plan->cfg, n_samples);
 }
 
 int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, int32_t n_utts,
@@ -381,7 +484,7 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
   std::vector<long long> s_off(n_utts + 1, 0), f_off(n_utts + 1, 0);
   std::vector<TileDesc> tiles;
   std::vector<int> tile_start(n_utts + 1, 0);
-  const int fpj = mode_is_pack2(plan->mode) ? 2 : 1;  // frames per FFT job
+  const int fpj = (plan->mode == MODE_HALF) ? 1 : 2;  // frames per FFT job
   for (int b = 0; b < n_utts; ++b) {
     tile_start[b] = (int)tiles.size();
     const int64_t L = sample_offsets_host[b + 1] - sample_offsets_host[b];
@@ -393,7 +496,7 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
       set_error(buf);
       return EVF_ERR_SHORT_INPUT;
     }
-    const int64_t T = L / hop + (plan->cfg.keep_last_frame ? 1 : 0);
+    const int64_t T = frames_of(plan->cfg, L);
     if (T > 0x7fffffff - fr) {
       set_error("evf_batch_create: utterance too long");
       return EVF_ERR_INVALID_ARGUMENT;
@@ -490,6 +593,17 @@ static int features_run_tiles(const evf_plan* plan, const evf_batch* batch, int 
                               const void* samples_dev, float* spec_out_dev, float* energy_out_dev, void* stream) {
   if (tile_end <= tile_begin) return EVF_OK;
   DeviceGuard guard(plan->device);
+  if (plan->mode == MODE_GENERIC) {
+    GenParams g = plan->gen;
+    g.samples = samples_dev;
+    g.tiles = batch->d_tiles + tile_begin;
+    g.n_tiles = tile_end - tile_begin;
+    g.spec_out = spec_out_dev;
+    g.energy_out = (plan->cfg.spec_type == EVF_SPEC_RAW) ? nullptr : energy_out_dev;
+    const int cap = plan->num_sms * plan->gen_grid_per_sm;
+    return generic_launch(plan->cfg.spec_type, plan->cfg.sample_format, g, g.n_tiles < cap ? g.n_tiles : cap,
+                          plan->smem_bytes, static_cast<cudaStream_t>(stream));
+  }
   FeatParams p = plan->carve;
   p.samples = samples_dev;
   p.tiles = batch->d_tiles + tile_begin;
@@ -622,6 +736,11 @@ int evf_features_backward(const evf_plan* plan, const evf_batch* batch, const fl
   if (!plan || !batch || batch->device != plan->device) {
     set_error("evf_features_backward: invalid plan / batch");
     return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (plan->mode == MODE_GENERIC) {
+    set_error("evf_features_backward: the backward kernels cover n_fft 1024 (hop <= n_fft) and 2048 (even hop) with a "
+              "triangular mel bank");
+    return EVF_ERR_UNSUPPORTED;
   }
   if (plan->cfg.sample_format != EVF_SAMPLES_F32 || plan->cfg.apply_log || plan->cfg.spec_type == EVF_SPEC_RAW) {
     set_error("evf_features_backward: needs float32 samples, a linear-domain plan (apply_log = 0; the log has its own "

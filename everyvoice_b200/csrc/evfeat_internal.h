@@ -17,6 +17,7 @@ constexpr int kScrStride = 34;       // padded row stride of the per-warp transp
 enum FftMode : int {
   MODE_PACK2 = 0,  // n_fft == 1024: two real frames packed as re/im of one complex FFT
   MODE_HALF = 1,   // n_fft == 2048: one real frame as a 1024-point complex FFT + split
+  MODE_GENERIC = 2,  // any n_fft / hop: shared-memory mixed-radix FFT over frame pairs (evfeat_generic.cu)
 };
 inline bool mode_is_pack2(int mode) { return mode == MODE_PACK2; }
 
@@ -107,6 +108,34 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
 int features_configure(int mode, int spec_type, int sample_format, int smem_bytes);
 int features_launch(int mode, int spec_type, int sample_format, const FeatParams& p, int grid, int smem_bytes,
                     cudaStream_t stream);
+
+// evfeat_generic.cu: the any-size kernel
+constexpr int kGenMaxStages = 24;
+struct GenStages {
+  int n;
+  int radix[kGenMaxStages];
+};
+struct GenParams {
+  const void* samples;
+  const TileDesc* tiles;
+  int n_tiles;
+  float* spec_out;
+  float* energy_out;
+  const float* window;     // [n_fft], pre-scaled by 0.5 (natural order)
+  const float2* tw;        // [n_fft] W_N^m = exp(-2 pi i m / n_fft), fp64-built
+  const double2* tw64;     // the same in float64; only when a prime factor > 5 needs a direct-DFT stage
+  const float2* melw;      // [k_used] {rising, falling} weight of every bin (triangular banks)
+  const int* kstart;       // [n_mels + 2] interval j (between filter centres j - 1 and j) owns bins [kstart[j], kstart[j + 1])
+  const float* fb_dense;   // [n_freq][n_mels]: set instead of melw / kstart for a bank that is not triangular
+  int n_fft, hop, n_freq, n_mels, row_floats, apply_log;
+  float log_clip;
+  int pairs;               // frame pairs (FFTs) per CTA iteration; a tile holds 2 * pairs frames
+  GenStages st;
+};
+int generic_factorize(int n_fft, GenStages* st, bool* needs_tw64);
+int generic_smem_bytes(int n_fft, int* pairs_out);
+int generic_configure(int spec_type, int sample_format, int smem_bytes);
+int generic_launch(int spec_type, int sample_format, const GenParams& p, int grid, int smem_bytes, cudaStream_t stream);
 
 // evfeat_backward.cu
 struct BwdParams {

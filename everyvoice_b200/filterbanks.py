@@ -30,25 +30,51 @@ def hann_window_padded(win_length: int, n_fft: int) -> torch.Tensor:
     return w.contiguous()
 
 
-def melscale_fbanks_htk_slaney(
-    n_freqs: int, f_min: float, f_max: float, n_mels: int, sample_rate: int
-) -> torch.Tensor:
-    """Returns ``fb[n_freqs, n_mels]`` float32."""
+def _hz_to_mel(freq: float, mel_scale: str) -> float:
+    if mel_scale == "htk":
+        return 2595.0 * math.log10(1.0 + (freq / 700.0))
+    f_sp = 200.0 / 3
+    if freq >= 1000.0:
+        return 1000.0 / f_sp + math.log(freq / 1000.0) / (math.log(6.4) / 27.0)
+    return freq / f_sp
+
+
+def melscale_fbanks(n_freqs: int, f_min: float, f_max: float, n_mels: int, sample_rate: int,
+                    norm: str | None = None, mel_scale: str = "htk") -> torch.Tensor:
+    """``torchaudio.functional.melscale_fbanks`` with the same float32 torch operations in the same order
+    (``mel_scale`` "htk" | "slaney", ``norm`` None | "slaney").  Returns ``fb[n_freqs, n_mels]`` float32.
+    ``T.MelSpectrogram`` defaults are htk / no norm (StyleTTS2: styletts2/utils.py:12-21, losses.py:42-48); the
+    reference's ``"mel"`` transform passes ``norm="slaney"`` (utils/heavy.py:57-68)."""
+    if norm is not None and norm != "slaney":
+        raise ValueError('norm must be one of None or "slaney"')
+    if mel_scale not in ("htk", "slaney"):
+        raise ValueError('mel_scale should be one of "htk" or "slaney".')
     if f_min > f_max:
         raise ValueError(f"Require f_min: {f_min} <= f_max: {f_max}")
     all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
-    m_min = 2595.0 * math.log10(1.0 + (f_min / 700.0))
-    m_max = 2595.0 * math.log10(1.0 + (f_max / 700.0))
-    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
-    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    m_pts = torch.linspace(_hz_to_mel(f_min, mel_scale), _hz_to_mel(f_max, mel_scale), n_mels + 2)
+    if mel_scale == "htk":
+        f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    else:
+        f_sp = 200.0 / 3
+        f_pts = f_sp * m_pts
+        min_log_mel = 1000.0 / f_sp
+        log_t = m_pts >= min_log_mel
+        f_pts[log_t] = 1000.0 * torch.exp((math.log(6.4) / 27.0) * (m_pts[log_t] - min_log_mel))
     f_diff = f_pts[1:] - f_pts[:-1]
     slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
     down_slopes = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
     up_slopes = slopes[:, 2:] / f_diff[1:]
     fb = torch.max(torch.zeros(1), torch.min(down_slopes, up_slopes))
-    enorm = 2.0 / (f_pts[2 : n_mels + 2] - f_pts[:n_mels])
-    fb = fb * enorm.unsqueeze(0)
+    if norm == "slaney":
+        enorm = 2.0 / (f_pts[2 : n_mels + 2] - f_pts[:n_mels])
+        fb = fb * enorm.unsqueeze(0)
     return fb.contiguous()
+
+
+def melscale_fbanks_htk_slaney(n_freqs: int, f_min: float, f_max: float, n_mels: int, sample_rate: int) -> torch.Tensor:
+    """The bank of the reference's ``"mel"`` transform (htk scale, slaney norm)."""
+    return melscale_fbanks(n_freqs, f_min, f_max, n_mels, sample_rate, "slaney", "htk")
 
 
 def librosa_mel_basis(sr: int, n_fft: int, n_mels: int, fmin: float, fmax: float | None) -> torch.Tensor:

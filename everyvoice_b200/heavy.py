@@ -70,6 +70,7 @@ class _Plan:
             keep_last_frame=int(keep_last),
             sample_format=sample_format,
             log_clip=1e-5,
+            fft_path=_lib.FFT_GENERIC if tf.fft_path == "generic" else _lib.FFT_AUTO,
         )
         win = tf.window.contiguous()
         fb = tf.mel_fb.contiguous() if tf.mel_fb is not None else None
@@ -214,19 +215,43 @@ class SpectralTransform:
     ``t.features(...)`` / ``t.run(...)`` are the fused log + energy paths."""
 
     def __init__(self, spec_type, n_fft, win_length, hop_length, sample_rate=None, n_mels=None,
-                 f_min=0, f_max=8000, device=None):
+                 f_min=0, f_max=8000, device=None, *, norm="slaney", mel_scale="htk", mel_fb=None, window=None,
+                 fft_path="auto"):
+        """The keyword-only arguments go beyond ``get_spectral_transform``'s signature (training-side mels, SURVEY
+        8f N4): ``norm`` / ``mel_scale`` are ``T.MelSpectrogram``'s (StyleTTS2 uses its defaults, None / "htk");
+        ``mel_fb`` is any ``[n_fft // 2 + 1, n_mels]`` basis (triangular banks take the sparse projection, anything
+        else a dense one); ``window`` replaces the Hann window (``[win_length]`` or ``[n_fft]``); ``fft_path="generic"``
+        forces the any-size FFT kernel (evf_fft_path)."""
         spec_type = getattr(spec_type, "value", spec_type)
         if spec_type not in _lib.SPEC_TYPES:
             raise ValueError(f"unsupported spec_type {spec_type!r}")
+        if fft_path not in ("auto", "generic"):
+            raise ValueError("fft_path must be 'auto' or 'generic'")
         self.spec_type = spec_type
+        self.fft_path = fft_path
         self.n_fft, self.win_length, self.hop_length = int(n_fft), int(win_length), int(hop_length)
         self.sample_rate, self.n_mels, self.f_min, self.f_max = sample_rate, n_mels, f_min, f_max
         self.n_freqs = self.n_fft // 2 + 1
-        self.window = filterbanks.hann_window_padded(self.win_length, self.n_fft)
-        if spec_type == "mel":  # heavy.py:57-68
-            self.mel_fb = filterbanks.melscale_fbanks_htk_slaney(
+        if window is None:
+            self.window = filterbanks.hann_window_padded(self.win_length, self.n_fft)
+        else:
+            w = torch.as_tensor(window, dtype=torch.float32).detach().cpu().reshape(-1)
+            if w.numel() == self.win_length and self.win_length < self.n_fft:
+                left = (self.n_fft - self.win_length) // 2
+                w = torch.nn.functional.pad(w, (left, self.n_fft - self.win_length - left))
+            if w.numel() != self.n_fft:
+                raise ValueError("window must have win_length or n_fft entries")
+            self.window = w.contiguous()
+        if mel_fb is not None and spec_type in ("mel", "mel-librosa"):
+            fb = torch.as_tensor(mel_fb, dtype=torch.float32).detach().cpu()
+            if fb.dim() != 2 or fb.shape[0] != self.n_freqs:
+                raise ValueError(f"mel_fb must be [n_fft // 2 + 1 = {self.n_freqs}, n_mels]")
+            self.mel_fb = fb.contiguous()
+            self.n_mels = n_mels = int(fb.shape[1])
+        elif spec_type == "mel":  # heavy.py:57-68
+            self.mel_fb = filterbanks.melscale_fbanks(
                 self.n_freqs, float(f_min), float(f_max if f_max is not None else sample_rate // 2),
-                int(n_mels), int(sample_rate))
+                int(n_mels), int(sample_rate), norm, mel_scale)
         elif spec_type == "mel-librosa":  # heavy.py:69-100
             self.mel_fb = filterbanks.librosa_mel_basis(int(sample_rate), self.n_fft, int(n_mels), f_min, f_max)
         else:
@@ -261,8 +286,11 @@ class SpectralTransform:
         return p
 
     def num_frames(self, n_samples: int, keep_last=False) -> int:
-        """``L // hop`` (what ``process_spec`` keeps, preprocessor.py:921) or ``L // hop + 1``."""
-        return int(n_samples) // self.hop_length + (1 if keep_last else 0)
+        """``L // hop`` (what ``process_spec`` keeps, preprocessor.py:921) or what ``torch.stft(center=True)`` yields:
+        ``1 + (L + 2 * (n_fft // 2) - n_fft) // hop`` (= ``L // hop + 1`` for even ``n_fft``)."""
+        if keep_last:
+            return 1 + (int(n_samples) + 2 * (self.n_fft // 2) - self.n_fft) // self.hop_length
+        return int(n_samples) // self.hop_length
 
     def make_batch(self, sample_offsets, device=None, apply_log=True, keep_last=False,
                    sample_dtype=torch.float32) -> RaggedBatch:

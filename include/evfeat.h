@@ -40,10 +40,10 @@ extern "C" {
 typedef enum evf_status {
   EVF_OK = 0,
   EVF_ERR_INVALID_ARGUMENT = 1,
-  EVF_ERR_UNSUPPORTED = 2,   /* e.g. n_fft not in {1024, 2048}, spec_type unknown */
+  EVF_ERR_UNSUPPORTED = 2,   /* spec_type unknown; n_fft > 14 000 (no such audio config) */
   EVF_ERR_SHORT_INPUT = 3,   /* an utterance has L <= n_fft/2: reflect padding undefined
                                 (torch.stft raises RuntimeError for the same input)       */
-  EVF_ERR_FILTERBANK = 4,    /* mel filterbank is not a bank of adjacent triangular filters */
+  EVF_ERR_FILTERBANK = 4,    /* (no longer returned: a bank that is not triangular runs as a dense projection) */
   EVF_ERR_CUDA = 5,          /* a CUDA runtime call failed; see evf_last_error()          */
   EVF_ERR_NO_DEVICE = 6,     /* no sm_100 device: this library has no other code path     */
   EVF_ERR_OUT_OF_MEMORY = 7
@@ -57,6 +57,14 @@ typedef enum evf_spec_type {
   EVF_SPEC_RAW = 3           /* "raw"          utils/heavy.py:107-113 (complex STFT, no log/energy)   */
 } evf_spec_type;
 
+/* Which FFT kernel a plan uses.  AUTO: the warp-per-FFT kernel for n_fft 1024 (hop <= n_fft) and 2048 (even hop),
+ * the any-size shared-memory mixed-radix kernel for every other n_fft / hop torch.stft accepts.  GENERIC forces the
+ * any-size kernel (the parity tests cross-check the two implementations against each other). */
+typedef enum evf_fft_path {
+  EVF_FFT_AUTO = 0,
+  EVF_FFT_GENERIC = 1
+} evf_fft_path;
+
 typedef enum evf_sample_format {
   EVF_SAMPLES_F32 = 0,       /* float32 in [-1, 1] (what torchaudio.load returns)                   */
   EVF_SAMPLES_S16 = 1        /* PCM16 as stored by process_audio; converted as s / 32768.0f on load */
@@ -67,7 +75,7 @@ typedef enum evf_sample_format {
 typedef struct evf_config {
   int32_t spec_type;      /* evf_spec_type                                                     */
   int32_t sample_rate;    /* informational (the mel basis is passed in explicitly)             */
-  int32_t n_fft;          /* 1024 or 2048 (n_fft 2048 needs an even hop)                                      */
+  int32_t n_fft;          /* any n_fft >= 1 torch.stft accepts (up to 14 000)                  */
   int32_t win_length;     /* <= n_fft; informational (window is passed in explicitly)          */
   int32_t hop_length;     /* fft_hop_size                                                      */
   int32_t n_mels;         /* rows of the mel basis; ignored for linear / raw                   */
@@ -79,6 +87,7 @@ typedef struct evf_config {
                              1: T = L // hop + 1 (what the bare transform returns)             */
   int32_t sample_format;  /* evf_sample_format                                                 */
   float   log_clip;       /* 1e-5f                                                             */
+  int32_t fft_path;       /* evf_fft_path; 0 = automatic                                       */
 } evf_config;
 
 typedef struct evf_plan evf_plan;
@@ -99,7 +108,8 @@ EVF_API int evf_plan_create(const evf_config* cfg, const float* window_host, con
 EVF_API int evf_plan_destroy(evf_plan* plan);
 /* floats written per frame: n_mels (mel types), n_fft/2+1 (linear), 2*(n_fft/2+1) (raw) */
 EVF_API int evf_plan_row_floats(const evf_plan* plan, int32_t* row_floats_out);
-/* frames produced for an utterance of n_samples (bit-exact with L // hop [+ 1]) */
+/* frames produced for an utterance of n_samples: L // hop (keep_last_frame 0), else what torch.stft(center=True)
+ * yields, 1 + (L + 2 * (n_fft // 2) - n_fft) // hop  (= L // hop + 1 for even n_fft) */
 EVF_API int64_t evf_plan_num_frames(const evf_plan* plan, int64_t n_samples);
 
 /* A ragged batch descriptor: utterance b occupies samples [sample_offsets[b],

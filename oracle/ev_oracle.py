@@ -334,7 +334,7 @@ def features_ragged(audios, transform, hop: int, durations=None):
 def truth_power_spectrogram(x: np.ndarray, n_fft: int, win_length: int, hop: int) -> np.ndarray:
     """|STFT|^2 in float64: periodic Hann of ``win_length`` zero-padded (centred) to
     ``n_fft``, reflect padding of ``n_fft//2``, frames ``t = 0 .. L//hop`` centred at
-    ``t*hop``.  Returns ``[n_fft//2+1, 1 + L//hop]``."""
+    ``t*hop``.  Returns ``[n_fft//2+1, T]`` with torch.stft's frame count ``T = 1 + (L + 2*(n_fft//2) - n_fft)//hop``."""
     x = np.asarray(x, dtype=np.float64)
     L = x.shape[-1]
     n = np.arange(win_length, dtype=np.float64)
@@ -343,7 +343,7 @@ def truth_power_spectrogram(x: np.ndarray, n_fft: int, win_length: int, hop: int
     win = np.zeros(n_fft)
     win[left : left + win_length] = w
     xp = np.pad(x, (n_fft // 2, n_fft // 2), mode="reflect")
-    T1 = 1 + L // hop
+    T1 = 1 + (L + 2 * (n_fft // 2) - n_fft) // hop  # == 1 + L // hop for even n_fft
     idx = np.arange(n_fft)[None, :] + hop * np.arange(T1)[:, None]
     frames = xp[idx] * win[None, :]
     X = np.fft.rfft(frames, axis=-1)

@@ -38,6 +38,19 @@ CONFIGS = {
     "B": (44100, 2048, 2048, 512, 128, 0, 8000),
     "Bfull": (44100, 2048, 2048, 512, 128, 0, 22050),
     "W": (22050, 1024, 800, 200, 80, 0, 8000),  # win_length < n_fft (window centre-padded)
+    # ---- the rest of the config-field domain (any-size FFT kernel) ----
+    "S512": (16000, 512, 512, 128, 80, 0, 8000),      # 16 kHz corpora
+    "W512": (16000, 512, 400, 160, 80, 0, 8000),      # win < n_fft, hop not a power of two
+    "R3": (16000, 3072, 3072, 768, 80, 0, 8000),      # "output" transform of a 16 -> 48 kHz vocoder config: 1024 * 3
+    "W3072": (16000, 3072, 2400, 600, 80, 0, 8000),
+    "H4096": (44100, 4096, 4096, 1024, 128, 0, 8000),
+    "W4096": (44100, 4096, 3000, 750, 128, 0, 11025),
+    "OddHop": (22050, 2048, 2048, 441, 80, 0, 8000),  # n_fft 2048 with an odd hop (20 ms)
+    "ST2": (16000, 2048, 1200, 300, 80, 0, 8000),     # StyleTTS2's spect_params (styletts2/utils.py:12-21)
+    "N400": (16000, 400, 400, 160, 80, 0, 8000),      # 25 ms / 10 ms frames: n_fft = 2^4 * 5^2
+    "O1001": (22050, 1001, 1001, 250, 40, 0, 8000),   # odd n_fft = 7 * 11 * 13: direct-DFT stages, 1 + (L - 1) // hop frames
+    "BigHop": (22050, 1024, 1024, 1024, 80, 0, 8000), # hop = n_fft: the warp kernel's input ring does not fit
+    "Gap": (22050, 512, 512, 700, 80, 0, 8000),       # hop > n_fft: samples between frames are skipped
 }
 SPEC_TYPES = ("mel", "mel-librosa", "linear", "raw")
 
@@ -106,8 +119,12 @@ def _keep(cname: str, st: str, iname: str) -> bool:
     if st in ("linear", "raw"):
         if cname == "Bfull":  # identical to B (only the mel basis differs)
             return False
-        if cname in ("B", "W"):
+        if cname in ("B", "W", "S512", "N400", "O1001", "Gap"):
             return iname in ("speech", "short")
+        if cname not in ("A",):  # the wide transforms: a few frames are enough to pin the bins
+            return iname == "short"
+    elif cname not in ("A", "B", "Bfull", "W"):
+        return iname != "white" or cname in ("S512", "O1001")
     return True
 
 

@@ -94,7 +94,9 @@ def test_argument_validation_needs_no_device(lib):
         c = _lib.evf_config(**cfg)
         return lib.evf_plan_create(C.byref(c), win.ctypes.data_as(C.c_void_p), None, 0, C.byref(handle))
 
-    assert create(n_fft=1000) == _lib.EVF_ERR_UNSUPPORTED and b"n_fft" in lib.evf_last_error()
+    assert create(n_fft=0) == _lib.EVF_ERR_INVALID_ARGUMENT and b"n_fft" in lib.evf_last_error()
+    assert create(n_fft=1000, win_length=1024) == _lib.EVF_ERR_INVALID_ARGUMENT   # win_length > n_fft
+    assert create(fft_path=7) == _lib.EVF_ERR_INVALID_ARGUMENT
     assert create(spec_type=9) == _lib.EVF_ERR_UNSUPPORTED
     assert create(hop_length=0) == _lib.EVF_ERR_INVALID_ARGUMENT
     assert create(spec_type=0) == _lib.EVF_ERR_INVALID_ARGUMENT  # mel without a filterbank
@@ -130,4 +132,4 @@ def test_sass_is_sm100a_with_bulk_copy(lib):
     archs = set(re.findall(r"sm_\d+a?", r.stdout))
     assert archs == {"sm_100a"}, archs
     sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
-    assert "features_kernel" in sass and "UBLKCP" in sass and "SYNCS" in sass
+    assert "features_kernel" in sass and "features_generic_kernel" in sass and "UBLKCP" in sass and "SYNCS" in sass

@@ -29,7 +29,9 @@ def assert_log_spec_close(ours: torch.Tensor, ref: torch.Tensor, truth: np.ndarr
     6.8e-3, with equal RMS error -- two correct fp32 FFTs cannot agree to 1e-3 on those bins.
     The bar for ``linear`` is therefore:
       * every bin with exact log-power >= -3: within 1e-3 of the reference;
-      * weaker bins: within 1e-2 of the reference, fewer than 1 % beyond 1e-3;
+      * weaker bins: within 1e-2 of the reference -- or, for the larger transforms whose round-off floor is higher
+        (n_fft 3072 / 4096: the reference itself is 1.0e-2 from the truth there, profiles/r02c_err_stats_wide.txt),
+        within 2.5x the reference's own worst error -- and fewer than 1 % beyond 1e-3;
       * accuracy no worse than the reference's: RMS error against the float64 truth
         <= 1.5x the reference's + 1e-5 (1 % of the tolerance: when every bin is strong both
         implementations sit at 1e-6 and the ratio of two round-off levels means nothing),
@@ -43,10 +45,10 @@ def assert_log_spec_close(ours: torch.Tensor, ref: torch.Tensor, truth: np.ndarr
     strong = t >= -3.0
     if bool(strong.any()):
         assert float(d[strong].max()) <= ATOL_LOG, float(d[strong].max())
-    assert float(d.max()) <= 1e-2, float(d.max())
-    assert float((d > ATOL_LOG).float().mean()) < 1e-2
     ours_err = (ours.double() - t).abs()
     ref_err = (ref.double() - t).abs()
+    assert float(d.max()) <= max(1e-2, 2.5 * float(ref_err.max())), (float(d.max()), float(ref_err.max()))
+    assert float((d > ATOL_LOG).float().mean()) < 1e-2
     assert float(ours_err.pow(2).mean().sqrt()) <= 1.5 * float(ref_err.pow(2).mean().sqrt()) + 1e-5
     assert float(ours_err.max()) <= max(3.0 * float(ref_err.max()), ATOL_LOG)
 
@@ -98,19 +100,19 @@ def test_golden_log_spec_and_energy(cuda_device, golden_dir, config, spec_type):
         assert float((energy - ref_e).abs().max()) <= ATOL_LOG
         # the bare transform returns T + 1 linear-domain frames; check the one process_spec drops
         lin = tf(xt)
-        assert lin.shape[-1] == T + 1
+        assert lin.shape[-1] == 1 + (len(x) + 2 * (n_fft // 2) - n_fft) // hop   # T + 1 for even n_fft
         ref_last = torch.from_numpy(gold[f"{spec_type}/{name}/lin_last"])
         log_last = torch.log(torch.clamp(lin[:, -1], min=1e-5))
         truth_last = None
         if spec_type == "linear":
             # same criterion as the kept frames: weak bins of a linear spectrogram sit in the reference's own fp32 noise
-            truth_last = np.log(np.maximum(O.truth_power_spectrogram(x, n_fft, win, hop)[:, T], 1e-5))
+            truth_last = np.log(np.maximum(O.truth_power_spectrogram(x, n_fft, win, hop)[:, lin.shape[-1] - 1], 1e-5))
         assert_log_spec_close(log_last, torch.log(torch.clamp(ref_last, min=1e-5)), truth_last, spec_type)
         n_checked += 1
     assert n_checked >= 1 or (config == "Bfull" and spec_type == "linear")
 
 
-@pytest.mark.parametrize("config", ["A", "B", "W"])
+@pytest.mark.parametrize("config", [c for c in CONFIGS if c != "Bfull"])
 def test_golden_raw_complex(cuda_device, golden_dir, config):
     gold = np.load(golden_dir / f"spectral_{config}.npz")
     tf, hop = _transform(config, "raw")
@@ -142,7 +144,7 @@ def _ragged_inputs(sr, hop, n_utts, seed, max_s=3.0):
     return xs
 
 
-@pytest.mark.parametrize("config", ["A", "B", "Bfull", "W"])
+@pytest.mark.parametrize("config", list(CONFIGS))
 @pytest.mark.parametrize("spec_type", ["mel", "mel-librosa", "linear"])
 def test_ragged_batch_matches_oracle(cuda_device, config, spec_type):
     import everyvoice_b200 as ev
@@ -167,6 +169,77 @@ def test_ragged_batch_matches_oracle(cuda_device, config, spec_type):
         assert_log_spec_close(spec, o_spec, truth, spec_type)
         worst_e = max(worst_e, float((energy - o_energy).abs().max()))
     assert worst_e <= ATOL_LOG, worst_e
+
+
+@pytest.mark.parametrize("config", ["A", "B", "W", "ST2"])
+@pytest.mark.parametrize("spec_type", SPEC_TYPES)
+def test_warp_kernel_and_any_size_kernel_agree(cuda_device, config, spec_type):
+    """Two independent FFT implementations behind one plan interface (evf_fft_path): the warp-per-FFT kernel and the
+    shared-memory mixed-radix kernel compute the same transform on the sizes both cover."""
+    import everyvoice_b200 as ev
+    from everyvoice_b200 import synth
+
+    sr, n_fft, win, hop, n_mels, f_min, f_max = CONFIGS[config]
+    xs = _ragged_inputs(sr, hop, 9, seed=19, max_s=1.5)
+    packed, offsets = synth.pack_ragged(xs)
+    x = torch.from_numpy(packed).to(cuda_device)
+    fast = ev.SpectralTransform(spec_type, n_fft, win, hop, sr, n_mels, f_min, f_max)
+    slow = ev.SpectralTransform(spec_type, n_fft, win, hop, sr, n_mels, f_min, f_max, fft_path="generic")
+    a, b = fast.features_ragged(x, offsets), slow.features_ragged(x, offsets)
+    assert np.array_equal(a.frame_offsets, b.frame_offsets)
+    if spec_type == "raw":
+        scale = float(a.spec.abs().max())
+        assert float((a.spec - b.spec).abs().max()) <= 4e-6 * scale + 1e-5
+    elif spec_type == "linear":   # weak bins sit at the float32 round-off floor of either FFT: compare powers
+        pa, pb = torch.exp(a.spec), torch.exp(b.spec)
+        assert float((pa - pb).abs().max()) <= 2e-5 * float(pa.max())
+        assert float((a.energy - b.energy).abs().max()) <= 2e-2
+    else:
+        assert float((a.spec - b.spec).abs().max()) <= ATOL_LOG
+        assert float((a.energy - b.energy).abs().max()) <= ATOL_LOG
+
+
+def test_dense_projection_for_a_bank_that_is_not_triangular(cuda_device):
+    """Any [n_freq, n_mels] basis is accepted: overlapping / negative / random filters take the dense projection of
+    the any-size kernel (a triangular bank takes the sparse one); both against a float64 matmul of the power
+    spectrogram."""
+    import everyvoice_b200 as ev
+    from everyvoice_b200 import synth
+    from oracle import ev_oracle as O
+
+    sr, n_fft, win, hop = 22050, 1024, 1024, 256
+    rng = np.random.default_rng(77)
+    fb = rng.uniform(-0.2, 1.0, size=(n_fft // 2 + 1, 24)).astype(np.float32)
+    x = synth.speech_like(60 * hop, sr, seed=5)
+    P = O.truth_power_spectrogram(x, n_fft, win, hop)                      # [513, T + 1] float64
+    want = fb.astype(np.float64).T @ P
+    tf = ev.SpectralTransform("mel", n_fft, win, hop, sr, mel_fb=fb)
+    got = tf(torch.from_numpy(x).to(cuda_device)).cpu().double().numpy()   # linear domain, T + 1 frames
+    assert got.shape == want.shape == (24, 61)
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+    # and a triangular bank handed over explicitly equals the built-in one bit for bit
+    tri = ev.SpectralTransform("mel", n_fft, win, hop, sr, 80, 0, 8000)
+    same = ev.SpectralTransform("mel", n_fft, win, hop, sr, mel_fb=tri.mel_fb)
+    xd = torch.from_numpy(x).to(cuda_device)
+    assert torch.equal(tri(xd), same(xd))
+
+
+def test_misaligned_sample_buffer_view(cuda_device):
+    """A contiguous view that does not start on a 16-byte boundary (wav[1:], pcm[3:]) keeps its odd data_ptr: the
+    bulk-copy staging must notice and fall back to element loads (advisor finding, round 1)."""
+    from everyvoice_b200 import synth
+
+    tf, hop = _transform("A", "mel")
+    x = torch.from_numpy(synth.speech_like(40 * hop + 8, 22050, seed=9)).to(cuda_device)
+    pcm = (x * 30000).round().to(torch.int16)
+    for buf, shifts in ((x, (1, 2, 3)), (pcm, (1, 3, 5, 7))):
+        for s in shifts:
+            view = buf[s:]
+            assert view.data_ptr() % 16 != 0
+            L = view.numel()
+            got = tf.features_ragged(view, np.array([0, L]))
+            ref = tf.features_ragged(view.clone(), np.array([0, L]))     # a fresh, aligned allocation
+            assert torch.equal(got.spec, ref.spec) and torch.equal(got.energy, ref.energy)
 
 
 def test_int16_input_equals_float_input(cuda_device):
@@ -457,9 +530,10 @@ def test_error_behaviour(cuda_device):
         tf(torch.zeros(512, device=cuda_device))
     assert ei.value.status == _lib.EVF_ERR_SHORT_INPUT
     assert tf(torch.zeros(513, device=cuda_device)).shape == (80, 3)
-    bad = ev.get_spectral_transform("mel", 1000, 1000, 250, 22050, 80, 0, 8000)
+    # every n_fft torch.stft accepts has a kernel; only absurd sizes (no audio config) are refused
+    huge = ev.get_spectral_transform("linear", 20000, 20000, 5000)
     with pytest.raises(_lib.EvfError) as ei:
-        bad(torch.zeros(4000, device=cuda_device))
+        huge(torch.zeros(40000, device=cuda_device))
     assert ei.value.status == _lib.EVF_ERR_UNSUPPORTED
     assert ev.get_spectral_transform("istft", 1024, 1024, 256) is None
     assert ev.get_spectral_transform("nope", 1024, 1024, 256) is None

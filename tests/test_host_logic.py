@@ -60,6 +60,17 @@ def test_frame_arithmetic_is_the_references():
     assert tf.n_rows == 80 and tf.n_freqs == 513 and not tf.is_complex
     lin = ev.get_spectral_transform("linear", 2048, 2048, 512)
     assert lin.n_rows == 1025 and lin.mel_fb is None
+    # odd n_fft: torch.stft pads n_fft // 2 on both sides, so the bare transform has 1 + (L - 1) // hop frames
+    from oracle import ev_oracle as O
+
+    for n_fft, hop in ((1001, 250), (15, 4), (401, 160)):
+        odd = ev.get_spectral_transform("linear", n_fft, n_fft, hop)
+        ref = O.get_spectral_transform("linear", n_fft, n_fft, hop)
+        for L in (n_fft // 2 + 1, 4 * hop, 4 * hop + 1, 7 * hop - 1, 1234):
+            if L <= n_fft // 2:
+                continue
+            assert odd.num_frames(L, keep_last=True) == ref(torch.zeros(L)).shape[-1], (n_fft, hop, L)
+            assert odd.num_frames(L) == L // hop <= odd.num_frames(L, keep_last=True)
     assert ev.get_spectral_transform("raw", 1024, 1024, 256).is_complex
 
 

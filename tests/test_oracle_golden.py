@@ -52,7 +52,7 @@ def test_oracle_reproduces_reference_log_spec_and_energy(golden_dir, config, spe
     assert n >= 1 or (config == "Bfull" and spec_type == "linear")
 
 
-@pytest.mark.parametrize("config", ["A", "B", "W"])
+@pytest.mark.parametrize("config", [c for c in CONFIGS if c != "Bfull"])
 def test_oracle_reproduces_reference_raw_stft(golden_dir, config):
     gold = np.load(golden_dir / f"spectral_{config}.npz")
     tf, hop = _tf(config, "raw")
@@ -63,7 +63,8 @@ def test_oracle_reproduces_reference_raw_stft(golden_dir, config):
         out = tf(torch.from_numpy(x))
         ref = torch.complex(torch.from_numpy(gold[f"raw/{name}/re"]), torch.from_numpy(gold[f"raw/{name}/im"]))
         assert out.dtype == torch.complex64 and tuple(out.shape) == tuple(ref.shape)
-        assert out.shape[-1] == len(x) // hop + 1
+        n_fft = CONFIGS[config][1]
+        assert out.shape[-1] == 1 + (len(x) + 2 * (n_fft // 2) - n_fft) // hop   # == L // hop + 1 for even n_fft
         assert float((out - ref).abs().max()) <= 1e-6 * float(ref.abs().max()) + 1e-6
         n += 1
     assert n >= 1
@@ -159,3 +160,37 @@ def test_process_spec_drops_last_frame_and_requires_reflectable_input():
     assert tf(torch.zeros(513)).shape == (80, 3)
     assert O.get_spectral_transform("istft", 1024, 1024, 256) is None
     assert set(SPEC_TYPES) == set(O.SPEC_TYPES)
+
+
+LJ_NAMES = ["LJ050-0269", "LJ050-0270", "LJ050-0271", "LJ050-0272", "LJ050-0273"]
+
+
+@pytest.mark.parametrize("spec_type", ["mel-librosa", "mel"])
+def test_oracle_reproduces_config1_bundled_lj_dataset(golden_dir, spec_type):
+    """BASELINE configs[0]: the reference's own 5-utterance LJ dataset through process_audio -> PCM16 wav ->
+    process_spec -> process_energy (real duration.pt) -> Scaler, generated by the live reference
+    (oracle/make_golden_lj.py)."""
+    gold = np.load(golden_dir / "lj_config1.npz")
+    durs = np.load(golden_dir / "lj_durations.npz")
+    tf = O.get_spectral_transform(spec_type, 1024, 1024, 256, 22050, 80, 0, 8000)
+    scaler = O.Scaler()
+    phones = {}
+    for name in LJ_NAMES:
+        x = gold[f"{name}/wav"].astype(np.float32) / np.float32(32768.0)
+        audio, sr = O.process_audio_tensor(x, 22050, resample_rate=22050, hop_size=256)
+        pcm = O.pcm16(audio)
+        assert sr == 22050 and np.array_equal(pcm, gold[f"{name}/pcm16"])
+        spec, energy, phone = O.features_one(torch.from_numpy(pcm.astype(np.float32) / np.float32(32768.0)), tf, 256,
+                                             torch.from_numpy(durs[name]))
+        assert float((spec - torch.from_numpy(gold[f"{spec_type}/{name}/spec"])).abs().max()) <= ATOL_SAME_ALGO
+        assert float((energy - torch.from_numpy(gold[f"{spec_type}/{name}/energy"])).abs().max()) <= 1e-4
+        assert np.allclose(phone.numpy(), gold[f"{spec_type}/{name}/phone"], atol=1e-4, equal_nan=True)
+        scaler.append(phone)
+        phones[name] = phone
+    stats = scaler.calculate_stats()
+    assert stats["sample_size"] == 5
+    for k in ("min", "max", "mean", "std", "norm_min", "norm_max"):
+        assert stats[k] == pytest.approx(float(gold[f"{spec_type}/stats/{k}"]), abs=1e-4)
+    for name in LJ_NAMES:
+        assert np.allclose(scaler.normalize(phones[name]).numpy(), gold[f"{spec_type}/{name}/phone_norm"], atol=1e-4,
+                           equal_nan=True)

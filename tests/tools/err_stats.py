@@ -9,7 +9,11 @@ from everyvoice_b200 import synth
 from oracle import ev_oracle as O
 
 dev = torch.device("cuda", 0)
-for cfg_name, (sr, n_fft, win, hop, n_mels) in {"A": (22050, 1024, 1024, 256, 80), "B": (44100, 2048, 2048, 512, 128)}.items():
+CASES = {"A": (22050, 1024, 1024, 256, 80), "B": (44100, 2048, 2048, 512, 128)}
+if "--wide" in sys.argv:   # the any-size kernel on the largest / smallest transforms
+    CASES = {"H4096": (44100, 4096, 4096, 1024, 128), "W4096": (44100, 4096, 3000, 750, 128), "S512": (16000, 512, 512, 128, 80),
+             "R3": (16000, 3072, 3072, 768, 80)}
+for cfg_name, (sr, n_fft, win, hop, n_mels) in CASES.items():
     for st in ("linear", "mel"):
         tf = ev.get_spectral_transform(st, n_fft, win, hop, sr, n_mels, 0, 8000).to(dev)
         otf = O.get_spectral_transform(st, n_fft, win, hop, sr, n_mels, 0, 8000)
