@@ -35,22 +35,12 @@ def assert_log_spec_close(ours: torch.Tensor, ref: torch.Tensor, truth: np.ndarr
       * accuracy no worse than the reference's: RMS error against the float64 truth
         <= 1.5x the reference's + 1e-5 (1 % of the tolerance: when every bin is strong both
         implementations sit at 1e-6 and the ratio of two round-off levels means nothing),
-        max error <= max(3x the reference's, 1e-3)."""
-    assert tuple(ours.shape) == tuple(ref.shape)
-    d = (ours - ref).abs()
-    if spec_type != "linear" or truth is None:
-        assert float(d.max()) <= ATOL_LOG, float(d.max())
-        return
-    t = torch.from_numpy(truth).to(torch.float64)
-    strong = t >= -3.0
-    if bool(strong.any()):
-        assert float(d[strong].max()) <= ATOL_LOG, float(d[strong].max())
-    ours_err = (ours.double() - t).abs()
-    ref_err = (ref.double() - t).abs()
-    assert float(d.max()) <= max(1e-2, 2.5 * float(ref_err.max())), (float(d.max()), float(ref_err.max()))
-    assert float((d > ATOL_LOG).float().mean()) < 1e-2
-    assert float(ours_err.pow(2).mean().sqrt()) <= 1.5 * float(ref_err.pow(2).mean().sqrt()) + 1e-5
-    assert float(ours_err.max()) <= max(3.0 * float(ref_err.max()), ATOL_LOG)
+        max error <= max(3x the reference's, 1e-3), or -- the max over ~1e5 bins being an extreme-value statistic -- the
+        offending bin's error in the amplitude domain below 16 float32 eps of the frame's RMS amplitude."""
+    from parity_pool import log_spec_mismatch   # one statement of the criterion, shared with the every-utterance checker
+
+    why = log_spec_mismatch(ours, ref, truth, spec_type)
+    assert why is None, why
 
 
 def _transform(config, spec_type):
@@ -546,7 +536,7 @@ def test_error_behaviour(cuda_device):
 
 
 # ------------------------------------------------------------------------------------------
-# BASELINE.json full sizes: size-independent properties (the oracle is too slow here)
+# BASELINE.json full sizes: every utterance against the oracle on all host cores, plus size-independent properties
 # ------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def full_size_batch(cuda_device):
@@ -564,21 +554,33 @@ def full_size_batch(cuda_device):
     return lens, off, x
 
 
-def test_full_size_frame_counts_and_sampled_oracle(cuda_device, full_size_batch):
+def _assert_every_utterance_matches_oracle(x, off, feats, cfg, spec_type, durations=None, phone_off=None, phone=None):
+    """All utterances, all frames, against the oracle on every host core (tests/parity_pool.py)."""
+    from parity_pool import compare_all
+
+    res = compare_all(x.cpu().numpy(), off, feats.spec.cpu().numpy(), feats.energy.cpu().numpy(), feats.frame_offsets,
+                      cfg, spec_type, durations, phone_off, None if phone is None else phone.cpu().numpy())
+    assert res["utterances"] == len(off) - 1 and res["frames"] == int(feats.frame_offsets[-1])
+    assert not res["failures"], res["failures"][:5]
+    return res
+
+
+def test_full_size_every_utterance_matches_oracle(cuda_device, full_size_batch):
+    """BASELINE configs[1] at full size: ALL 1 000 utterances / 470 190 frames of log-mel, energy and phone-level
+    averages against the oracle (north_star: 1e-3; frame counts and NaN positions exact)."""
     import everyvoice_b200 as ev
-    from oracle import ev_oracle as O
+    from everyvoice_b200 import synth
 
     lens, off, x = full_size_batch
-    tf = ev.get_spectral_transform("mel", 1024, 1024, 256, 22050, 80, 0, 8000).to(cuda_device)
-    feats = tf.features_ragged(x, off)
+    pre = ev.Preprocessor(ev.AudioConfig(spec_type="mel"), device=cuda_device)
+    feats = pre.process_spec_batch(x, off)
     assert np.array_equal(np.diff(feats.frame_offsets), lens // 256)      # bit-exact T = L // hop for all 1 000
     assert feats.spec.shape == (int((lens // 256).sum()), 80) == (470190, 80)
     assert bool(torch.isfinite(feats.spec).all()) and float(feats.spec.min()) >= np.log(1e-5) - 1e-6
-    otf = O.get_spectral_transform("mel", 1024, 1024, 256, 22050, 80, 0, 8000)
-    for b in (0, 50, 333, 500, 999):  # a sample of utterances against the oracle (first, last, speech-like, noise)
-        o_spec, o_energy, _ = O.features_one(x[off[b] : off[b + 1]].cpu(), otf, 256)
-        assert float((feats.utterance(b).cpu() - o_spec).abs().max()) <= ATOL_LOG
-        assert float((feats.utterance_energy(b).cpu() - o_energy).abs().max()) <= ATOL_LOG
+    d_packed, p_off = synth.pack_ragged([synth.synthetic_durations(int(L) // 256, seed=1234 + i) for i, L in enumerate(lens)])
+    phone, _ = pre.process_energy_batch(feats, torch.from_numpy(d_packed.astype(np.int64)), p_off)
+    res = _assert_every_utterance_matches_oracle(x, off, feats, CONFIGS["A"], "mel", d_packed, p_off, phone)
+    assert res["max_spec"] <= ATOL_LOG and res["max_energy"] <= ATOL_LOG and res["max_phone"] <= ATOL_LOG
 
 
 def test_full_size_energy_is_norm_of_log_spec_and_checksums(cuda_device, full_size_batch):
@@ -667,9 +669,9 @@ def test_full_size_phone_average_round_trip(cuda_device, full_size_batch):
 
 
 @pytest.mark.parametrize("config,spec_type", [("B", "mel"), ("A", "linear"), ("A", "mel-librosa")])
-def test_other_baseline_configs_sampled_oracle(cuda_device, config, spec_type):
+def test_other_baseline_configs_every_utterance(cuda_device, config, spec_type):
     """configs[2] (44.1 kHz / 2048 / 512 / 128 mels) and configs[3] (linear + energy) at 200
-    ragged utterances: exact frame counts everywhere, oracle parity on a sample."""
+    ragged utterances: exact frame counts and oracle parity on every utterance."""
     import everyvoice_b200 as ev
     from everyvoice_b200 import synth
     from oracle import ev_oracle as O
@@ -683,13 +685,7 @@ def test_other_baseline_configs_sampled_oracle(cuda_device, config, spec_type):
     tf = ev.get_spectral_transform(spec_type, n_fft, win, hop, sr, n_mels, f_min, f_max).to(cuda_device)
     feats = tf.features_ragged(x, off)
     assert np.array_equal(np.diff(feats.frame_offsets), lens // hop)
-    otf = O.get_spectral_transform(spec_type, n_fft, win, hop, sr, n_mels, f_min, f_max)
-    for b in (0, 99, 199):
-        xb = x[off[b] : off[b + 1]].cpu()
-        o_spec, o_energy, _ = O.features_one(xb, otf, hop)
-        truth = O.truth_features(xb.numpy(), spec_type, n_fft, win, hop, sr, n_mels, f_min, f_max)[0] if spec_type == "linear" else None
-        assert_log_spec_close(feats.utterance(b).cpu(), o_spec, truth, spec_type)
-        assert float((feats.utterance_energy(b).cpu() - o_energy).abs().max()) <= ATOL_LOG
+    _assert_every_utterance_matches_oracle(x, off, feats, CONFIGS[config], spec_type)
 
 
 def test_config5_rank_shard_of_100h_corpus(cuda_device):
@@ -723,11 +719,8 @@ def test_config5_rank_shard_of_100h_corpus(cuda_device):
     assert np.array_equal(np.diff(feats.frame_offsets), T) and feats.spec.shape == (int(T.sum()), 80)
     e_torch = torch.linalg.norm(feats.spec, dim=1)
     assert float((feats.energy - e_torch).abs().max()) <= 2e-5 * float(e_torch.max())
-    otf = O.get_spectral_transform("mel", 1024, 1024, hop, sr, 80, 0, 8000)
-    for b in (0, len(lens) // 2, len(lens) - 1):
-        o_spec, o_energy, _ = O.features_one(x[off[b] : off[b + 1]].cpu(), otf, hop)
-        assert float((feats.utterance(b).cpu() - o_spec).abs().max()) <= ATOL_LOG
-        assert float((feats.utterance_energy(b).cpu() - o_energy).abs().max()) <= ATOL_LOG
+    res = _assert_every_utterance_matches_oracle(x, off, feats, CONFIGS["A"], "mel")     # all ~8.2 k utterances
+    assert res["max_spec"] <= ATOL_LOG and res["max_energy"] <= ATOL_LOG
     # statistics of the frame-level energy: 8 logical shards -> [8, 5] summaries -> merged == one global pass
     f_off = feats.frame_offsets
     cuts = [int(f_off[i]) for i in np.linspace(0, len(lens), world + 1).astype(int)]
