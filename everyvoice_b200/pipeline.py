@@ -86,22 +86,29 @@ class CorpusPipeline:
         self.total_samples = int(off[-1] - off[0])
         esize = 2 if sample_dtype == torch.int16 else 4
         # ---- chunk plan: consecutive utterances, about chunk_bytes of samples each ---------------
-        # ONE batch descriptor for the shard; chunks are utterance ranges of it (evf_features_run_range)
-        self.batch = transform.make_batch(off - off[0], self.device, apply_log=True, keep_last=False,
-                                          sample_dtype=sample_dtype)
-        assert np.array_equal(self.batch.frame_offsets, self.frame_offsets)
+        # Small chunks at both ends: the first kernel waits for the first chunk's H2D and the last D2H for the last
+        # chunk's kernel, so the pipeline's fill and drain shrink with them (chunk_bytes / 8, / 4, / 2 ... / 2, / 4, / 8).
+        # ONE batch descriptor for the shard (built lazily by run(), after the first copies are in flight); chunks
+        # are utterance ranges of it (evf_features_run_range)
+        self._batch = None
         self.chunks: list[_Chunk] = []
-        limit = max(1, chunk_bytes // esize)
+        full = max(1, chunk_bytes // esize)
         align = 16 // esize
+        total = int(off[-1] - off[0])
         u = 0
+        ramp = full // 8
         while u < self.n_utts:
+            left = total - int(off[u] - off[0])
+            limit = max(1, min(ramp, full, max(left // 2, full // 8)))
+            ramp *= 2
             v = int(np.searchsorted(off, off[u] + limit, side="right")) - 1   # last v with off[v] - off[u] <= limit
             v = min(max(v, u + 1), self.n_utts)
             s0 = int(off[u] - off[0])
             self.chunks.append(_Chunk(u, v, s0, int(off[v] - off[0]), int(self.frame_offsets[u]),
                                       int(self.frame_offsets[v]), s0 % align))
             u = v
-        self.row_floats = self.batch.plan.row_floats
+        self.row_floats = transform.plan(self.device, True, False,
+                                         _lib.SAMPLES_S16 if sample_dtype == torch.int16 else _lib.SAMPLES_F32).row_floats
         max_s = max((c.s1 - c.s0 + c.pad for c in self.chunks), default=0)
         max_f = max((c.f1 - c.f0 for c in self.chunks), default=0)
         self.want_energy = want_energy and not transform.is_complex
@@ -135,6 +142,16 @@ class CorpusPipeline:
         self.kernel_launches_per_run = len(self.chunks) * (2 if self.has_phones else 1) + (3 if self.has_phones else 0)
         self.esize = esize
 
+    @property
+    def batch(self) -> RaggedBatch:
+        """The shard's batch descriptor (tile work list, frame offsets): host index arithmetic plus one upload."""
+        if self._batch is None:
+            off = self.sample_offsets
+            self._batch = self.tf.make_batch(off - off[0], self.device, apply_log=True, keep_last=False,
+                                             sample_dtype=self.sample_dtype)
+            assert np.array_equal(self._batch.frame_offsets, self.frame_offsets)
+        return self._batch
+
     # ------------------------------------------------------------------------------------------
     def run(self, host_samples: torch.Tensor, host_spec: torch.Tensor, host_energy: torch.Tensor | None = None,
             host_phone: torch.Tensor | None = None, normalize_phones: bool = True, group=None):
@@ -160,15 +177,25 @@ class CorpusPipeline:
                     self._d_durations[: self.n_phones].copy_(self._h_durations, non_blocking=True)
                     self._d_phone_off[: self.n_utts + 1].copy_(self._h_phone_off, non_blocking=True)
                 s_compute.wait_stream(s_in)
-            for i, c in enumerate(self.chunks):
-                b = i & 1
-                ns, nf = c.s1 - c.s0, c.f1 - c.f0
-                # -- H2D (buffer b is free once the kernels of chunk i-2 have consumed it)
+            def copy_in(i):
+                c, b = self.chunks[i], i & 1
+                # buffer b is free once the kernels of chunk i-2 have consumed it
                 if i >= 2:
                     s_in.wait_event(ev_comp[b])
                 with torch.cuda.stream(s_in):
-                    self._d_samples[b][c.pad : c.pad + ns].copy_(host_samples[h0 + c.s0 : h0 + c.s1], non_blocking=True)
+                    self._d_samples[b][c.pad : c.pad + c.s1 - c.s0].copy_(host_samples[h0 + c.s0 : h0 + c.s1],
+                                                                         non_blocking=True)
                     ev_in[b].record(s_in)
+
+            # the first two copies fly while the host builds the batch descriptor (tile list + one upload)
+            for i in range(min(2, len(self.chunks))):
+                copy_in(i)
+            batch = self.batch
+            for i, c in enumerate(self.chunks):
+                b = i & 1
+                ns, nf = c.s1 - c.s0, c.f1 - c.f0
+                if i >= 2:
+                    copy_in(i)
                 # -- kernels (output buffer b is free once chunk i-2 has been copied out)
                 s_compute.wait_event(ev_in[b])
                 if i >= 2:
@@ -179,12 +206,12 @@ class CorpusPipeline:
                 spec_base = self._d_spec[b].data_ptr() - c.f0 * self.row_floats * 4
                 energy_base = self._d_energy[b].data_ptr() - c.f0 * 4
                 need_energy = self.want_energy or self.has_phones
-                _lib.check(lib.evf_features_run_range(self.batch.plan.handle, self.batch.handle, c.u0, c.u1,
+                _lib.check(lib.evf_features_run_range(batch.plan.handle, batch.handle, c.u0, c.u1,
                                                       C.c_void_p(samples_base), C.c_void_p(spec_base),
                                                       C.c_void_p(energy_base if need_energy else 0), st))
                 if self.has_phones:
                     _lib.check(lib.evf_segment_mean(C.c_void_p(energy_base),
-                                                    C.c_void_p(self.batch.frame_offsets_dev_ptr + 8 * c.u0),
+                                                    C.c_void_p(batch.frame_offsets_dev_ptr + 8 * c.u0),
                                                     C.c_void_p(self._d_durations.data_ptr()),
                                                     C.c_void_p(self._d_phone_off.data_ptr() + 8 * c.u0),
                                                     c.u1 - c.u0, C.c_void_p(self._d_phone.data_ptr()), st))

@@ -63,7 +63,7 @@ def log_spec_mismatch(ours, ref, truth, spec_type: str):
     return None
 
 
-def _init(tmp, cfg, spec_type, with_phones):
+def _init(tmp, cfg, spec_type, with_phones, want_phone=False):
     import torch
 
     for p in (str(ROOT), str(ROOT / "tests")):
@@ -80,6 +80,7 @@ def _init(tmp, cfg, spec_type, with_phones):
               x=np.load(os.path.join(tmp, "x.npy"), mmap_mode="r"), off=np.load(os.path.join(tmp, "off.npy")),
               spec=np.load(os.path.join(tmp, "spec.npy"), mmap_mode="r"),
               energy=np.load(os.path.join(tmp, "energy.npy"), mmap_mode="r"), f_off=np.load(os.path.join(tmp, "f_off.npy")))
+    _W["want_phone"] = want_phone
     if with_phones:
         _W.update(dur=np.load(os.path.join(tmp, "dur.npy")), p_off=np.load(os.path.join(tmp, "p_off.npy")),
                   phone=np.load(os.path.join(tmp, "phone.npy")))
@@ -116,12 +117,12 @@ def _check(rng):
             d_p = float(np.abs(got[m] - want[m]).max()) if m.any() else 0.0
             if err is None and (not nan_ok or d_p > bar_e):
                 err = f"phone averages: NaN positions equal {nan_ok}, max |d| {d_p:.3e}"
-        out.append((b, err, d_s, d_e, d_p, f1 - f0))
+        out.append((b, err, d_s, d_e, d_p, f1 - f0, o_phone.numpy() if (dur is not None and _W.get('want_phone')) else None))
     return out
 
 
 def compare_all(x, off, spec, energy, f_off, cfg, spec_type, durations=None, phone_off=None, phone=None, workers=None,
-                utterances=None):
+                utterances=None, return_oracle_phone=False):
     """``x`` packed samples (float32 / int16 numpy), ``spec [frames, F]``, ``energy [frames]`` (numpy, ours).  Runs the
     oracle over every utterance (or ``utterances``) and returns ``dict(failures=[(b, why)], max_spec=, max_energy=,
     max_phone=, frames=, utterances=)``."""
@@ -143,13 +144,15 @@ def compare_all(x, off, spec, energy, f_off, cfg, spec_type, durations=None, pho
         else:
             chunks = [(b, b + 1) for b in idx]
         if workers == 1:
-            _init(tmp, cfg, spec_type, with_phones)
+            _init(tmp, cfg, spec_type, with_phones, return_oracle_phone)
             rows = [r for c in chunks for r in _check(c)]
         else:
-            with mp.get_context("spawn").Pool(workers, initializer=_init, initargs=(tmp, cfg, spec_type, with_phones)) as pool:
+            with mp.get_context("spawn").Pool(workers, initializer=_init, initargs=(tmp, cfg, spec_type, with_phones, return_oracle_phone)) as pool:
                 rows = [r for part in pool.map(_check, chunks) for r in part]
     ok = [r for r in rows if r[1] is None]
+    rows.sort(key=lambda r: r[0])
     return {
+        "oracle_phone": [r[6] for r in rows] if return_oracle_phone else None,
         "failures": [(r[0], r[1]) for r in rows if r[1] is not None],
         "max_spec": max((r[2] for r in ok), default=0.0), "max_energy": max((r[3] for r in rows), default=0.0),
         "max_phone": max((r[4] for r in rows), default=0.0), "frames": int(sum(r[5] for r in rows)),
