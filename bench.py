@@ -372,9 +372,11 @@ def run_reference_arm(args, w, wname):
 # our arm
 # ------------------------------------------------------------------------------------------------
 class DeviceJob:
-    """One rank's shard resident in HBM and the step over it.  With N > 1 the statistics exchange and the
-    normalisation of step i run on a side stream while the feature kernel of step i + 1 already runs on the main
-    stream (phone values / summaries are double-buffered): the all-gather's latency is off the critical path."""
+    """One rank's shard resident in HBM and the step over it.  Everything runs on ONE stream: overlapping the
+    statistics exchange of step i with the feature kernel of step i + 1 on a side stream was measured and is slower
+    (N = 2: 0.766 vs 0.720 ms per step, profiles/r02g_bench_n2_side_stream.json) -- the persistent feature kernel owns
+    every SM (148 CTAs x 64 K registers), so the NCCL kernel cannot co-reside and delays one CTA of a statically
+    partitioned grid instead."""
 
     def __init__(self, w, wname, rank, world, device, data):
         import torch
@@ -406,7 +408,7 @@ class DeviceJob:
         self.stats = [torch.empty(5, dtype=torch.float64, device=device) for _ in range(2)]
         self.gathered = [torch.empty((world, 5), dtype=torch.float64, device=device) for _ in range(2)] if world > 1 else None
         self.main = torch.cuda.current_stream(device)
-        self.side = torch.cuda.Stream(device) if world > 1 else None
+        self.side = None
         self.ev_stats = [torch.cuda.Event() for _ in range(2)]
         self.ev_norm = [torch.cuda.Event() for _ in range(2)]
         self.launches = 0
@@ -440,9 +442,14 @@ class DeviceJob:
                                         C.c_void_p(self.phone_offsets_dev.data_ptr()), len(self.lengths),
                                         C.c_void_p(phone.data_ptr()), st))                         # 1
         _lib.check(lib.evf_stats_partial(C.c_void_p(phone.data_ptr()), phone.numel(), C.c_void_p(stats.data_ptr()), 0, st))  # 2
-        if self.side is None:
+        if self.world == 1:
             _lib.check(lib.evf_normalize_by_stats(C.c_void_p(phone.data_ptr()), phone.numel(),
                                                   C.c_void_p(stats.data_ptr()), st))               # 1
+        elif self.side is None:
+            parts = allgather_stats(stats, out=self.gathered[b])                                   # ONE NCCL collective
+            _lib.check(lib.evf_normalize_by_gathered_stats(
+                C.c_void_p(phone.data_ptr()), phone.numel(), C.c_void_p(parts.data_ptr()), parts.shape[0],
+                parts.shape[1], st))                                                               # 1
         else:
             self.ev_stats[b].record(self.main)
             self.side.wait_event(self.ev_stats[b])
@@ -872,8 +879,8 @@ def run_ours(args, w, wname):
             "preprocess_flow": flow,
             "gpu_launches": launches,
             "clocks": clock_info,
-            "exchange": ("statistics all-gather + normalisation of step i on a side stream under the feature kernel of "
-                         "step i + 1 (double-buffered phone values)" if world > 1 else "none (N = 1)"),
+            "exchange": ("one all-gather of the 5-number summaries per step, on the compute stream" if world > 1
+                         else "none (N = 1)"),
         }
     del job
     torch.cuda.empty_cache()

@@ -29,7 +29,7 @@ SPEC_TYPES = {"mel": 0, "mel-librosa": 1, "linear": 2, "raw": 3}
 SAMPLES_F32, SAMPLES_S16 = 0, 1
 FFT_AUTO, FFT_GENERIC = 0, 1
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class evf_config(C.Structure):
@@ -88,7 +88,8 @@ PROTOTYPES = {
     "evf_audio_finalize": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, C.c_int64, _P, _P, _P, _P]),
     "evf_audio_loudness_scratch_floats": (C.c_int64, [C.c_int32, C.c_int64]),
     "evf_audio_loudness_step": (C.c_int32, [C.c_int32]),
-    "evf_audio_loudness": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P]),
+    "evf_audio_loudness": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int32, _P, C.c_float, C.c_float, _P, _P,
+                                     _P, _P, _P]),
 }
 
 

@@ -106,9 +106,54 @@ def _fmt(t: torch.Tensor) -> int:
     raise ValueError("samples must be float32 or int16 PCM")
 
 
-def loudness_batch(samples: torch.Tensor, offsets, sample_rate: int) -> torch.Tensor:
+_KW_CACHE: dict = {}
+
+
+def k_weighting_coefficients(sample_rate: int) -> np.ndarray:
+    """The ten float32 numbers of BS.1770's K-weighting as ``torchaudio.functional.loudness`` gets them:
+    ``treble_biquad(4 dB, 1500 Hz, Q = 1/sqrt(2))`` and ``highpass_biquad(38 Hz, Q = 0.5)``, each as
+    ``{b0, b1, b2, a1, a2} / a0`` (``_lfilter`` normalises first).  Evaluated with float32 torch tensor operations,
+    like torchaudio does, by whatever torch build is installed: torch's sin / cos / exp differ from libm's by an ulp
+    for some arguments, and the 38 Hz high-pass (double pole at 1 - 2 pi 38 / sr) turns that ulp into 1e-3 LKFS.
+    Host-side constants (ten scalars), no signal processing."""
+    sr = int(sample_rate)
+    if sr not in _KW_CACHE:
+        import math
+
+        t = lambda v: torch.as_tensor(v, dtype=torch.float32)  # noqa: E731
+        out = []
+        # treble_biquad
+        central_freq, Q, gain = t(1500.0), t(1 / math.sqrt(2)), t(4.0)
+        w0 = 2 * math.pi * central_freq / sr
+        alpha = torch.sin(w0) / 2 / Q
+        A = torch.exp(gain / 40 * math.log(10))
+        temp1 = 2 * torch.sqrt(A) * alpha
+        temp2 = (A - 1) * torch.cos(w0)
+        temp3 = (A + 1) * torch.cos(w0)
+        b = torch.stack([A * ((A + 1) + temp2 + temp1), -2 * A * ((A - 1) + temp3), A * ((A + 1) + temp2 - temp1)])
+        a = torch.stack([(A + 1) - temp2 + temp1, 2 * ((A - 1) - temp3), (A + 1) - temp2 - temp1])
+        out += (b / a[0]).tolist() + (a / a[0])[1:].tolist()
+        # highpass_biquad
+        cutoff_freq, Q = t(38.0), t(0.5)
+        w0 = 2 * math.pi * cutoff_freq / sr
+        alpha = torch.sin(w0) / 2.0 / Q
+        b0 = (1 + torch.cos(w0)) / 2
+        b = torch.stack([b0, -1 - torch.cos(w0), b0])
+        a = torch.stack([1 + alpha, -2 * torch.cos(w0), 1 - alpha])
+        out += (b / a[0]).tolist() + (a / a[0])[1:].tolist()
+        _KW_CACHE[sr] = np.asarray(out, dtype=np.float32)
+    return _KW_CACHE[sr]
+
+
+LOUDNESS_REFINE_BAND = 0.05  # LKFS: 25x the fast pass' error; inside it the exact pass decides
+
+
+def loudness_batch(samples: torch.Tensor, offsets, sample_rate: int, refine_band: float = LOUDNESS_REFINE_BAND,
+                   return_refined: bool = False):
     """``torchaudio.transforms.Loudness(sr)`` of every mono utterance of a packed float32 / int16 PCM device batch
-    (int16 is ``s / 32768``, what ``torchaudio.load`` returns for a PCM16 wav)."""
+    (int16 is ``s / 32768``, what ``torchaudio.load`` returns for a PCM16 wav).  Utterances within ``refine_band`` LKFS
+    of the -36 LKFS gate (or with a block that close to a block-gating threshold) are re-evaluated with the
+    reference's exact float32 arithmetic, so that the keep / skip decision is the reference's."""
     lib = _lib.load()
     device = samples.device
     offsets = np.ascontiguousarray(np.asarray(offsets, dtype=np.int64))
@@ -116,17 +161,19 @@ def loudness_batch(samples: torch.Tensor, offsets, sample_rate: int) -> torch.Te
     step = int(lib.evf_audio_loudness_step(int(sample_rate)))   # the 100 ms step in samples, as the library rounds it
     if step < 1:
         raise ValueError("unsupported sampling rate for the loudness measurement")
-    per = lens // step + 4                # == evf_audio_loudness_scratch_floats(sr, n) for every n
+    per = 5 * (lens // step + 5)          # == evf_audio_loudness_scratch_floats(sr, n) for every n
     s_off = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
     scratch = torch.empty(int(s_off[-1]), dtype=torch.float32, device=device)
     out = torch.empty(len(lens), dtype=torch.float32, device=device)
+    flags = torch.zeros(max(len(lens), 1), dtype=torch.int32, device=device)
+    coeffs = k_weighting_coefficients(sample_rate)
     d_off, d_soff = torch.from_numpy(offsets).to(device), torch.from_numpy(s_off).to(device)
     with torch.cuda.device(device):
         _lib.check(lib.evf_audio_loudness(_ptr(samples), _fmt(samples), _ptr(d_off), len(lens),
-                                          int(lens.max()) if len(lens) else 0,
-                                          int(sample_rate), _ptr(scratch),
-                                          _ptr(d_soff), _ptr(out), _stream_ptr(device)))
-    return out
+                                          int(lens.max()) if len(lens) else 0, int(sample_rate),
+                                          coeffs.ctypes.data_as(C.c_void_p), float(refine_band), LOUDNESS_GATE_LKFS,
+                                          _ptr(scratch), _ptr(d_soff), _ptr(flags), _ptr(out), _stream_ptr(device)))
+    return (out, flags[: len(lens)]) if return_refined else out
 
 
 def _consecutive_views(waves) -> bool:

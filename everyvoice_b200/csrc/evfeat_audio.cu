@@ -200,20 +200,23 @@ __global__ void __launch_bounds__(256) finalize_kernel(const SampleT* __restrict
 
 // ---- BS.1770-4 loudness (torchaudio.functional.loudness) ---------------------------------------
 struct Biquad {
-  float b0, b1, b2, a1, a2;  // already divided by a0
+  float b0, b1, b2, a1, a2;  // already divided by a0 (torchaudio's _lfilter normalises the coefficients first)
 };
 struct LoudnessParams {
   Biquad shelf, highpass;
-  int gate, step;  // gate == 4 * step
+  int gate, step;  // 400 ms block and 100 ms step in samples: round(0.4 sr), round(gate / 4); gate - 4 step is in [-2, 2]
 };
+constexpr int kLdRec = 5;  // scratch floats per step: sum of z^2, z^2 of its first two and of its last two samples
 
-// Pass 1, one thread per 100 ms step of one utterance: the two K-weighting biquads (torchaudio's lfilter(clamp=True)
+// Pass 1 (fast), one thread per 100 ms step of one utterance: the two K-weighting biquads (torchaudio's lfilter(clamp=True)
 // clamps each filter's OUTPUT to [-1, 1], the recursion itself runs on the unclamped state),
 // squared and summed over the step.  The recursion is sequential in time, so every thread starts one step early
 // from a zero state: the slowest pole of the 38 Hz high-pass (a double pole at 1 - 2*pi*38/sr) has decayed to
 // n * r^n < 1e-7 after one step at every sampling rate, i.e. below float32 resolution of the running state.
 // A block is ONE warp owning 32 consecutive steps; the 32 sample streams advance together in tiles of 64 samples
 // that the warp loads row by row (coalesced) into a padded shared-memory tile and each lane then reads along its row.
+// Accuracy: about 2e-3 LKFS against torchaudio (restart + transposed form); utterances whose gate decision could
+// depend on that are re-evaluated by loudness_exact_kernel.
 constexpr int kLdTile = 64;
 template <typename SampleT>
 __global__ void __launch_bounds__(32) loudness_partial_kernel(const SampleT* __restrict__ x,
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(32) loudness_partial_kernel(const SampleT* __r
   const int b = blockIdx.y;
   const SampleT* xs = x + off[b];
   const long long L = off[b + 1] - off[b];
-  const long long n_sub = L / P.step;
+  const long long n_sub = (L + P.step - 1) / P.step;  // the last, partial step too: a block may reach 2 samples into it
   const long long q0 = (long long)blockIdx.x * 32;
   if (q0 >= n_sub) return;
   const int lane = threadIdx.x;
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(32) loudness_partial_kernel(const SampleT* __r
   float s1a = 0.f, s2a = 0.f;   // shelf state
   float s1b = 0.f, s2b = 0.f;   // high-pass state (its input is the CLAMPED shelf output, like lfilter(clamp=True))
   const Biquad s = P.shelf, h = P.highpass;
-  float acc = 0.f;
+  float acc = 0.f, h0 = 0.f, h1 = 0.f, l0 = 0.f, l1 = 0.f;
   const int total = 2 * P.step;
   // Software pipeline: the 64 loads of tile c + 1 are issued before the recursion runs over tile c (they sit in
   // registers until the tile buffer is free), so the DRAM round trip hides behind 64 x ~22 dependent instructions.
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(32) loudness_partial_kernel(const SampleT* __r
     const int n_it = min(kLdTile, total - c0);
     for (int i = 0; i < n_it; ++i) {
       // transposed direct form II: two state words per biquad, 5 dependent-free-ish FMAs each (the same transfer
-      // function as torchaudio's direct form I; rounding differs at the 1e-7 level, far inside the LKFS tolerance)
+      // function as torchaudio's direct form I; rounding differs at the 1e-7 level per sample)
       const float x0 = tile[lane][i];
       const float u0 = fmaf(s.b0, x0, s1a);
       s1a = fmaf(s.b1, x0, fmaf(-s.a1, u0, s2a));
@@ -276,34 +279,147 @@ __global__ void __launch_bounds__(32) loudness_partial_kernel(const SampleT* __r
       s1b = fmaf(h.b1, cc, fmaf(-h.a1, v0, s2b));
       s2b = fmaf(h.b2, cc, -h.a2 * v0);
       const float z = fminf(fmaxf(v0, -1.f), 1.f);
-      if (t_begin + c0 + i >= t_acc) acc = fmaf(z, z, acc);
+      const int k = c0 + i - P.step;  // index inside the accumulated step
+      if (k >= 0) {
+        const float zz = (t_acc + k < L) ? z * z : 0.f;  // nothing past the end of the utterance
+        acc += zz;
+        if (k == 0) h0 = zz;
+        if (k == 1) h1 = zz;
+        l0 = l1;
+        l1 = zz;
+      }
     }
   }
-  if (live) scratch[scratch_off[b] + q] = acc;
+  if (live) {
+    float* rec = scratch + scratch_off[b] + kLdRec * q;
+    rec[0] = acc;
+    rec[1] = h0;
+    rec[2] = h1;
+    rec[3] = l0;
+    rec[4] = l1;
+  }
 }
 
-// Pass 2, one thread per utterance: 400 ms block energies (four steps, 75 % overlap) and the two gating passes.
+// Exact pass for the utterances flagged by the gate kernel: one warp per utterance, lane 0 runs torchaudio's float32
+// arithmetic sample by sample from t = 0 -- coefficients normalised by a0, feed-forward part as
+// fma(b0, x[t], fma(b1, x[t-1], b2 * x[t-2])) (conv1d's accumulation), recursion y = (ff - a2 y[t-2]) - a1 y[t-1] with
+// separate roundings on the UNclamped outputs (_lfilter_core_loop), each filter's output clamped to [-1, 1] -- so the
+// K-weighted signal is bit-identical to the reference's; the other lanes only fetch the samples (coalesced) and hand
+// them over by shuffle.  Sequential, ~5 ms for a 10 s utterance: it only ever runs for utterances whose keep / skip
+// decision is within the fast pass' error of a gating threshold.
+template <typename SampleT>
+__global__ void __launch_bounds__(32) loudness_exact_kernel(const SampleT* __restrict__ x,
+                                                            const long long* __restrict__ off, LoudnessParams P,
+                                                            const int* __restrict__ refine, float* __restrict__ scratch,
+                                                            const long long* __restrict__ scratch_off) {
+  const int b = blockIdx.x;
+  if (!refine[b]) return;
+  const SampleT* xs = x + off[b];
+  const long long L = off[b + 1] - off[b];
+  const int lane = threadIdx.x;
+  float* rec = scratch + scratch_off[b];
+  const Biquad s = P.shelf, h = P.highpass;
+  float x1 = 0.f, x2 = 0.f, ya1 = 0.f, ya2 = 0.f;  // shelf: previous inputs / unclamped outputs
+  float u1 = 0.f, u2 = 0.f, yb1 = 0.f, yb2 = 0.f;  // high-pass: previous (clamped shelf) inputs / unclamped outputs
+  double acc = 0.0;
+  float h0 = 0.f, h1 = 0.f, l0 = 0.f, l1 = 0.f;
+  int k = 0;         // index inside the current step
+  long long q = 0;   // current step
+  const long long n_used = L;
+  float nxt = (lane < n_used) ? sample_to_float(__ldg(xs + lane)) : 0.f;
+  for (long long t0 = 0; t0 < n_used; t0 += 32) {
+    const float cur = nxt;
+    const long long tn = t0 + 32 + lane;
+    nxt = (tn < n_used) ? sample_to_float(__ldg(xs + tn)) : 0.f;  // in flight during the 32 sequential steps below
+    const int n_it = (int)((n_used - t0 < 32) ? (n_used - t0) : 32);
+    for (int i = 0; i < n_it; ++i) {
+      const float x0 = __shfl_sync(0xffffffffu, cur, i);
+      if (lane == 0) {
+        const float ffa = fmaf(s.b0, x0, fmaf(s.b1, x1, __fmul_rn(s.b2, x2)));
+        const float ya = __fsub_rn(__fsub_rn(ffa, __fmul_rn(s.a2, ya2)), __fmul_rn(s.a1, ya1));
+        x2 = x1;
+        x1 = x0;
+        ya2 = ya1;
+        ya1 = ya;
+        const float u0 = fminf(fmaxf(ya, -1.f), 1.f);
+        const float ffb = fmaf(h.b0, u0, fmaf(h.b1, u1, __fmul_rn(h.b2, u2)));
+        const float yb = __fsub_rn(__fsub_rn(ffb, __fmul_rn(h.a2, yb2)), __fmul_rn(h.a1, yb1));
+        u2 = u1;
+        u1 = u0;
+        yb2 = yb1;
+        yb1 = yb;
+        const float z = fminf(fmaxf(yb, -1.f), 1.f);
+        const float zz = __fmul_rn(z, z);
+        acc += (double)zz;
+        if (k == 0) h0 = zz;
+        if (k == 1) h1 = zz;
+        l0 = l1;
+        l1 = zz;
+        if (++k == P.step) {
+          float* r = rec + kLdRec * q;
+          r[0] = (float)acc;
+          r[1] = h0;
+          r[2] = h1;
+          r[3] = l0;
+          r[4] = l1;
+          acc = 0.0;
+          k = 0;
+          ++q;
+          h0 = h1 = 0.f;
+        }
+      }
+    }
+  }
+  if (lane == 0 && k > 0) {  // the last, partial step (a block may reach 2 samples into it)
+    float* r = rec + kLdRec * q;
+    r[0] = (float)acc;
+    r[1] = h0;
+    r[2] = h1;
+    r[3] = 0.f;
+    r[4] = 0.f;
+  }
+}
+
+// Pass 2, one thread per utterance: 400 ms block energies (four steps, 75 % overlap; gate - 4 * step samples are
+// added from the next step's head or removed from the last step's tail) and the two gating passes.  With
+// refine_out != NULL it also flags the utterances whose result the fast pass cannot be trusted with: loudness within
+// `band` LKFS of the -36 LKFS gate, or a block within `band` of one of the two block-gating thresholds (a block that
+// changes sides moves the mean by 1 / n_blocks).  With only_refined != NULL only flagged utterances are evaluated.
 __global__ void __launch_bounds__(64) loudness_gate_kernel(const long long* __restrict__ off, int n_utts,
                                                            LoudnessParams P, const float* __restrict__ scratch,
                                                            const long long* __restrict__ scratch_off,
-                                                           float* __restrict__ lkfs) {
+                                                           float* __restrict__ lkfs, float band, float gate_lkfs,
+                                                           int* __restrict__ refine_out,
+                                                           const int* __restrict__ only_refined) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_utts) return;
+  if (only_refined != nullptr && !only_refined[b]) return;
   const long long L = off[b + 1] - off[b];
   const float* sub = scratch + scratch_off[b];
   const long long n_blk = (L >= P.gate) ? (L - P.gate) / P.step + 1 : 0;
   if (n_blk == 0) {
     lkfs[b] = __int_as_float(0x7fc00000);  // shorter than one gating block: the reference cannot measure it
+    if (refine_out) refine_out[b] = 0;
     return;
   }
   const float inv_gate = 1.0f / (float)P.gate;
-  auto energy = [&](long long i) { return ((sub[i] + sub[i + 1]) + (sub[i + 2] + sub[i + 3])) * inv_gate; };
+  const int extra = P.gate - 4 * P.step;  // in [-2, 2]
+  auto energy = [&](long long i) {
+    const float* r = sub + kLdRec * i;
+    float e = (r[0] + r[kLdRec]) + (r[2 * kLdRec] + r[3 * kLdRec]);
+    if (extra > 0) e += r[4 * kLdRec + 1] + (extra > 1 ? r[4 * kLdRec + 2] : 0.f);      // head of step i + 4
+    if (extra < 0) e -= r[3 * kLdRec + 4] + (extra < -1 ? r[3 * kLdRec + 3] : 0.f);     // tail of step i + 3
+    return e * inv_gate;
+  };
   auto lk = [](float e) { return -0.691f + 10.0f * log10f(e); };
+  bool fragile = false;
   float sum = 0.f;
   int cnt = 0;
   for (long long i = 0; i < n_blk; ++i) {  // absolute gate (-70 LKFS)
     const float e = energy(i);
-    if (lk(e) > -70.0f) {
+    const float l = lk(e);
+    if (fabsf(l + 70.0f) < band) fragile = true;
+    if (l > -70.0f) {
       sum += e;
       ++cnt;
     }
@@ -314,12 +430,15 @@ __global__ void __launch_bounds__(64) loudness_gate_kernel(const long long* __re
   for (long long i = 0; i < n_blk; ++i) {  // relative gate (-10 LU below the absolute-gated mean)
     const float e = energy(i);
     const float l = lk(e);
+    if (fabsf(l - gamma_rel) < band) fragile = true;
     if (l > -70.0f && l > gamma_rel) {
       sum += e;
       ++cnt;
     }
   }
-  lkfs[b] = lk(sum / (float)cnt);
+  const float out = lk(sum / (float)cnt);
+  lkfs[b] = out;
+  if (refine_out) refine_out[b] = (band > 0.f && (fragile || fabsf(out - gate_lkfs) < band)) ? 1 : 0;
 }
 
 // RBJ cookbook biquads as torchaudio.functional.{treble_biquad, highpass_biquad} build them: every operation in
@@ -585,13 +704,18 @@ int32_t evf_audio_loudness_step(int32_t sample_rate) {
 int64_t evf_audio_loudness_scratch_floats(int32_t sample_rate, int64_t n_samples) {
   const long long step = evf_audio_loudness_step(sample_rate);
   if (step < 1 || n_samples < 0) return -1;
-  return n_samples / step + 4;  // one partial sum per 100 ms step; the block energies read up to 3 past their index
+  // kLdRec floats per 100 ms step; a block energy reads up to 4 steps past its index
+  return kLdRec * (n_samples / step + 5);
 }
 
 int evf_audio_loudness(const void* x_dev, int32_t x_format, const int64_t* offsets_dev, int32_t n_utts,
-                       int64_t max_len, int32_t sample_rate, float* scratch_dev, const int64_t* scratch_offsets_dev,
-                       float* lkfs_dev, void* stream) {
-  if (n_utts < 0 || sample_rate < 1 || max_len < 0 || (x_format != EVF_SAMPLES_F32 && x_format != EVF_SAMPLES_S16) || (n_utts > 0 && (!x_dev || !offsets_dev || !scratch_dev || !scratch_offsets_dev || !lkfs_dev))) {
+                       int64_t max_len, int32_t sample_rate, const float* biquad_coeffs_host,
+                       float refine_band_lkfs, float gate_lkfs, float* scratch_dev,
+                       const int64_t* scratch_offsets_dev, int32_t* refine_flags_dev, float* lkfs_dev, void* stream) {
+  if (n_utts < 0 || sample_rate < 1 || max_len < 0 || (x_format != EVF_SAMPLES_F32 && x_format != EVF_SAMPLES_S16) ||
+      !(refine_band_lkfs >= 0.f) ||
+      (n_utts > 0 && (!x_dev || !offsets_dev || !scratch_dev || !scratch_offsets_dev || !lkfs_dev)) ||
+      (n_utts > 0 && refine_band_lkfs > 0.f && !refine_flags_dev)) {
     set_error("evf_audio_loudness: invalid argument");
     return EVF_ERR_INVALID_ARGUMENT;
   }
@@ -599,17 +723,23 @@ int evf_audio_loudness(const void* x_dev, int32_t x_format, const int64_t* offse
   // Python's round() is round-half-even; 0.4 * sr and gate * 0.25 are compared on the same doubles
   P.gate = (int)std::nearbyint(0.4 * (double)sample_rate);
   P.step = (int)std::nearbyint((double)P.gate * (1.0 - 0.75));
-  if (P.step < 1 || P.gate != 4 * P.step) {
-    set_error("evf_audio_loudness: sample rate whose 400 ms gating block is not four 100 ms steps is not supported");
+  if (P.step < 2 || P.gate - 4 * P.step < -2 || P.gate - 4 * P.step > 2) {
+    set_error("evf_audio_loudness: sampling rate too low for 100 ms steps");
     return EVF_ERR_UNSUPPORTED;
   }
   if (n_utts == 0) return EVF_OK;
-  P.shelf = make_treble((float)sample_rate, 4.0f, 1500.0f, (float)(1.0 / std::sqrt(2.0)));
-  P.highpass = make_highpass((float)sample_rate, 38.0f, 0.5f);
+  if (biquad_coeffs_host != nullptr) {  // {b0, b1, b2, a1, a2} / a0 of the shelf, then of the high-pass
+    const float* c = biquad_coeffs_host;
+    P.shelf = Biquad{c[0], c[1], c[2], c[3], c[4]};
+    P.highpass = Biquad{c[5], c[6], c[7], c[8], c[9]};
+  } else {
+    P.shelf = make_treble((float)sample_rate, 4.0f, 1500.0f, (float)(1.0 / std::sqrt(2.0)));
+    P.highpass = make_highpass((float)sample_rate, 38.0f, 0.5f);
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long* off = reinterpret_cast<const long long*>(offsets_dev);
   const long long* soff = reinterpret_cast<const long long*>(scratch_offsets_dev);
-  const long long max_sub = max_len / P.step;
+  const long long max_sub = (max_len + P.step - 1) / P.step;
   if (max_sub > 0) {
     for (int y0 = 0; y0 < n_utts; y0 += kMaxGridY) {
       const dim3 grid((unsigned)((max_sub + 31) / 32), (unsigned)(n_utts - y0 < kMaxGridY ? n_utts - y0 : kMaxGridY));
@@ -622,8 +752,22 @@ int evf_audio_loudness(const void* x_dev, int32_t x_format, const int64_t* offse
       EVF_CUDA(cudaGetLastError());
     }
   }
-  loudness_gate_kernel<<<(n_utts + 63) / 64, 64, 0, st>>>(off, n_utts, P, scratch_dev, soff, lkfs_dev);
+  const bool refine = refine_band_lkfs > 0.f;
+  loudness_gate_kernel<<<(n_utts + 63) / 64, 64, 0, st>>>(off, n_utts, P, scratch_dev, soff, lkfs_dev, refine_band_lkfs,
+                                                          gate_lkfs, refine ? refine_flags_dev : nullptr, nullptr);
   EVF_CUDA(cudaGetLastError());
+  if (refine) {
+    if (x_format == EVF_SAMPLES_S16)
+      loudness_exact_kernel<short><<<n_utts, 32, 0, st>>>(static_cast<const short*>(x_dev), off, P, refine_flags_dev,
+                                                          scratch_dev, soff);
+    else
+      loudness_exact_kernel<float><<<n_utts, 32, 0, st>>>(static_cast<const float*>(x_dev), off, P, refine_flags_dev,
+                                                          scratch_dev, soff);
+    EVF_CUDA(cudaGetLastError());
+    loudness_gate_kernel<<<(n_utts + 63) / 64, 64, 0, st>>>(off, n_utts, P, scratch_dev, soff, lkfs_dev, 0.f, gate_lkfs,
+                                                            nullptr, refine_flags_dev);
+    EVF_CUDA(cudaGetLastError());
+  }
   return EVF_OK;
 }
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define EVF_ABI_VERSION 8
+#define EVF_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define EVF_API __attribute__((visibility("default")))
@@ -248,15 +248,25 @@ EVF_API int evf_audio_finalize(const void* x_dev, int32_t x_format, const int64_
                                const float* absmax_dev, float* out_f32_dev, int16_t* out_s16_dev, void* stream);
 /* torchaudio.transforms.Loudness(sr)(audio) for mono utterances (preprocessor.py:177-186: skipped when NaN or
  * < -36): ITU-R BS.1770-4 K-weighting, 400 ms blocks with 75 % overlap, absolute (-70) and relative (-10) gates.
+ *   Fast pass: the filters' recursion is restarted every 100 ms with a 100 ms run-in, so all steps of all utterances
+ *   run in parallel; about 2e-3 LKFS from torchaudio.
+ *   Exact pass (refine_band_lkfs > 0): utterances whose loudness lies within the band of gate_lkfs (the caller's
+ *   threshold, -36), or that hold a block within the band of a block-gating threshold, are re-evaluated with
+ *   torchaudio's float32 arithmetic sample by sample (K-weighted signal bit-identical to the reference's), so the
+ *   keep / skip decision is the reference's.  refine_flags_dev (int32[n_utts]) receives which ones were.
+ * biquad_coeffs_host: 10 floats {b0, b1, b2, a1, a2} / a0 of the treble shelf and of the high-pass as the caller's
+ *   torch build evaluates torchaudio's formulas (its sin / cos / exp can differ from libm's by an ulp, which the
+ *   38 Hz high-pass amplifies); NULL: computed here with libm.
  * scratch_dev: float32, evf_audio_loudness_scratch_floats(sr, L_b) entries per utterance at scratch_offsets_dev;
- * max_len = the longest utterance (grid sizing).  The filters' recursion is restarted every 100 ms with a 100 ms
- * run-in (state error < 1e-7 relative), so all steps of all utterances run in parallel. */
+ * max_len = the longest utterance (grid sizing). */
 EVF_API int64_t evf_audio_loudness_scratch_floats(int32_t sample_rate, int64_t n_samples);
 /* the 100 ms step in samples as torchaudio rounds it (round(round(0.4 * sr) * 0.25), half to even); -1 on bad input */
 EVF_API int32_t evf_audio_loudness_step(int32_t sample_rate);
 EVF_API int evf_audio_loudness(const void* x_dev, int32_t x_format, const int64_t* offsets_dev, int32_t n_utts,
-                               int64_t max_len, int32_t sample_rate, float* scratch_dev,
-                               const int64_t* scratch_offsets_dev, float* lkfs_dev, void* stream);
+                               int64_t max_len, int32_t sample_rate, const float* biquad_coeffs_host,
+                               float refine_band_lkfs, float gate_lkfs, float* scratch_dev,
+                               const int64_t* scratch_offsets_dev, int32_t* refine_flags_dev, float* lkfs_dev,
+                               void* stream);
 
 #ifdef __cplusplus
 }

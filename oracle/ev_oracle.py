@@ -414,44 +414,60 @@ def resample(x: np.ndarray, orig_freq: int, new_freq: int) -> np.ndarray:
 
 
 def _biquad_f32(x: np.ndarray, b, a) -> np.ndarray:
-    """Direct-form-I biquad in float32 like torchaudio's lfilter: feed-forward part, divided by a0, then the
-    recursion on the unclamped outputs; the result is clamped to [-1, 1] (lfilter's clamp=True)."""
+    """``torchaudio.functional.biquad`` -> ``lfilter(clamp=True)`` in float32, operation for operation (torchaudio
+    2.7 - 2.11 ``_lfilter``): the coefficients are divided by a0 FIRST; the feed-forward part is ``conv1d`` over
+    ``[b2, b1, b0] / a0`` whose accumulation is ``fma(b0, x[t], fma(b1, x[t-1], b2 * x[t-2]))``; the recursion
+    (``_lfilter_core_loop``, C++) subtracts ``a2 * y[t-2]`` and then ``a1 * y[t-1]`` with separate roundings, on the
+    UNclamped outputs; the result is clamped to [-1, 1].  Bit-exact against this container's torchaudio
+    (tests/test_frontend_oracle.py): the 38 Hz high-pass has a double pole at 1 - 2 pi 38 / sr, so any other
+    rounding order moves its output by 1e-4 and the loudness by up to 1e-3 LKFS."""
     f = np.float32
     b0, b1, b2 = (f(v) for v in b)
     a0, a1, a2 = (f(v) for v in a)
-    a1, a2 = f(a1 / a0), f(a2 / a0)
-    xp = np.concatenate([np.zeros(2, f), x.astype(f)])
-    ff = ((b2 * xp[:-2] + b1 * xp[1:-1]).astype(f) + b0 * xp[2:]).astype(f)
-    ff = (ff / a0).astype(f)
+    b0, b1, b2, a1, a2 = f(b0 / a0), f(b1 / a0), f(b2 / a0), f(a1 / a0), f(a2 / a0)
+    xp = np.concatenate([np.zeros(2, f), x.astype(f)]).astype(np.float64)
+    t2 = (f(b2) * xp[:-2].astype(f)).astype(f).astype(np.float64)            # b2 * x[t-2], rounded
+    t1 = (np.float64(b1) * xp[1:-1] + t2).astype(f).astype(np.float64)       # fma(b1, x[t-1], .): exact product in float64
+    ff = (np.float64(b0) * xp[2:] + t1).astype(f)                            # fma(b0, x[t], .)
     y = np.zeros(len(x) + 2, f)
     for t in range(len(x)):
-        y[t + 2] = f(f(ff[t] - f(a2 * y[t])) - f(a1 * y[t + 1]))  # the order of torchaudio's CPU loop
+        y[t + 2] = f(f(ff[t] - f(a2 * y[t])) - f(a1 * y[t + 1]))
     return np.clip(y[2:], -1.0, 1.0)
 
 
 def k_weighting_coeffs(sample_rate: int):
     """Coefficients of torchaudio's treble_biquad(4 dB, 1500 Hz, Q=1/sqrt(2)) and highpass_biquad(38 Hz, Q=0.5),
-    evaluated in float32 like torchaudio does (tensor math in the waveform dtype)."""
-    f = np.float32
-    sr = f(sample_rate)
+    evaluated with the SAME float32 torch tensor operations torchaudio runs (torch.sin / cos / exp / sqrt differ from
+    libm's by an ulp for some arguments -- at 48 kHz that alone moves the loudness by 2e-3 LKFS)."""
+    t = lambda v: torch.as_tensor(v, dtype=torch.float32)  # noqa: E731
 
-    def treble(gain, fc, Q):
-        w0 = f(f(f(2 * math.pi) * f(fc)) / sr)
-        alpha = f(f(np.sin(w0)) / f(2) / f(Q))
-        A = f(np.exp(f(f(gain) / f(40) * f(math.log(10)))))
-        t1 = f(f(2) * f(np.sqrt(A)) * alpha)
-        t2 = f((A - f(1)) * f(np.cos(w0)))
-        t3 = f((A + f(1)) * f(np.cos(w0)))
-        b = (A * ((A + 1) + t2 + t1), -2 * A * ((A - 1) + t3), A * ((A + 1) + t2 - t1))
-        a = ((A + 1) - t2 + t1, 2 * ((A - 1) - t3), (A + 1) - t2 - t1)
-        return tuple(f(v) for v in b), tuple(f(v) for v in a)
+    def treble(gain, central_freq, Q):  # torchaudio.functional.treble_biquad
+        central_freq, Q, gain = t(central_freq), t(Q), t(gain)
+        w0 = 2 * math.pi * central_freq / sample_rate
+        alpha = torch.sin(w0) / 2 / Q
+        A = torch.exp(gain / 40 * math.log(10))
+        temp1 = 2 * torch.sqrt(A) * alpha
+        temp2 = (A - 1) * torch.cos(w0)
+        temp3 = (A + 1) * torch.cos(w0)
+        b0 = A * ((A + 1) + temp2 + temp1)
+        b1 = -2 * A * ((A - 1) + temp3)
+        b2 = A * ((A + 1) + temp2 - temp1)
+        a0 = (A + 1) - temp2 + temp1
+        a1 = 2 * ((A - 1) - temp3)
+        a2 = (A + 1) - temp2 - temp1
+        return tuple(np.float32(float(v)) for v in (b0, b1, b2)), tuple(np.float32(float(v)) for v in (a0, a1, a2))
 
-    def highpass(fc, Q):
-        w0 = f(f(f(2 * math.pi) * f(fc)) / sr)
-        alpha = f(f(np.sin(w0)) / f(2) / f(Q))
-        c = f(np.cos(w0))
-        b0 = f((f(1) + c) / f(2))
-        return (b0, f(f(-1) - c), b0), (f(f(1) + alpha), f(f(-2) * c), f(f(1) - alpha))
+    def highpass(cutoff_freq, Q):  # torchaudio.functional.highpass_biquad
+        cutoff_freq, Q = t(cutoff_freq), t(Q)
+        w0 = 2 * math.pi * cutoff_freq / sample_rate
+        alpha = torch.sin(w0) / 2.0 / Q
+        b0 = (1 + torch.cos(w0)) / 2
+        b1 = -1 - torch.cos(w0)
+        b2 = b0
+        a0 = 1 + alpha
+        a1 = -2 * torch.cos(w0)
+        a2 = 1 - alpha
+        return tuple(np.float32(float(v)) for v in (b0, b1, b2)), tuple(np.float32(float(v)) for v in (a0, a1, a2))
 
     return treble(4.0, 1500.0, 1 / math.sqrt(2)), highpass(38.0, 0.5)
 

@@ -211,3 +211,43 @@ def test_int16_waveforms_equal_float_waveforms_bitwise(cuda_device):
     c = pre.process_audio_batch(views, 44100, resample_rate=22050, hop_size=256, out_dtype=torch.int16)
     d = pre.process_audio_batch(as_i16, 44100, resample_rate=22050, hop_size=256, out_dtype=torch.int16)
     assert torch.equal(c.samples, d.samples)
+
+
+def test_gate_decisions_at_the_thresholds(cuda_device, golden_dir):
+    """Keep / skip is index work: it must be the reference's, also AT the gates.  tests/golden/gates.npz holds the live
+    reference's decisions for utterances scaled to -36 LKFS +- {1e-4, 1e-3, 1e-2} at five sampling rates (11 025 Hz:
+    a 400 ms block that is not four 100 ms steps) and for lengths one sample either side of 0.4 s / 11 s.  The fast
+    loudness pass is 2e-3 LKFS accurate; every one of these utterances must be flagged and re-evaluated by the exact
+    pass (K-weighted signal bit-identical to torchaudio's), landing within 2e-5 LKFS and on the same side."""
+    from everyvoice_b200.audio import loudness_batch
+    from oracle.make_golden_gate import DELTAS, LENGTHS, SIGNALS, gate_inputs, length_inputs
+
+    gold = np.load(golden_dir / "gates.npz")
+    pre = _pre(cuda_device)
+    for name in SIGNALS:
+        x, sr = gate_inputs(name)
+        ys, keys = [], []
+        for d in DELTAS:
+            key = f"{name}/{d:+.0e}"
+            ys.append(torch.from_numpy((x * gold[key + "/scale"]).astype(np.float32)))
+            keys.append(key)
+        res = pre.process_audio_batch(ys, sr, resample_rate=sr, hop_size=256)
+        for i, (key, d) in enumerate(zip(keys, DELTAS)):
+            assert abs(float(res.loudness[i]) - float(gold[key + "/loudness"])) <= 2e-5, (key, float(res.loudness[i]))
+            if d != 0.0:
+                assert (i in res.kept) == bool(gold[key + "/keep"]), key
+        # every one of them went through the exact pass; a loud utterance next to them does not
+        from everyvoice_b200 import synth
+        packed, off = synth.pack_ragged([y.numpy() for y in ys] + [x])
+        _, flags = loudness_batch(torch.from_numpy(packed).to(cuda_device), off, sr, return_refined=True)
+        assert flags.cpu().tolist() == [1] * len(ys) + [0], name
+        # the PCM the wav files hold: same decisions as for the float samples they load as
+        pcm = [(y * 32768.0).round().clamp(-32768, 32767).to(torch.int16) for y in ys]
+        want = pre.process_audio_batch([p.to(torch.float32) / 32768.0 for p in pcm], sr, resample_rate=sr, hop_size=256)
+        got = pre.process_audio_batch(pcm, sr, resample_rate=sr, hop_size=256)
+        assert got.kept == want.kept and np.array_equal(got.loudness, want.loudness, equal_nan=True)
+    for sr, lens in LENGTHS.items():
+        xs = [torch.from_numpy(length_inputs(sr, n)) for n in lens]
+        res = pre.process_audio_batch(xs, sr, resample_rate=sr, hop_size=256)
+        assert [i in res.kept for i in range(len(lens))] == [bool(gold[f"length/{sr}/{n}/keep"]) for n in lens]
+        assert [res.skipped.get(i) for i in range(len(lens))] == ["audio_too_short", None, None, "audio_too_long"]

@@ -42,18 +42,19 @@ def test_resampled_and_kept_lengths_match_the_reference_formulas():
     assert lib.evf_resampler_out_length(C.c_void_p(0), 100) == -1
 
 
-@pytest.mark.parametrize("sr", [8000, 16000, 22050, 24000, 32000, 44100, 48000])
+@pytest.mark.parametrize("sr", [8000, 11025, 16000, 22050, 24000, 32000, 44099, 44100, 48000])
 def test_loudness_block_arithmetic(sr):
     """torchaudio.functional.loudness: gate = round(0.4 sr), step = round(0.25 gate) (Python round-half-even); the
-    kernels need gate == 4 * step and one partial sum per step (+ 3 read past the last block's index)."""
+    kernels keep one 5-float record per step (sum, first two, last two squares), a block is four steps plus / minus
+    gate - 4 * step in [-2, 2] samples, and a block reads up to 4 records past its index."""
     lib = _lib.load()
     gate = int(round(0.4 * sr))
     step = int(round(gate * (1 - 0.75)))
-    assert gate == 4 * step
+    assert -2 <= gate - 4 * step <= 2 and lib.evf_audio_loudness_step(sr) == step
     for n in (0, 1, step - 1, step, gate - 1, gate, 10 * sr + 17):
-        assert lib.evf_audio_loudness_scratch_floats(sr, n) == n // step + 4
+        assert lib.evf_audio_loudness_scratch_floats(sr, n) == 5 * (n // step + 5)
         n_blk = (n - gate) // step + 1 if n >= gate else 0          # unfold(-1, gate, step)
-        assert n_blk + 3 <= n // step + 4
+        assert n_blk + 4 <= n // step + 5
     assert lib.evf_audio_loudness_scratch_floats(0, 10) == -1
 
 

@@ -64,14 +64,19 @@ def main():
 
     st = _stream_ptr(dev)
     d_off = torch.from_numpy(off).to(dev)
-    step = int(round(int(round(0.4 * sr_in)) * 0.25))
-    s_off = np.concatenate([[0], np.cumsum(lens // step + 4)]).astype(np.int64)
+    step = int(lib.evf_audio_loudness_step(sr_in))
+    s_off = np.concatenate([[0], np.cumsum(5 * (lens // step + 5))]).astype(np.int64)
     d_soff = torch.from_numpy(s_off).to(dev)
     scratch = torch.empty(int(s_off[-1]), dtype=torch.float32, device=dev)
     lk = torch.empty(n, dtype=torch.float32, device=dev)
-    rec("loudness (partial + gate)",
-        timed(lambda: _lib.check(lib.evf_audio_loudness(_ptr(x), _lib.SAMPLES_F32, _ptr(d_off), n, int(lens.max()), sr_in, _ptr(scratch),
-                                                        _ptr(d_soff), _ptr(lk), st))), 4 * int(off[-1]))
+    flags = torch.zeros(n, dtype=torch.int32, device=dev)
+    from everyvoice_b200.audio import k_weighting_coefficients
+    import ctypes as C
+    kw = k_weighting_coefficients(sr_in)
+    rec("loudness (partial + gate + exact pass for utterances at the gate)",
+        timed(lambda: _lib.check(lib.evf_audio_loudness(_ptr(x), _lib.SAMPLES_F32, _ptr(d_off), n, int(lens.max()), sr_in,
+                                                        kw.ctypes.data_as(C.c_void_p), 0.05, -36.0, _ptr(scratch),
+                                                        _ptr(d_soff), _ptr(flags), _ptr(lk), st))), 4 * int(off[-1]))
     rs = ev.Resampler(sr_in, sr_out, dev)
     y, y_off = rs(x, off)
     d_yoff = torch.from_numpy(y_off).to(dev)
