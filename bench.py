@@ -680,44 +680,35 @@ def measure_e2e(job, args, world, sample_dtype):
     return audio_s_all * steps / dt, steps, info, dt / steps
 
 
-def measure_preprocess_flow(job, steps=4, pcm16=True):
+def measure_preprocess_flow(job, steps=6, pcm16=True):
     """The whole numeric flow behind `everyvoice preprocess` for one batch, host to host, every step: the wav files'
-    samples (pinned host) -> process_audio (gates, loudness, peak normalisation, truncation, PCM16) -> process_spec ->
-    process_energy (phone-level) -> compute_stats / normalize_stats -> log-spectrogram, energy and normalised phone
-    values back in pinned host memory.  An extra, informative key of the bench line (N = 1 only)."""
+    samples (pinned host) -> process_audio (loudness gate with its exact pass, peak normalisation, truncation, PCM16) ->
+    process_spec -> process_energy (phone-level) -> statistics / normalisation -> processed PCM16 audio,
+    log-spectrogram, energy and normalised phone values back in pinned host memory, as ONE chunked three-stream
+    pipeline with the gate consumed on the device (Preprocessor.make_flow_pipeline).  Planning included, every step.
+    An extra, informative key of the bench line (N = 1 only)."""
     import torch
 
     spec_type, sr, n_fft, win, hop, *_ = job.w
     pre, device, off = job.pre, job.device, job.sample_offsets
-    n = len(off) - 1
     if pcm16:  # the wav files' own samples
         host_all = torch.empty(int(off[-1]), dtype=torch.int16).pin_memory()
         host_all.copy_((job.samples * 32767.0).round().to(torch.int16))
     else:      # what load_audio returns
         host_all = torch.empty(int(off[-1]), dtype=torch.float32).pin_memory()
         host_all.copy_(job.samples)
-    host_list = [host_all[int(off[b]):int(off[b + 1])] for b in range(n)]
-    durs = torch.from_numpy(job.d_packed.astype(np.int64)).to(device)
+    host_durs = torch.from_numpy(job.d_packed.astype(np.int64)).pin_memory()
+    h_spec = torch.empty((job.total_frames, job.batch.plan.row_floats), dtype=torch.float32).pin_memory()
+    h_energy = torch.empty(job.total_frames, dtype=torch.float32).pin_memory()
+    h_phone = torch.empty(int(job.phone_offsets[-1]), dtype=torch.float32).pin_memory()
+    h_audio = torch.empty(int(off[-1]), dtype=torch.int16).pin_memory()
     out = {}
 
     def step():
-        audio = pre.process_audio_batch(host_list, sr, resample_rate=sr, hop_size=hop, out_dtype=torch.int16)
-        feats = pre.process_spec_batch(audio.samples, audio.offsets)
-        if len(audio.kept) == n:
-            phone, p_off = pre.process_energy_batch(feats, durs, job.phone_offsets)
-        else:  # a gate dropped something: frame-level energy keeps the step well defined
-            phone, p_off = pre.process_energy_batch(feats)
-        e_scaler, _ = pre.compute_stats(energy=phone, n_energy_files=len(audio.kept))
-        stats = pre.normalize_stats(e_scaler, None, distributed=False)
-        if "spec" not in out:
-            out["spec"] = torch.empty(tuple(feats.spec.shape), dtype=torch.float32).pin_memory()
-            out["energy"] = torch.empty(tuple(feats.energy.shape), dtype=torch.float32).pin_memory()
-            out["phone"] = torch.empty(tuple(phone.shape), dtype=torch.float32).pin_memory()
-        out["spec"].copy_(feats.spec, non_blocking=True)
-        out["energy"].copy_(feats.energy, non_blocking=True)
-        out["phone"].copy_(phone, non_blocking=True)
-        torch.cuda.synchronize(device)
-        out["kept"], out["mean"] = len(audio.kept), stats["energy"]["mean"]
+        flow = pre.make_flow_pipeline(off, sr, host_all.dtype, host_durs, job.phone_offsets)
+        res = flow.run(host_all, h_spec, h_energy, h_phone, h_audio)()
+        out.update(kept=int(res.keep.sum()), h2d=flow.h2d_bytes, d2h=flow.d2h_bytes + h_audio.numel() * 2,
+                   chunks=len(flow.chunks))
 
     for _ in range(2):
         step()
@@ -727,10 +718,10 @@ def measure_preprocess_flow(job, steps=4, pcm16=True):
     dt = (time.perf_counter() - t0) / steps
     return {"value": job.audio_s / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "utterances_kept": out["kept"],
             "input_format": "int16 PCM (the wav files' samples), pinned host" if pcm16 else "float32, pinned host",
-            "h2d_bytes_per_step": int(off[-1]) * (2 if pcm16 else 4),
-            "d2h_bytes_per_step": int(out["spec"].numel() + out["energy"].numel() + out["phone"].numel()) * 4,
-            "api": "process_audio_batch -> process_spec_batch -> process_energy_batch -> compute_stats -> "
-                   "normalize_stats, host waveforms in, host log-mel / energy / phone values out"}
+            "h2d_bytes_per_step": out["h2d"], "d2h_bytes_per_step": out["d2h"], "chunks": out["chunks"],
+            "api": "Preprocessor.make_flow_pipeline(...).run(host buffers): process_audio (gates on the device) -> "
+                   "process_spec -> process_energy -> statistics -> normalise; processed PCM16 audio, log-mel, energy "
+                   "and phone values back on the host"}
 
 
 def run_extra(wname, args, rank, local_rank, world, device):

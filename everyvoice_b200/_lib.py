@@ -88,6 +88,7 @@ PROTOTYPES = {
     "evf_audio_finalize": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int32, C.c_int64, _P, _P, _P, _P]),
     "evf_audio_loudness_scratch_floats": (C.c_int64, [C.c_int32, C.c_int64]),
     "evf_audio_loudness_step": (C.c_int32, [C.c_int32]),
+    "evf_audio_gate_mask": (C.c_int, [_P, C.c_float, _P, _P, C.c_int32, _P, _P]),
     "evf_audio_loudness": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int64, C.c_int32, _P, C.c_float, C.c_float, _P, _P,
                                      _P, _P, _P]),
 }

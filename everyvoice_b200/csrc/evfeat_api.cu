@@ -716,6 +716,16 @@ int evf_pitch_fill_unvoiced(const double* pitch_dev, const int64_t* offsets_dev,
   return launch_pitch_fill_unvoiced(pitch_dev, offsets_dev, n_utts, out_dev, static_cast<cudaStream_t>(stream));
 }
 
+int evf_audio_gate_mask(const float* lkfs_dev, float gate_lkfs, float* values_dev, const int64_t* value_offsets_dev,
+                        int32_t n_utts, int32_t* keep_out_dev, void* stream) {
+  if (n_utts < 0 || (n_utts > 0 && (!lkfs_dev || (values_dev && !value_offsets_dev)))) {
+    set_error("evf_audio_gate_mask: invalid argument");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_gate_mask(lkfs_dev, gate_lkfs, values_dev, value_offsets_dev, n_utts, keep_out_dev,
+                          static_cast<cudaStream_t>(stream));
+}
+
 int evf_log_compress_backward(const float* in_dev, const float* grad_out_dev, float* grad_in_dev, int64_t n,
                               float clip_val, void* stream) {
   if (n < 0 || (n > 0 && (!in_dev || !grad_out_dev || !grad_in_dev))) {

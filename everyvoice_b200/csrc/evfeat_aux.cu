@@ -352,6 +352,32 @@ int launch_pitch_fill_unvoiced(const double* pitch, const int64_t* offsets, int 
   return EVF_OK;
 }
 
+// The loudness gate consumed on the device (preprocessor.py:177-186: skipped when the loudness is NaN or < -36): the
+// per-utterance values of a skipped utterance become NaN, so that the NaN-skipping statistics leave it out and the
+// host can drop it after the batch; keep[b] tells which ones stay.  One warp per utterance.
+__global__ void __launch_bounds__(128) gate_mask_kernel(const float* __restrict__ lkfs, float gate,
+                                                        float* __restrict__ values, const long long* __restrict__ off,
+                                                        int n_utts, int* __restrict__ keep_out) {
+  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (b >= n_utts) return;
+  const float l = lkfs[b];
+  const bool keep = !(l != l) && !(l < gate);
+  const int lane = threadIdx.x & 31;
+  if (keep_out != nullptr && lane == 0) keep_out[b] = keep ? 1 : 0;
+  if (keep || values == nullptr) return;
+  const float nan = __int_as_float(0x7fc00000);
+  for (long long i = off[b] + lane; i < off[b + 1]; i += 32) values[i] = nan;
+}
+
+int launch_gate_mask(const float* lkfs, float gate, float* values, const int64_t* offsets, int n_utts, int* keep_out,
+                     cudaStream_t s) {
+  if (n_utts == 0) return EVF_OK;
+  gate_mask_kernel<<<(n_utts + 3) / 4, 128, 0, s>>>(lkfs, gate, values, reinterpret_cast<const long long*>(offsets), n_utts,
+                                                   keep_out);
+  EVF_CUDA(cudaGetLastError());
+  return EVF_OK;
+}
+
 int launch_log_compress(const float* in, float* out, int64_t n, float c, float clip, cudaStream_t s) {
   if (n == 0) return EVF_OK;
   log_compress_kernel<<<grid_for(n, 256 * 4, 148 * 8), 256, 0, s>>>(in, out, n, c, clip);

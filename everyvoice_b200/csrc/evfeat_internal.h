@@ -171,5 +171,7 @@ int launch_normalize_by_gathered(float* values, int64_t n, const double* parts, 
 int launch_stats_merge(const double* parts, int n_parts, int stride, double* out5, cudaStream_t s);
 int launch_log_compress(const float* in, float* out, int64_t n, float c, float clip, cudaStream_t s);
 int launch_pitch_fill_unvoiced(const double* pitch, const int64_t* offsets, int n_utts, float* out, cudaStream_t s);
+int launch_gate_mask(const float* lkfs, float gate, float* values, const int64_t* offsets, int n_utts, int* keep_out,
+                     cudaStream_t s);
 
 }  // namespace evf

@@ -266,6 +266,19 @@ class Preprocessor:
         return CorpusPipeline(transform, sample_offsets, device, sample_dtype, durations, phone_offsets, chunk_bytes,
                               resources=res)
 
+    def make_flow_pipeline(self, raw_offsets, sr: int, sample_dtype=torch.int16, durations=None, phone_offsets=None,
+                           normalize=True, chunk_bytes: int = 16 << 20):
+        """The whole ``process_audio -> process_spec -> process_energy -> statistics`` flow for one batch of loaded
+        wavs as one chunked pipeline with the loudness gate consumed on the device (``pipeline.FlowPipeline``)."""
+        from .pipeline import FlowPipeline, PipelineResources
+
+        device = _require_cuda(self.device)
+        res = getattr(self, "_pipeline_resources", None)
+        if res is None or res.device != device:
+            res = self._pipeline_resources = PipelineResources(device)
+        return FlowPipeline(self.input_spectral_transform, raw_offsets, sr, self.audio_config.fft_hop_size, device,
+                            sample_dtype, durations, phone_offsets, chunk_bytes, normalize, resources=res)
+
     def process_energy_batch(self, feats: RaggedFeatures, durations=None, phone_offsets=None):
         """The in-memory core of ``process_energy`` (preprocessor.py:641-650): frame energy, and
         phone-level averages when ``durations`` (packed int64 + ``phone_offsets``, or a list of

@@ -268,6 +268,13 @@ EVF_API int evf_audio_loudness(const void* x_dev, int32_t x_format, const int64_
                                const int64_t* scratch_offsets_dev, int32_t* refine_flags_dev, float* lkfs_dev,
                                void* stream);
 
+/* The loudness gate consumed on the device, without a host round trip (preprocessor.py:177-186: a file is skipped when
+ * its loudness is NaN or < gate_lkfs = -36): keep_out_dev[b] = 1 / 0, and the per-utterance values of a skipped
+ * utterance (values_dev[value_offsets[b] .. value_offsets[b + 1]), e.g. its phone-level energies; may be NULL) become
+ * NaN, which the statistics (evf_stats_partial) skip.  The host drops the skipped utterances after the batch. */
+EVF_API int evf_audio_gate_mask(const float* lkfs_dev, float gate_lkfs, float* values_dev,
+                                const int64_t* value_offsets_dev, int32_t n_utts, int32_t* keep_out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
