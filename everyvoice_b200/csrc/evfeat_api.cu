@@ -747,11 +747,6 @@ int evf_features_backward(const evf_plan* plan, const evf_batch* batch, const fl
     set_error("evf_features_backward: invalid plan / batch");
     return EVF_ERR_INVALID_ARGUMENT;
   }
-  if (plan->mode == MODE_GENERIC) {
-    set_error("evf_features_backward: the backward kernels cover n_fft 1024 (hop <= n_fft) and 2048 (even hop) with a "
-              "triangular mel bank");
-    return EVF_ERR_UNSUPPORTED;
-  }
   if (plan->cfg.sample_format != EVF_SAMPLES_F32 || plan->cfg.apply_log || plan->cfg.spec_type == EVF_SPEC_RAW) {
     set_error("evf_features_backward: needs float32 samples, a linear-domain plan (apply_log = 0; the log has its own "
               "backward, evf_log_compress_backward) and a real spec_type");
@@ -763,6 +758,20 @@ int evf_features_backward(const evf_plan* plan, const evf_batch* batch, const fl
     return EVF_ERR_INVALID_ARGUMENT;
   }
   DeviceGuard guard(plan->device);
+  if (plan->mode == MODE_GENERIC) {  // any n_fft / hop / mel basis: the shared-memory mixed-radix kernels
+    GenParams g = plan->gen;
+    g.samples = samples_dev;
+    g.tiles = batch->d_tiles;
+    g.n_tiles = batch->n_tiles;
+    g.apply_log = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int cap = plan->num_sms * plan->gen_grid_per_sm;
+    int rc = generic_backward_launch(plan->cfg.spec_type, g, grad_spec_dev, scratch_dev, plan->d_jk, plan->k_used,
+                                     g.n_tiles < cap ? g.n_tiles : cap, plan->smem_bytes, st);
+    if (rc != EVF_OK) return rc;
+    return overlap_add_launch(scratch_dev, batch->d_sample_off, batch->d_frame_off, batch->n_utts, batch->max_len,
+                              plan->cfg.n_fft, plan->cfg.hop_length, grad_samples_dev, st);
+  }
   BwdParams p{};
   p.samples = samples_dev;
   p.tiles = batch->d_tiles;

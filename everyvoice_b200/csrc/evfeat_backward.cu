@@ -311,13 +311,16 @@ int features_backward_launch(const BwdParams& p, cudaStream_t st) {
       return EVF_ERR_UNSUPPORTED;
   }
   if (rc != EVF_OK) return rc;
-  if (p.max_len > 0) {
-    for (int y0 = 0; y0 < p.n_utts; y0 += 65535) {  // gridDim.y limit: slices of utterances
-      const dim3 grid((unsigned)((p.max_len + 255) / 256), (unsigned)(p.n_utts - y0 < 65535 ? p.n_utts - y0 : 65535));
-      overlap_add_kernel<<<grid, 256, 0, st>>>(p.frame_grad, p.sample_off + y0, p.frame_off + y0, p.n_fft, p.hop,
-                                               p.grad_samples);
-      EVF_CUDA(cudaGetLastError());
-    }
+  return overlap_add_launch(p.frame_grad, p.sample_off, p.frame_off, p.n_utts, p.max_len, p.n_fft, p.hop, p.grad_samples, st);
+}
+
+int overlap_add_launch(const float* frame_grad, const long long* sample_off, const long long* frame_off, int n_utts,
+                       long long max_len, int n_fft, int hop, float* grad_samples, cudaStream_t st) {
+  if (max_len <= 0) return EVF_OK;
+  for (int y0 = 0; y0 < n_utts; y0 += 65535) {  // gridDim.y limit: slices of utterances
+    const dim3 grid((unsigned)((max_len + 255) / 256), (unsigned)(n_utts - y0 < 65535 ? n_utts - y0 : 65535));
+    overlap_add_kernel<<<grid, 256, 0, st>>>(frame_grad, sample_off + y0, frame_off + y0, n_fft, hop, grad_samples);
+    EVF_CUDA(cudaGetLastError());
   }
   return EVF_OK;
 }

@@ -276,6 +276,131 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_kernel(const Gen
   }
 }
 
+// ---- backward of the any-size transform ------------------------------------------------
+// d loss / d (windowed frame) for every frame pair of a tile, written as one row of n_fft floats per frame into the
+// scratch that overlap_add_kernel (evfeat_backward.cu) folds back onto the samples.  Same steps as the warp kernel's
+// backward: recompute Z of the pair, separate X_a / X_b, transposed mel projection (a bin feeds two adjacent filters:
+// no reduction; a bank that is not triangular takes the dense row), G = 2 g_P X (x 1 / (2 sqrt(P + 1e-9)) for
+// mel-librosa), Hermitian extension packed as C = C_a + i C_b, inverse DFT through the FORWARD Stockham stages with
+// real and imaginary parts swapped on the way in and out, times the window.
+template <int SPEC>
+__global__ void __launch_bounds__(kGenThreads) features_generic_backward_kernel(const GenParams p, const float* __restrict__ grad_spec,
+                                                                                float* __restrict__ frame_grad,
+                                                                                const int* __restrict__ jk, int k_used) {
+  constexpr bool kMel = (SPEC == EVF_SPEC_MEL || SPEC == EVF_SPEC_MEL_LIBROSA);
+  extern __shared__ __align__(16) float2 gsm[];
+  const int N = p.n_fft;
+  const int pairs = p.pairs;
+  const int ts = kGenThreads / pairs;
+  const int tid = threadIdx.x;
+  const int team = tid / ts, lt = tid % ts;
+  float2* bufA = gsm + (size_t)team * 2 * N;
+  float2* bufB = bufA + N;
+  float* s_gm = reinterpret_cast<float*>(gsm + (size_t)pairs * 2 * N) + (size_t)team * 2 * p.n_mels;  // [2][n_mels]
+  const float* __restrict__ samples = static_cast<const float*>(p.samples);
+  const int hop = p.hop, n_freq = p.n_freq, n_mels = p.n_mels;
+
+  auto fft = [&](float2*& cur, float2*& oth) {  // forward transform of `cur`, in natural order, result in `cur`
+    int Ns = 1;
+    for (int s = 0; s < p.st.n; ++s) {
+      const int radix = p.st.radix[s];
+      switch (radix) {
+        case 4: stage_radix<4>(cur, oth, p.tw, N, Ns, lt, ts); break;
+        case 2: stage_radix<2>(cur, oth, p.tw, N, Ns, lt, ts); break;
+        case 3: stage_radix<3>(cur, oth, p.tw, N, Ns, lt, ts); break;
+        case 5: stage_radix<5>(cur, oth, p.tw, N, Ns, lt, ts); break;
+        default: stage_generic(cur, oth, p.tw64, N, Ns, radix, lt, ts); break;
+      }
+      __syncthreads();
+      float2* t = cur;
+      cur = oth;
+      oth = t;
+      Ns *= radix;
+    }
+  };
+
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const TileDesc ti = load_tile_desc(p.tiles, tile);
+    const int fa = 2 * team;
+    const bool a_valid = fa < ti.nvalid, b_valid = fa + 1 < ti.nvalid;
+    const float* src = samples + ti.s_off;
+    const long long fr_a = ti.out_frame0 + fa;
+    if (a_valid) {
+      const int s0 = ti.start + fa * hop;
+      for (int n = lt; n < N; n += ts) {
+        const float w = __ldg(p.window + n);
+        const float xa = __ldg(src + reflect_index(s0 + n, ti.L));
+        const float xb = b_valid ? __ldg(src + reflect_index(s0 + hop + n, ti.L)) : 0.f;
+        bufA[n] = make_float2(w * xa, w * xb);
+      }
+      if constexpr (kMel) {
+        const float* ga = grad_spec + fr_a * (long long)p.row_floats;
+        for (int m = lt; m < n_mels; m += ts) {
+          s_gm[m] = __ldg(ga + m);
+          s_gm[n_mels + m] = b_valid ? __ldg(ga + p.row_floats + m) : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+    float2* cur = bufA;
+    float2* oth = bufB;
+    fft(cur, oth);  // every thread takes part in the barriers; idle teams transform stale data that is never used
+    // ---- spectrum gradients -> packed, Hermitian-extended input of the inverse (re / im swapped) in `oth` --------
+    if (a_valid) {
+      auto g_power = [&](int k, int f) -> float {
+        if constexpr (kMel) {
+          const float* gm = s_gm + f * n_mels;
+          if (p.fb_dense != nullptr) {
+            float acc = 0.f;
+            for (int m = 0; m < n_mels; ++m) acc = fmaf(__ldg(p.fb_dense + (size_t)k * n_mels + m), gm[m], acc);
+            return acc;
+          }
+          if (k >= k_used) return 0.f;
+          const float2 w = __ldg(p.melw + k);
+          const int jj = __ldg(jk + k);
+          const float wr = (jj < n_mels) ? w.x : 0.f, wf = (jj >= 1) ? w.y : 0.f;
+          return fmaf(wr, gm[min(jj, n_mels - 1)], wf * gm[max(jj - 1, 0)]);
+        } else {
+          return (f == 0 || b_valid) ? __ldg(grad_spec + (fr_a + f) * (long long)p.row_floats + k) : 0.f;
+        }
+      };
+      for (int k = lt; k < n_freq; k += ts) {
+        const int km = (k == 0) ? 0 : N - k;
+        const float2 z = cur[k], m = cur[km];
+        const float ar = z.x + m.x, ai = z.y - m.y;
+        const float br = z.y + m.y, bi = m.x - z.x;
+        float gpa = g_power(k, 0), gpb = g_power(k, 1);
+        if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
+          gpa *= 0.5f * rsqrtf(fmaf(ar, ar, ai * ai) + 1e-9f);
+          gpb *= 0.5f * rsqrtf(fmaf(br, br, bi * bi) + 1e-9f);
+        }
+        const float ur = gpa * ar, ui = gpa * ai, vr = gpb * br, vi = gpb * bi;  // u = G_a / 2, v = G_b / 2
+        if (km == k) {  // k = 0, and k = N / 2 for even N: the spectrum is real there; C = Re G_a + i Re G_b
+          oth[k] = make_float2(2.f * vr, 2.f * ur);              // swapped: (im, re)
+        } else {
+          oth[k] = make_float2(ui + vr, ur - vi);                // u + i v, swapped
+          oth[km] = make_float2(vr - ui, ur + vi);               // conj(u) + i conj(v), swapped
+        }
+      }
+    }
+    __syncthreads();
+    float2* c2 = oth;
+    float2* o2 = cur;
+    fft(c2, o2);
+    // FFT(swap(C)) = swap(r_a + i r_b): r_a = imaginary part, r_b = real part; times the true window (2 x stored)
+    if (a_valid) {
+      float* fg = frame_grad + fr_a * (long long)N;
+      for (int n = lt; n < N; n += ts) {
+        const float w = 2.f * __ldg(p.window + n);
+        const float2 y = c2[n];
+        fg[n] = w * y.y;
+        if (b_valid) fg[N + n] = w * y.x;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <int SPEC>
 int launch_generic_s(int fmt, const GenParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
   if (fmt == EVF_SAMPLES_S16) {
@@ -351,6 +476,33 @@ int generic_configure(int spec_type, int sample_format, int smem_bytes) {
 
 int generic_launch(int spec_type, int sample_format, const GenParams& p, int grid, int smem_bytes, cudaStream_t stream) {
   return dispatch_generic(spec_type, sample_format, p, grid, smem_bytes, stream, false);
+}
+
+int generic_backward_launch(int spec_type, const GenParams& p, const float* grad_spec, float* frame_grad, const int* jk,
+                            int k_used, int grid, int smem_bytes, cudaStream_t st) {
+  // + [pairs][2][n_mels] mel gradients behind the FFT buffers
+  const int smem = smem_bytes + p.pairs * 2 * (p.n_mels > 0 ? p.n_mels : 0) * (int)sizeof(float);
+  if (smem > 227 * 1024) {
+    set_error("evf_features_backward: n_fft / n_mels too large for the backward's shared memory");
+    return EVF_ERR_UNSUPPORTED;
+  }
+#define EVF_LAUNCH_GBWD(SPEC)                                                                              \
+  {                                                                                                        \
+    auto k = features_generic_backward_kernel<SPEC>;                                                       \
+    EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                  \
+    k<<<grid, kGenThreads, smem, st>>>(p, grad_spec, frame_grad, jk, k_used);                              \
+  }
+  switch (spec_type) {
+    case EVF_SPEC_MEL: EVF_LAUNCH_GBWD(EVF_SPEC_MEL) break;
+    case EVF_SPEC_MEL_LIBROSA: EVF_LAUNCH_GBWD(EVF_SPEC_MEL_LIBROSA) break;
+    case EVF_SPEC_LINEAR: EVF_LAUNCH_GBWD(EVF_SPEC_LINEAR) break;
+    default:
+      set_error("evf_features_backward: spec_type has no backward (raw is complex)");
+      return EVF_ERR_UNSUPPORTED;
+  }
+#undef EVF_LAUNCH_GBWD
+  EVF_CUDA(cudaGetLastError());
+  return EVF_OK;
 }
 
 }  // namespace evf

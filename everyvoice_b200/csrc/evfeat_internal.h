@@ -136,6 +136,11 @@ int generic_factorize(int n_fft, GenStages* st, bool* needs_tw64);
 int generic_smem_bytes(int n_fft, int* pairs_out);
 int generic_configure(int spec_type, int sample_format, int smem_bytes);
 int generic_launch(int spec_type, int sample_format, const GenParams& p, int grid, int smem_bytes, cudaStream_t stream);
+int generic_backward_launch(int spec_type, const GenParams& p, const float* grad_spec, float* frame_grad, const int* jk,
+                            int k_used, int grid, int smem_bytes, cudaStream_t st);
+// evfeat_backward.cu: folds the per-frame gradient rows back onto the samples (reflect padding included)
+int overlap_add_launch(const float* frame_grad, const long long* sample_off, const long long* frame_off, int n_utts,
+                       long long max_len, int n_fft, int hop, float* grad_samples, cudaStream_t st);
 
 // evfeat_backward.cu
 struct BwdParams {

@@ -388,6 +388,16 @@ class SpectralTransform:
         (``T.MelSpectrogram`` / ``T.Spectrogram`` / the mel-librosa closure)."""
         return self.features(x, normalize=False, keep_last=True)
 
+    def training_mel(self, generated_wav: torch.Tensor, drop_first: bool = True) -> torch.Tensor:
+        """HiFiGAN's training-time mel of the generated audio (hfgl/model.py:719-721, 812-814):
+        ``dynamic_range_compression_torch(transform(wav).squeeze(1)[:, :, 1:])`` for ``wav[B, 1, L]`` -- the log is
+        fused into the kernel, the first frame is dropped like the reference does (its target mels come from
+        ``process_spec``'s ``[:, :L // hop]`` of a segment that starts one hop earlier).  Differentiable."""
+        y = self.features(generated_wav, normalize=True, keep_last=True)
+        if y.dim() >= 4 and y.shape[-3] == 1:
+            y = y.squeeze(-3)
+        return y[..., 1:] if drop_first else y
+
 
 def get_spectral_transform(
     spec_type,
