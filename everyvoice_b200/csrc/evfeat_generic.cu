@@ -38,6 +38,12 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }  // -i * a
 
+// A team (the threads of one frame pair: a multiple of 32) synchronises on its own named barrier; the teams of a CTA
+// never wait for each other.
+__device__ __forceinline__ void team_sync(int team, int ts) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(ts) : "memory");
+}
+
 template <int P>
 __device__ __forceinline__ void dft_small(float2 (&v)[P]);
 template <>
@@ -90,8 +96,9 @@ __device__ __forceinline__ void stage_radix(const float2* __restrict__ in, float
                                             const float2* __restrict__ tw, int N, int Ns, int lt, int ts) {
   const int nb = N / P;
   const int step = N / (Ns * P);
+  const bool pow2 = (Ns & (Ns - 1)) == 0;  // the usual case: no integer division in the loop
   for (int j = lt; j < nb; j += ts) {
-    const int k = j % Ns;
+    const int k = pow2 ? (j & (Ns - 1)) : (j % Ns);
     float2 v[P];
 #pragma unroll
     for (int r = 0; r < P; ++r) v[r] = in[j + r * nb];
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_kernel(const Gen
         bufA[n] = make_float2(w * xa, w * xb);
       }
     }
-    __syncthreads();
+    team_sync(team, ts);
     // ---- FFT ----------------------------------------------------------------------------------------------
     float2* cur = bufA;
     float2* oth = bufB;
@@ -180,7 +187,7 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_kernel(const Gen
           default: stage_generic(cur, oth, p.tw64, N, Ns, radix, lt, ts); break;
         }
       }
-      __syncthreads();
+      team_sync(team, ts);
       float2* t = cur;
       cur = oth;
       oth = t;
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_kernel(const Gen
       }
     }
     if constexpr (kMel) {
-      __syncthreads();
+      team_sync(team, ts);
       if (a_valid) {
         const int n_mels = p.n_mels;
         for (int o = lt; o < 2 * n_mels; o += ts) {
@@ -259,7 +266,7 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_kernel(const Gen
           s_red[2 * warp] = ea;
           s_red[2 * warp + 1] = eb;
         }
-        __syncthreads();
+        team_sync(team, ts);
         if (lt == 0 && a_valid) {
           const int w0 = (team * ts) >> 5, nw = ts >> 5;  // the team's warps (ts is a multiple of 32)
           float sa = 0.f, sb = 0.f;
@@ -272,7 +279,7 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_kernel(const Gen
         }
       }
     }
-    __syncthreads();  // the buffers are reused by the next tile
+    team_sync(team, ts);  // the team's buffers are reused by its next tile
   }
 }
 
@@ -311,7 +318,7 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_backward_kernel(
         case 5: stage_radix<5>(cur, oth, p.tw, N, Ns, lt, ts); break;
         default: stage_generic(cur, oth, p.tw64, N, Ns, radix, lt, ts); break;
       }
-      __syncthreads();
+      team_sync(team, ts);
       float2* t = cur;
       cur = oth;
       oth = t;
@@ -341,7 +348,7 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_backward_kernel(
         }
       }
     }
-    __syncthreads();
+    team_sync(team, ts);
     float2* cur = bufA;
     float2* oth = bufB;
     fft(cur, oth);  // every thread takes part in the barriers; idle teams transform stale data that is never used
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_backward_kernel(
         }
       }
     }
-    __syncthreads();
+    team_sync(team, ts);
     float2* c2 = oth;
     float2* o2 = cur;
     fft(c2, o2);
@@ -397,7 +404,7 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_backward_kernel(
         if (b_valid) fg[N + n] = w * y.x;
       }
     }
-    __syncthreads();
+    team_sync(team, ts);
   }
 }
 

@@ -23,12 +23,14 @@ WORK = {
     "melB": ("mel", 44100, 2048, 2048, 512, 128, 0, 8000),
     "librosaA": ("mel-librosa", 22050, 1024, 1024, 256, 80, 0, 8000),
     "melA_s16": ("mel", 22050, 1024, 1024, 256, 80, 0, 8000),
+    "mel512": ("mel", 16000, 512, 512, 128, 80, 0, 8000),        # any-size kernel
+    "mel4096": ("mel", 44100, 4096, 4096, 1024, 128, 0, 8000),   # any-size kernel
 }
 
 
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-    names = sys.argv[2].split(",") if len(sys.argv) > 2 else list(WORK)
+    names = sys.argv[2].split(",") if len(sys.argv) > 2 else [n for n in WORK if not n.startswith("mel5") and not n.startswith("mel4")]
     dev = torch.device("cuda", 0)
     tag = os.environ.get("EVF_TAG", Path(os.environ.get("EVF_LIB", "default")).stem)
     for name in names:
