@@ -29,7 +29,7 @@ SPEC_TYPES = {"mel": 0, "mel-librosa": 1, "linear": 2, "raw": 3}
 SAMPLES_F32, SAMPLES_S16 = 0, 1
 FFT_AUTO, FFT_GENERIC = 0, 1
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class evf_config(C.Structure):
@@ -79,6 +79,11 @@ PROTOTYPES = {
     "evf_features_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "evf_log_compress_backward": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, _P]),
     "evf_pitch_fill_unvoiced": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
+    # pitch tracking (DIO + StoneMask, restated from WORLD; parity unpinned)
+    "evf_pitch_num_frames": (C.c_int64, [C.c_int32, C.c_double, C.c_int64]),
+    "evf_pitch_scratch_bytes": (C.c_int64, [_P, C.c_int32, C.c_int32, C.c_double, C.c_int32]),
+    "evf_pitch_dio_stonemask": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_double,
+                                          C.c_double, C.c_double, C.c_double, _P, C.c_int64, _P, _P]),
     # audio front-end (process_audio numerics)
     "evf_resampler_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.POINTER(_P)]),
     "evf_resampler_destroy": (C.c_int, [_P]),

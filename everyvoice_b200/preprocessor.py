@@ -130,8 +130,9 @@ class Preprocessor:
         return res.utterance(0).cpu(), res.sr
 
     # ------------------------------------------------------------------------------------------
-    # Pitch (preprocessor.py:236-285): DIO / StoneMask stay with pyworld on the CPU like in the reference;
-    # everything after them runs on the device
+    # Pitch (preprocessor.py:236-285): DIO + StoneMask and everything after them run on the device.  pyworld is a
+    # third-party dependency that is not available offline: the kernels restate WORLD's published algorithm and are
+    # PARITY UNPINNED (include/evfeat.h, oracle/world_pitch.py).
     # ------------------------------------------------------------------------------------------
     def postprocess_pitch_batch(self, tracks):
         """``tracks``: list of float64 pitch tracks as pyworld returns them (0 = unvoiced).  Unvoiced frames are
@@ -143,24 +144,60 @@ class Preprocessor:
         lens = np.array([len(a) for a in arrs], dtype=np.int64)
         off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
         packed = torch.from_numpy(np.concatenate(arrs) if arrs else np.zeros(0)).to(device)
+        return self._fill_unvoiced(packed, off), off
+
+    def _fill_unvoiced(self, packed_f64: torch.Tensor, off: np.ndarray) -> torch.Tensor:
+        device = packed_f64.device
         out = torch.empty(int(off[-1]), dtype=torch.float32, device=device)
-        d_off = torch.from_numpy(off).to(device)
+        d_off = torch.from_numpy(np.ascontiguousarray(off, dtype=np.int64)).to(device)
         lib = _lib.load()
         with torch.cuda.device(device):
-            _lib.check(lib.evf_pitch_fill_unvoiced(_ptr(packed), _ptr(d_off), len(arrs), _ptr(out), _stream_ptr(device)))
-        return out, off
+            _lib.check(lib.evf_pitch_fill_unvoiced(_ptr(packed_f64), _ptr(d_off), len(off) - 1, _ptr(out), _stream_ptr(device)))
+        return out
+
+    def track_pitch_batch(self, samples: torch.Tensor, sample_offsets, speed: int = 4, f0_floor: float = 71.0,
+                          f0_ceil: float = 800.0, channels_in_octave: float = 2.0, allowed_range: float = 0.1):
+        """``pw.dio(x, sr, frame_period=hop / sr * 1000, speed=4)`` then ``pw.stonemask(x, f0, t, sr)`` (:257-277) for a
+        packed ragged batch (float32 or int16 PCM, on the device or not).  Returns ``(f0 packed float64 device tensor,
+        frame offsets)``: WORLD's ``f0_length = int(1000 * L / sr / frame_period) + 1`` values per utterance, 0 where
+        unvoiced."""
+        import ctypes as C
+
+        device = samples.device if samples.is_cuda else _require_cuda(self.device)
+        x = samples.to(device)
+        if x.dtype not in (torch.float32, torch.int16):
+            x = x.to(torch.float32)
+        x = x.contiguous()
+        off = np.ascontiguousarray(np.asarray(sample_offsets, dtype=np.int64))
+        n = len(off) - 1
+        sr = int(self.input_sampling_rate)
+        frame_period = self.audio_config.fft_hop_size / self.input_sampling_rate * 1000     # the reference's expression
+        lib = _lib.load()
+        flen = np.array([lib.evf_pitch_num_frames(sr, frame_period, int(L)) for L in np.diff(off)], dtype=np.int64)
+        f_off = np.concatenate([[0], np.cumsum(flen)]).astype(np.int64)
+        nbytes = int(lib.evf_pitch_scratch_bytes(off.ctypes.data_as(C.c_void_p), n, sr, frame_period, int(speed)))
+        if nbytes < 0:
+            raise ValueError("invalid arguments for the pitch tracker")
+        scratch = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+        f0 = torch.empty(int(f_off[-1]), dtype=torch.float64, device=device)
+        fmt = _lib.SAMPLES_S16 if x.dtype == torch.int16 else _lib.SAMPLES_F32
+        with torch.cuda.device(device):
+            _lib.check(lib.evf_pitch_dio_stonemask(_ptr(x), fmt, off.ctypes.data_as(C.c_void_p), n, sr, frame_period,
+                                                   int(speed), float(f0_floor), float(f0_ceil), float(channels_in_octave),
+                                                   float(allowed_range), _ptr(scratch), nbytes, _ptr(f0), _stream_ptr(device)))
+        return f0, f_off
+
+    def extract_pitch_batch(self, samples: torch.Tensor, sample_offsets):
+        """``extract_pitch`` for a packed ragged batch: tracker, then the unvoiced frames filled by interpolation.
+        Returns ``(pitch packed float32 device tensor, frame offsets)``."""
+        f0, f_off = self.track_pitch_batch(samples, sample_offsets)
+        return self._fill_unvoiced(f0, f_off), f_off
 
     def extract_pitch(self, audio_tensor: torch.Tensor):
-        """Reference: preprocessor.py:244-285, same argument and result (``[T]`` float32 CPU tensor).  pyworld's
-        ``dio`` (``speed=4``, ``frame_period = hop / sr * 1000``) and ``stonemask`` run on the CPU exactly as in the
-        reference (third-party C++; ImportError if pyworld is missing); the rest is ``postprocess_pitch_batch``."""
-        import pyworld as pw
-
-        x = audio_tensor.squeeze(0).detach().cpu().numpy().astype(np.float64)
-        pitch, t = pw.dio(x, self.input_sampling_rate,
-                          frame_period=self.audio_config.fft_hop_size / self.input_sampling_rate * 1000, speed=4)
-        pitch = pw.stonemask(x, pitch, t, self.input_sampling_rate)
-        out, _ = self.postprocess_pitch_batch([pitch])
+        """Reference: preprocessor.py:244-285, same argument and result (``[T]`` float32 CPU tensor): DIO (``speed=4``,
+        ``frame_period = hop / sr * 1000``), StoneMask, zeros -> interpolated -- all on the device."""
+        x = audio_tensor.squeeze(0).detach().reshape(-1)
+        out, _ = self.extract_pitch_batch(x, np.array([0, x.numel()], dtype=np.int64))
         return out.cpu()
 
     # ------------------------------------------------------------------------------------------

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define EVF_ABI_VERSION 9
+#define EVF_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define EVF_API __attribute__((visibility("default")))
@@ -193,6 +193,24 @@ EVF_API int evf_stats_merge(const double* parts_dev, int32_t n_parts, int32_t st
                     void* stream);
 EVF_API int evf_normalize_by_gathered_stats(float* values_dev, int64_t n, const double* parts_dev, int32_t n_parts,
                                     int32_t stride_doubles, void* stream);
+
+/* ---- pitch tracking: what Preprocessor.extract_pitch gets from pyworld,
+ * everyvoice/preprocessor/preprocessor.py:257-277 -- pw.dio(x, sr, frame_period = hop / sr * 1000, speed = 4) followed by
+ * pw.stonemask(x, f0, t, sr) -- for a ragged batch, in float64 like WORLD.  PARITY UNPINNED: pyworld (a wrapper of the
+ * WORLD vocoder, C++) is a third-party dependency that is not available offline; the kernels restate WORLD's published
+ * algorithm (dio.cpp, stonemask.cpp, matlabfunctions.cpp) and are tested against the CPU restatement oracle/world_pitch.py.
+ *   evf_pitch_num_frames  : WORLD's GetSamplesForDIO, (int)(1000.0 * n / fs / frame_period) + 1, the same double arithmetic
+ *   offsets_host          : [n_utts + 1] sample offsets into x_dev (HOST memory: the layout is planned on the host)
+ *   f0_out_dev            : packed float64 tracks, evf_pitch_num_frames entries per utterance (0 = unvoiced)
+ *   scratch_dev           : evf_pitch_scratch_bytes(...) bytes, 8-byte aligned
+ * pyworld's defaults: f0_floor 71, f0_ceil 800, channels_in_octave 2, allowed_range 0.1. */
+EVF_API int64_t evf_pitch_num_frames(int32_t sample_rate, double frame_period_ms, int64_t n_samples);
+EVF_API int64_t evf_pitch_scratch_bytes(const int64_t* offsets_host, int32_t n_utts, int32_t sample_rate,
+                                        double frame_period_ms, int32_t speed);
+EVF_API int evf_pitch_dio_stonemask(const void* x_dev, int32_t x_format, const int64_t* offsets_host, int32_t n_utts,
+                                    int32_t sample_rate, double frame_period_ms, int32_t speed, double f0_floor,
+                                    double f0_ceil, double channels_in_octave, double allowed_range, void* scratch_dev,
+                                    int64_t scratch_bytes, double* f0_out_dev, void* stream);
 
 /* Pitch post-processing of Preprocessor.extract_pitch, everyvoice/preprocessor/preprocessor.py:278-285 (everything
  * after pyworld's dio / stonemask, which stay on the CPU with the reference): zeros (unvoiced) are filled by linear

@@ -251,3 +251,56 @@ def test_gate_decisions_at_the_thresholds(cuda_device, golden_dir):
         res = pre.process_audio_batch(xs, sr, resample_rate=sr, hop_size=256)
         assert [i in res.kept for i in range(len(lens))] == [bool(gold[f"length/{sr}/{n}/keep"]) for n in lens]
         assert [res.skipped.get(i) for i in range(len(lens))] == ["audio_too_short", None, None, "audio_too_long"]
+
+
+def test_pitch_tracker_matches_the_world_restatement(cuda_device):
+    """DIO (speed 4) + StoneMask on the device against oracle/world_pitch.py (WORLD's published algorithm restated on
+    the CPU in its FFT-domain form; the kernels use the time-domain form).  PARITY UNPINNED: pyworld is not available
+    offline.  Voiced / unvoiced decisions must agree frame by frame, voiced f0 within 1e-6 relative (float64 both)."""
+    import everyvoice_b200 as ev
+    from everyvoice_b200 import synth
+    from oracle import world_pitch as W
+
+    sr, hop = 22050, 256
+    pre = ev.Preprocessor(ev.AudioConfig(spec_type="mel"), device=cuda_device)
+    rng = np.random.default_rng(31)
+    xs = []
+    for i in range(7):
+        n = int(rng.integers(12000, 70000)) // hop * hop
+        x = synth.speech_like(n, sr, seed=800 + i) * np.float32(rng.uniform(0.2, 0.9))
+        if i == 2:
+            x[: n // 3] = 0            # a silent stretch: unvoiced frames to interpolate over
+        if i == 4:
+            x = synth.white_noise(n, seed=9) * np.float32(0.3)
+        if i == 5:
+            x = np.zeros(n, np.float32)  # nothing voiced at all
+        xs.append(x.astype(np.float32))
+    packed, off = synth.pack_ragged(xs)
+    f0, f_off = pre.track_pitch_batch(torch.from_numpy(packed).to(cuda_device), off)
+    pitch, _ = pre.extract_pitch_batch(torch.from_numpy(packed).to(cuda_device), off)
+    fp = hop / sr * 1000
+    for b, x in enumerate(xs):
+        want, t = W.dio(x.astype(np.float64), sr, frame_period=fp, speed=4)
+        want = W.stonemask(x.astype(np.float64), want, t, sr)
+        got = f0[int(f_off[b]):int(f_off[b + 1])].cpu().numpy()
+        assert got.shape == want.shape == (len(x) // hop + 1,)
+        assert np.array_equal(got > 0, want > 0), (b, int(((got > 0) != (want > 0)).sum()))
+        v = want > 0
+        if v.any():
+            assert np.abs(got[v] / want[v] - 1.0).max() < 1e-6, b
+        full = pitch[int(f_off[b]):int(f_off[b + 1])].cpu().numpy()
+        assert np.array_equal(full, O_postprocess(want))
+    # the reference's single-utterance call
+    one = pre.extract_pitch(torch.from_numpy(xs[0])[None])
+    assert one.dtype == torch.float32 and np.array_equal(one.numpy(), pitch[: int(f_off[1])].cpu().numpy())
+    # int16 PCM input: the same samples as float
+    pcm = np.clip(np.rint(packed * 32768.0), -32768, 32767).astype(np.int16)
+    a, _ = pre.track_pitch_batch(torch.from_numpy(pcm).to(cuda_device), off)
+    bb, _ = pre.track_pitch_batch(torch.from_numpy(pcm.astype(np.float32) / np.float32(32768.0)).to(cuda_device), off)
+    assert torch.equal(a, bb)
+
+
+def O_postprocess(f0):
+    from oracle import ev_oracle as O
+
+    return O.postprocess_pitch(f0)
