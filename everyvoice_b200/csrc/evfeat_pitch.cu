@@ -7,9 +7,9 @@
 // follows WORLD's FFT-domain formulation, the kernels the equivalent time-domain one).  Everything is float64, like
 // WORLD.
 //
-//   dio_decimate_kernel   decimate(): 9 reflected margin samples, 3rd-order Chebyshev IIR forwards and backwards
-//                         (zero phase), every r-th sample; mean of the decimated signal.  The recursion is sequential:
-//                         one thread per utterance.
+//   dio_decimate_*_kernel decimate(): 9 reflected margin samples, 3rd-order Chebyshev IIR forwards and backwards
+//                         (zero phase), every r-th sample.  One thread per 256-sample segment with a run-in as long
+//                         as the filter's (measured) memory; dio_mean_kernel: mean of the decimated signal.
 //   dio_lowcut_kernel     DC removal + the 50 Hz low-cut FIR (minus a normalised Hann window plus a unit impulse; WORLD
 //                         multiplies spectra of a zero-padded FFT, which IS this linear convolution).
 //   dio_band_kernel       one warp per (utterance, band): Nuttall low-pass FIR of the band, the four zero-crossing
@@ -51,52 +51,94 @@ struct PitchLayout {
 __device__ __forceinline__ double sample_d(const float* x, long long i) { return (double)x[i]; }
 __device__ __forceinline__ double sample_d(const short* x, long long i) { return (double)((float)x[i] * (1.0f / 32768.0f)); }
 
+// decimate(): the 3rd-order IIR runs over the margin-extended signal forwards, then over the reversed result.  The
+// recursion is sequential, but the filter forgets: its impulse response falls below 1e-18 of its peak within `runin`
+// samples (host-measured from the coefficients), so a thread that starts `runin` samples early from a zero state
+// reproduces the sequential recursion to the last bit or two of float64.  One thread per segment of kDecSeg samples.
+constexpr int kDecSeg = 256;
 template <typename SampleT>
-__global__ void __launch_bounds__(64) dio_decimate_kernel(const SampleT* __restrict__ x, PitchLayout lay, int n_utts,
-                                                          DioParams P, double* __restrict__ fwd, double* __restrict__ y,
-                                                          double* __restrict__ mean_out) {
+__device__ __forceinline__ double dec_input(const SampleT* xs, long long n, long long i, double x_first, double x_last) {
+  if (i < kNFact) return 2.0 * x_first - sample_d(xs, kNFact - i);
+  if (i < kNFact + n) return sample_d(xs, i - kNFact);
+  return 2.0 * x_last - sample_d(xs, n - 2 - (i - (kNFact + n)));
+}
+
+template <typename SampleT>
+__global__ void __launch_bounds__(128) dio_decimate_fwd_kernel(const SampleT* __restrict__ x, PitchLayout lay, DioParams P,
+                                                               int runin, double* __restrict__ fwd) {
+  const int b = blockIdx.y;
+  const SampleT* xs = x + lay.x_off[b];
+  const long long n = lay.x_off[b + 1] - lay.x_off[b];
+  const long long total = n + 2 * kNFact;
+  const long long s0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * kDecSeg;
+  if (s0 >= total) return;
+  double* f = fwd + lay.x_off[b] + 2ll * kNFact * b;
+  const double a0 = P.dec_a[0], a1 = P.dec_a[1], a2 = P.dec_a[2], b0 = P.dec_b[0], b1 = P.dec_b[1];
+  const double x_first = sample_d(xs, 0), x_last = sample_d(xs, n - 1);
+  double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+  const long long start = s0 - runin > 0 ? s0 - runin : 0;
+  const long long end = s0 + kDecSeg < total ? s0 + kDecSeg : total;
+  for (long long i = start; i < end; ++i) {
+    const double wt = dec_input(xs, n, i, x_first, x_last) + a0 * w0 + a1 * w1 + a2 * w2;
+    if (i >= s0) f[i] = b0 * wt + b1 * w0 + b1 * w1 + b0 * w2;
+    w2 = w1;
+    w1 = w0;
+    w0 = wt;
+  }
+}
+
+__global__ void __launch_bounds__(128) dio_decimate_bwd_kernel(PitchLayout lay, DioParams P, int runin,
+                                                               const double* __restrict__ fwd, double* __restrict__ y) {
+  const int b = blockIdx.y;
+  const long long n = lay.x_off[b + 1] - lay.x_off[b];
+  const long long total = n + 2 * kNFact;
+  const long long s0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * kDecSeg;  // in the REVERSED sequence
+  if (s0 >= total) return;
+  const double* f = fwd + lay.x_off[b] + 2ll * kNFact * b;
+  const long long y_len = lay.y_off[b + 1] - lay.y_off[b];
+  double* yb = y + lay.y_off[b];
+  const double a0 = P.dec_a[0], a1 = P.dec_a[1], a2 = P.dec_a[2], b0 = P.dec_b[0], b1 = P.dec_b[1];
+  const long long nout = (n - 1) / P.r + 1;
+  const long long nbeg = P.r - P.r * nout + n;
+  double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+  const long long start = s0 - runin > 0 ? s0 - runin : 0;
+  const long long end = s0 + kDecSeg < total ? s0 + kDecSeg : total;
+  for (long long i = start; i < end; ++i) {
+    const double wt = f[total - 1 - i] + a0 * w0 + a1 * w1 + a2 * w2;
+    const double v = b0 * wt + b1 * w0 + b1 * w1 + b0 * w2;
+    w2 = w1;
+    w1 = w0;
+    w0 = wt;
+    if (i >= s0) {
+      const long long j = total - 1 - i;         // position in the re-reversed result
+      const long long idx = j - (kNFact - 1);    // decimate() reads tmp1[idx + kNFact - 1] for idx = nbeg, nbeg + r, ... < n + kNFact
+      if (idx >= nbeg && idx < n + kNFact && (idx - nbeg) % P.r == 0) {
+        const long long c = (idx - nbeg) / P.r;
+        if (c < y_len) yb[c] = v;
+      }
+    }
+  }
+}
+
+// r == 1 copy, zero fill past the decimated samples, and the mean (summed in index order, like WORLD's loop)
+template <typename SampleT>
+__global__ void __launch_bounds__(64) dio_mean_kernel(const SampleT* __restrict__ x, PitchLayout lay, int n_utts, DioParams P,
+                                                      double* __restrict__ y, double* __restrict__ mean_out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_utts) return;
   const SampleT* xs = x + lay.x_off[b];
   const long long n = lay.x_off[b + 1] - lay.x_off[b];
   const long long y_len = lay.y_off[b + 1] - lay.y_off[b];
   double* yb = y + lay.y_off[b];
+  long long n_set;  // entries of y the decimation wrote
   if (P.r == 1) {
     for (long long i = 0; i < y_len; ++i) yb[i] = (i < n) ? sample_d(xs, i) : 0.0;
+    n_set = y_len;
   } else {
-    double* f = fwd + lay.x_off[b] + 2ll * kNFact * b;
-    const long long total = n + 2 * kNFact;
-    const double a0 = P.dec_a[0], a1 = P.dec_a[1], a2 = P.dec_a[2], b0 = P.dec_b[0], b1 = P.dec_b[1];
-    double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-    const double x_first = sample_d(xs, 0), x_last = sample_d(xs, n - 1);
-    for (long long i = 0; i < total; ++i) {
-      double xin;
-      if (i < kNFact) xin = 2.0 * x_first - sample_d(xs, kNFact - i);
-      else if (i < kNFact + n) xin = sample_d(xs, i - kNFact);
-      else xin = 2.0 * x_last - sample_d(xs, n - 2 - (i - (kNFact + n)));
-      const double wt = xin + a0 * w0 + a1 * w1 + a2 * w2;
-      f[i] = b0 * wt + b1 * w0 + b1 * w1 + b0 * w2;
-      w2 = w1;
-      w1 = w0;
-      w0 = wt;
-    }
     const long long nout = (n - 1) / P.r + 1;
     const long long nbeg = P.r - P.r * nout + n;
-    for (long long i = 0; i < y_len; ++i) yb[i] = 0.0;
-    w0 = w1 = w2 = 0.0;
-    for (long long i = 0; i < total; ++i) {  // the reversed signal through the same filter; position j of the re-reversed result
-      const double wt = f[total - 1 - i] + a0 * w0 + a1 * w1 + a2 * w2;
-      const double v = b0 * wt + b1 * w0 + b1 * w1 + b0 * w2;
-      w2 = w1;
-      w1 = w0;
-      w0 = wt;
-      const long long j = total - 1 - i;
-      const long long idx = j - (kNFact - 1);  // decimate() reads tmp1[idx + kNFact - 1] for idx = nbeg, nbeg + r, ... < n + kNFact
-      if (idx >= nbeg && idx < n + kNFact && (idx - nbeg) % P.r == 0) {
-        const long long c = (idx - nbeg) / P.r;
-        if (c < y_len) yb[c] = v;
-      }
-    }
+    n_set = (n + kNFact - nbeg + P.r - 1) / P.r;
+    for (long long i = n_set; i < y_len; ++i) yb[i] = 0.0;
   }
   double sum = 0.0;
   for (long long i = 0; i < y_len; ++i) sum += yb[i];
@@ -221,8 +263,8 @@ __global__ void __launch_bounds__(kBandWarps * 32) dio_band_kernel(const double*
     const bool in0 = p >= 0 && p <= y_len - 2, in2 = p >= 0 && p <= y_len - 3;
     const bool fl[4] = {in0 && sp0 > 0.0 && sp1 <= 0.0, in0 && -sp0 > 0.0 && -sp1 <= 0.0,
                         in2 && d0 > 0.0 && d1 <= 0.0, in2 && -d0 > 0.0 && -d1 <= 0.0};
-    const double fine_s = (double)(p + 1) - sp0 / (sp1 - sp0);
-    const double fine_d = (double)(p + 1) - d0 / (d1 - d0);
+    const double fine_s = (fl[0] || fl[1]) ? (double)(p + 1) - sp0 / (sp1 - sp0) : 0.0;
+    const double fine_d = (fl[2] || fl[3]) ? (double)(p + 1) - d0 / (d1 - d0) : 0.0;
 #pragma unroll
     for (int kind = 0; kind < 4; ++kind) {
       unsigned mask = __ballot_sync(0xffffffffu, fl[kind]);
@@ -628,10 +670,42 @@ int evf_pitch_dio_stonemask(const void* x_dev, int32_t x_format, const int64_t* 
   // fwd rows are addressed as x_off[b] + 18 b: rebase so that utterance 0 starts at d_fwd
   double* fwd_base = d_fwd - x_off[0];
   const bool s16 = x_format == EVF_SAMPLES_S16;
+  if (P.r > 1) {
+    // how long the decimation filter remembers: impulse response below 1e-18 of its peak (measured, not assumed)
+    int runin = 64;
+    {
+      double w0 = 0, w1 = 0, w2 = 0, peak = 0;
+      int last_big = 0;
+      for (int i = 0; i < 20000; ++i) {
+        const double wt = (i == 0 ? 1.0 : 0.0) + P.dec_a[0] * w0 + P.dec_a[1] * w1 + P.dec_a[2] * w2;
+        const double v = std::fabs(P.dec_b[0] * wt + P.dec_b[1] * w0 + P.dec_b[1] * w1 + P.dec_b[0] * w2);
+        w2 = w1;
+        w1 = w0;
+        w0 = wt;
+        peak = v > peak ? v : peak;
+        if (v > 1e-18 * peak) last_big = i;
+      }
+      runin = last_big + 16;
+    }
+    long long max_total = 0;
+    for (int b = 0; b < n_utts; ++b) max_total = std::max(max_total, x_off[b + 1] - x_off[b] + 2 * kNFact);
+    const long long segs = (max_total + kDecSeg - 1) / kDecSeg;
+    for (int y0 = 0; y0 < n_utts; y0 += 65535) {
+      const int ny = n_utts - y0 < 65535 ? n_utts - y0 : 65535;
+      PitchLayout l2{lay.x_off + y0, lay.y_off + y0, lay.f_off + y0};
+      const dim3 grid((unsigned)((segs + 127) / 128), (unsigned)ny);
+      double* fb = fwd_base + 2ll * kNFact * y0;
+      if (s16) dio_decimate_fwd_kernel<short><<<grid, 128, 0, st>>>(static_cast<const short*>(x_dev), l2, P, runin, fb);
+      else dio_decimate_fwd_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(x_dev), l2, P, runin, fb);
+      EVF_CUDA(cudaGetLastError());
+      dio_decimate_bwd_kernel<<<grid, 128, 0, st>>>(l2, P, runin, fb, d_y);
+      EVF_CUDA(cudaGetLastError());
+    }
+  }
   if (s16)
-    dio_decimate_kernel<short><<<(n_utts + 63) / 64, 64, 0, st>>>(static_cast<const short*>(x_dev), lay, n_utts, P, fwd_base, d_y, d_mean);
+    dio_mean_kernel<short><<<(n_utts + 63) / 64, 64, 0, st>>>(static_cast<const short*>(x_dev), lay, n_utts, P, d_y, d_mean);
   else
-    dio_decimate_kernel<float><<<(n_utts + 63) / 64, 64, 0, st>>>(static_cast<const float*>(x_dev), lay, n_utts, P, fwd_base, d_y, d_mean);
+    dio_mean_kernel<float><<<(n_utts + 63) / 64, 64, 0, st>>>(static_cast<const float*>(x_dev), lay, n_utts, P, d_y, d_mean);
   EVF_CUDA(cudaGetLastError());
   {
     const size_t smem = (256 + 2 * (size_t)C) * sizeof(double);
