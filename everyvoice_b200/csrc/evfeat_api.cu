@@ -29,9 +29,13 @@ struct evf_plan {
   unsigned* d_ltab = nullptr;
   float2* d_melw = nullptr;  // per-bin {rising, falling} weights and interval index: the backward's transposed mel
   int* d_jk = nullptr;
-  // MODE_GENERIC (evfeat_generic.cu)
+  // MODE_GENERIC (evfeat_generic.cu); the n_fft 512 / 256 warp modes keep these too: their backward runs there
   evf::GenParams gen{};
+  bool has_gen = false;
   int gen_grid_per_sm = 1;
+  int gen_smem_bytes = 0;
+  int gen_frames_per_tile = 0;
+  float* d_gen_window = nullptr;  // natural order, pre-scaled by 0.5
   float2* d_tw = nullptr;
   double2* d_tw64 = nullptr;
   int* d_kstart = nullptr;
@@ -49,6 +53,9 @@ struct evf_batch {
   long long* d_sample_off = nullptr;
   long long* d_frame_off = nullptr;
   evf::TileDesc* d_tiles = nullptr;
+  // tiles of the any-size kernels when the plan's forward uses other tiles (n_fft 512 / 256: backward only)
+  int n_gen_tiles = 0;
+  evf::TileDesc* d_gen_tiles = nullptr;
 };
 
 namespace evf {
@@ -213,6 +220,7 @@ void free_plan_tables(evf_plan* p) {
   cudaFree(p->d_tw64);
   cudaFree(p->d_kstart);
   cudaFree(p->d_fb_dense);
+  cudaFree(p->d_gen_window);
 }
 
 // frames of an utterance of L samples: torch.stft(center=True) yields 1 + (L + 2 * (n_fft / 2) - n_fft) / hop
@@ -233,13 +241,13 @@ int create_generic_plan(evf_plan* p, const float* window_host, const float* fb_d
     set_error("evf_plan_create: n_fft has more prime factors than the stage list holds");
     return EVF_ERR_UNSUPPORTED;
   }
-  p->smem_bytes = generic_smem_bytes(N, &g.pairs);
-  if (p->smem_bytes < 0) {
+  p->gen_smem_bytes = generic_smem_bytes(N, &g.pairs);
+  if (p->gen_smem_bytes < 0) {
     set_error("evf_plan_create: n_fft is too large for the shared-memory FFT (two buffers of n_fft complex points "
               "must fit into 227 KB: n_fft <= 14 000)");
     return EVF_ERR_UNSUPPORTED;
   }
-  p->frames_per_tile = 2 * g.pairs;
+  p->gen_frames_per_tile = 2 * g.pairs;
   g.n_fft = N;
   g.hop = c.hop_length;
   g.n_freq = p->n_freq;
@@ -257,8 +265,8 @@ int create_generic_plan(evf_plan* p, const float* window_host, const float* fb_d
     tw[m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
     if (needs64) tw64[m] = make_double2(std::cos(ang), std::sin(ang));
   }
-  int rc = generic_configure(c.spec_type, c.sample_format, p->smem_bytes);
-  if (rc == EVF_OK) rc = upload(win, &p->d_window);
+  int rc = generic_configure(c.spec_type, c.sample_format, p->gen_smem_bytes);
+  if (rc == EVF_OK) rc = upload(win, &p->d_gen_window);
   if (rc == EVF_OK) rc = upload(tw, &p->d_tw);
   if (rc == EVF_OK) rc = upload(tw64, &p->d_tw64);
   if (rc == EVF_OK && mel) {
@@ -266,24 +274,25 @@ int create_generic_plan(evf_plan* p, const float* window_host, const float* fb_d
       std::vector<float> fb(fb_dense_host, fb_dense_host + (size_t)p->n_freq * c.n_mels);
       rc = upload(fb, &p->d_fb_dense);
     } else {
-      rc = upload(t.melw, &p->d_melw);
+      if (!p->d_melw) rc = upload(t.melw, &p->d_melw);
       if (rc == EVF_OK) rc = upload(t.kstart, &p->d_kstart);
       std::vector<int> jk(t.jk.begin(), t.jk.begin() + t.k_used);
-      if (rc == EVF_OK) rc = upload(jk, &p->d_jk);
+      if (rc == EVF_OK && !p->d_jk) rc = upload(jk, &p->d_jk);
     }
   }
   if (rc != EVF_OK) return rc;
-  g.window = p->d_window;
+  g.window = p->d_gen_window;
   g.tw = p->d_tw;
   g.tw64 = p->d_tw64;
   g.melw = p->d_melw;
   g.kstart = p->d_kstart;
   g.fb_dense = p->d_fb_dense;
   // resident CTAs per SM: shared memory (the opt-in 227 KB) and 2048 threads
-  int per_sm = (227 * 1024) / (p->smem_bytes + 1024);
+  int per_sm = (227 * 1024) / (p->gen_smem_bytes + 1024);
   if (per_sm > 8) per_sm = 8;
   if (per_sm < 1) per_sm = 1;
   p->gen_grid_per_sm = per_sm;
+  p->has_gen = true;
   return EVF_OK;
 }
 
@@ -349,14 +358,18 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   if (!p) return EVF_ERR_OUT_OF_MEMORY;
   p->cfg = *cfg;
   p->device = device;
-  // the warp-per-FFT kernel covers n_fft 1024 (any hop <= n_fft) and 2048 (even hops); everything else -- and
-  // whatever does not fit its shared-memory carve-up or its triangular-bank tables -- runs in the any-size kernel
+  // the warp-per-FFT kernel covers n_fft 1024, 512 and 256 (any hop <= n_fft) and 2048 (even hops); everything else --
+  // and whatever does not fit its shared-memory carve-up or its triangular-bank tables -- runs in the any-size kernel
   const bool fast_shape = cfg->fft_path == EVF_FFT_AUTO && cfg->hop_length <= cfg->n_fft &&
-                          (cfg->n_fft == 1024 || (cfg->n_fft == 2048 && (cfg->hop_length & 1) == 0));
-  p->mode = !fast_shape ? MODE_GENERIC : (cfg->n_fft == 1024 ? MODE_PACK2 : MODE_HALF);
+                          (cfg->n_fft == 1024 || cfg->n_fft == 512 || cfg->n_fft == 256 ||
+                           (cfg->n_fft == 2048 && (cfg->hop_length & 1) == 0));
+  p->mode = !fast_shape ? MODE_GENERIC
+                        : (cfg->n_fft == 1024 ? MODE_PACK2
+                                              : (cfg->n_fft == 512 ? MODE_PACK2_512
+                                                                   : (cfg->n_fft == 256 ? MODE_PACK2_256 : MODE_HALF)));
   p->n_freq = cfg->n_fft / 2 + 1;
   p->warps = kMaxWarps;  // one CTA per SM
-  p->frames_per_tile = (p->mode == MODE_HALF) ? p->warps : 32;     // 16 jobs of two frames (n_fft 1024)
+  p->frames_per_tile = p->warps * mode_frames_per_warp(p->mode);  // n_fft 1024: 16 jobs of two frames
   p->num_sms = prop.multiProcessorCount;
   p->row_floats = mel ? cfg->n_mels : (cfg->spec_type == EVF_SPEC_RAW ? 2 * p->n_freq : p->n_freq);
 
@@ -386,23 +399,27 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
       delete p;
       return rc;
     }
+    p->smem_bytes = p->gen_smem_bytes;
+    p->frames_per_tile = p->gen_frames_per_tile;
     *plan_out = p;
     return EVF_OK;
   }
+  const int n_pts = cfg->n_fft < kFftSize ? cfg->n_fft : kFftSize;  // points of one packed job
+  const int rows = n_pts / 32;                                       // its first-pass rows = lanes per job afterwards
   t.window.resize(cfg->n_fft);
   if (mode_is_pack2(p->mode)) {
-    // pair layout for LDS.64: [r][lane] = {w[32 * r + lane], w[32 * (r + 16) + lane]}, r < 16: the two inputs of
-    // one first-stage butterfly of the first pass (evfeat_fft.cuh, win_head); 0.5 is exact
-    for (int r = 0; r < 16; ++r)
+    // pair layout for LDS.64: [r][lane] = {w[32 * r + lane], w[32 * (r + rows / 2) + lane]}, r < rows / 2: the two
+    // inputs of one first-stage butterfly of the first pass (evfeat_fft.cuh, win_head); 0.5 is exact
+    for (int r = 0; r < rows / 2; ++r)
       for (int lane = 0; lane < 32; ++lane) {
         t.window[(r * 32 + lane) * 2 + 0] = 0.5f * window_host[32 * r + lane];
-        t.window[(r * 32 + lane) * 2 + 1] = 0.5f * window_host[32 * (r + 16) + lane];
+        t.window[(r * 32 + lane) * 2 + 1] = 0.5f * window_host[32 * (r + rows / 2) + lane];
       }
   } else {
     for (int i = 0; i < cfg->n_fft; ++i) t.window[i] = 0.5f * window_host[i];  // exact scaling
   }
-  // four-step twiddles W_1024^(n2 * k1), applied after the transpose (lane = k1) inside the first butterfly
-  // stage of the second pass: entry [n][lane] = {t[n], t[n + 16]}, n < 16
+  // four-step twiddles W_N^(n2 * k1), N = points of a job, applied after the transpose (lane = (job, k1)) inside the
+  // first butterfly stage of the second pass: entry [n][lane] = {t[n], t[n + 16]}, n < 16
   t.tw4.resize(kFftSize / 2);
   const double two_pi = 6.283185307179586476925286766559;
   for (int n = 0; n < 16; ++n) {
@@ -410,7 +427,7 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
       float c[2], sn[2];
       for (int h = 0; h < 2; ++h) {
         const int n2 = n + 16 * h;
-        const double ang = -two_pi * (double)((lane * n2) % kFftSize) / (double)kFftSize;
+        const double ang = -two_pi * (double)(((lane % rows) * n2) % n_pts) / (double)n_pts;
         c[h] = (float)std::cos(ang);
         sn[h] = (float)std::sin(ang);
       }
@@ -442,6 +459,8 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
     std::vector<int> jk(t.jk.begin(), t.jk.begin() + t.k_used);
     if (rc == EVF_OK) rc = upload(jk, &p->d_jk);
   }
+  // n_fft 512 / 256: the backward runs in the any-size kernels (own tables, own tiles: evf_batch_create)
+  if (rc == EVF_OK && mode_jobs_per_warp(p->mode) > 1) rc = create_generic_plan(p, window_host, nullptr, t);
   if (rc != EVF_OK) {
     free_plan_tables(p);
     delete p;
@@ -482,9 +501,11 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
   }
   const int hop = plan->cfg.hop_length, n_fft = plan->cfg.n_fft, fr = plan->frames_per_tile;
   std::vector<long long> s_off(n_utts + 1, 0), f_off(n_utts + 1, 0);
-  std::vector<TileDesc> tiles;
+  std::vector<TileDesc> tiles, gen_tiles;
   std::vector<int> tile_start(n_utts + 1, 0);
-  const int fpj = (plan->mode == MODE_HALF) ? 1 : 2;  // frames per FFT job
+  // frames a warp (any-size kernel: a team) loads together: the span of a tile covers whole groups
+  const int fpj = (plan->mode == MODE_GENERIC) ? 2 : mode_frames_per_warp(plan->mode);
+  const bool want_gen_tiles = plan->mode != MODE_GENERIC && plan->has_gen;
   for (int b = 0; b < n_utts; ++b) {
     tile_start[b] = (int)tiles.size();
     const int64_t L = sample_offsets_host[b + 1] - sample_offsets_host[b];
@@ -517,6 +538,19 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
       d.span = (njobs * fpj - 1) * hop + n_fft;
       tiles.push_back(d);
     }
+    if (want_gen_tiles) {
+      const int gfr = plan->gen_frames_per_tile;
+      for (int64_t f0 = 0; f0 < T; f0 += gfr) {
+        TileDesc d;
+        d.s_off = sample_offsets_host[b];
+        d.out_frame0 = f_off[b] + f0;
+        d.L = (int)L;
+        d.start = (int)(f0 * hop) - n_fft / 2;
+        d.nvalid = (int)((T - f0 < gfr) ? (T - f0) : gfr);
+        d.span = (((d.nvalid + 1) / 2) * 2 - 1) * hop + n_fft;
+        gen_tiles.push_back(d);
+      }
+    }
   }
   tile_start[n_utts] = (int)tiles.size();
   for (int b = 0; b <= n_utts; ++b) s_off[b] = n_utts ? sample_offsets_host[b] : 0;
@@ -537,10 +571,13 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
   // one device block, one copy: [sample offsets | frame offsets | tile descriptors]
   const size_t off_bytes = (size_t)(n_utts + 1) * sizeof(long long);
   const size_t tile_bytes = tiles.size() * sizeof(TileDesc);
-  std::vector<unsigned char> blob(2 * off_bytes + tile_bytes);
+  const size_t gen_tile_bytes = gen_tiles.size() * sizeof(TileDesc);
+  std::vector<unsigned char> blob(2 * off_bytes + tile_bytes + gen_tile_bytes);
   memcpy(blob.data(), s_off.data(), off_bytes);
   memcpy(blob.data() + off_bytes, f_off.data(), off_bytes);
   if (tile_bytes) memcpy(blob.data() + 2 * off_bytes, tiles.data(), tile_bytes);
+  if (gen_tile_bytes) memcpy(blob.data() + 2 * off_bytes + tile_bytes, gen_tiles.data(), gen_tile_bytes);
+  bt->n_gen_tiles = (int)gen_tiles.size();
   unsigned char* d_blob = nullptr;
   int rc = upload(blob, &d_blob);
   if (rc != EVF_OK) {
@@ -550,6 +587,7 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
   bt->d_sample_off = reinterpret_cast<long long*>(d_blob);  // owns the block
   bt->d_frame_off = reinterpret_cast<long long*>(d_blob + off_bytes);
   bt->d_tiles = reinterpret_cast<evf::TileDesc*>(d_blob + 2 * off_bytes);  // 16 * (n_utts + 1) bytes in: 16-byte aligned
+  bt->d_gen_tiles = reinterpret_cast<evf::TileDesc*>(d_blob + 2 * off_bytes + tile_bytes);
   *batch_out = bt;
   return EVF_OK;
 }
@@ -758,16 +796,16 @@ int evf_features_backward(const evf_plan* plan, const evf_batch* batch, const fl
     return EVF_ERR_INVALID_ARGUMENT;
   }
   DeviceGuard guard(plan->device);
-  if (plan->mode == MODE_GENERIC) {  // any n_fft / hop / mel basis: the shared-memory mixed-radix kernels
+  if (plan->mode == MODE_GENERIC || plan->has_gen) {  // any n_fft / hop / mel basis: the shared-memory mixed-radix kernels
     GenParams g = plan->gen;
     g.samples = samples_dev;
-    g.tiles = batch->d_tiles;
-    g.n_tiles = batch->n_tiles;
+    g.tiles = (plan->mode == MODE_GENERIC) ? batch->d_tiles : batch->d_gen_tiles;
+    g.n_tiles = (plan->mode == MODE_GENERIC) ? batch->n_tiles : batch->n_gen_tiles;
     g.apply_log = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int cap = plan->num_sms * plan->gen_grid_per_sm;
     int rc = generic_backward_launch(plan->cfg.spec_type, g, grad_spec_dev, scratch_dev, plan->d_jk, plan->k_used,
-                                     g.n_tiles < cap ? g.n_tiles : cap, plan->smem_bytes, st);
+                                     g.n_tiles < cap ? g.n_tiles : cap, plan->gen_smem_bytes, st);
     if (rc != EVF_OK) return rc;
     return overlap_add_launch(scratch_dev, batch->d_sample_off, batch->d_frame_off, batch->n_utts, batch->max_len,
                               plan->cfg.n_fft, plan->cfg.hop_length, grad_samples_dev, st);

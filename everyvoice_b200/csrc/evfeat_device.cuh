@@ -11,13 +11,32 @@ template <>
 struct ModeTraits<MODE_PACK2> {
   static constexpr int kNfft = 1024;
   static constexpr int kFramesPerJob = 2;
+  static constexpr int kJobs = 1;        // packed jobs a warp runs side by side
   using SlotT = float4;  // partial sums {rising a, rising b, falling a, falling b} of the two frames of a job
 };
 template <>
 struct ModeTraits<MODE_HALF> {
   static constexpr int kNfft = 2048;
   static constexpr int kFramesPerJob = 1;
+  static constexpr int kJobs = 1;
   using SlotT = float2;  // {rising, falling}
+};
+// n_fft 512 / 256: the warp's 32 x 32 register file holds 2 / 4 packed jobs of 16 x 32 / 8 x 32 points: lane n2 keeps
+// rows n1 < 32 / J of every job in register block j in the first pass, lane (j, k1) owns Z_j[k1 + (32 / J) * k2] after
+// the second (warp_fft1024_tail<J>)
+template <>
+struct ModeTraits<MODE_PACK2_512> {
+  static constexpr int kNfft = 512;
+  static constexpr int kFramesPerJob = 2;
+  static constexpr int kJobs = 2;
+  using SlotT = float4;
+};
+template <>
+struct ModeTraits<MODE_PACK2_256> {
+  static constexpr int kNfft = 256;
+  static constexpr int kFramesPerJob = 2;
+  static constexpr int kJobs = 4;
+  using SlotT = float4;
 };
 
 // Staged samples are kept in their input format (the bulk copy cannot convert); int16 PCM becomes
@@ -51,10 +70,14 @@ __device__ __forceinline__ float compress(float v, int apply_log, float clip) {
 // Shared-memory instruction diet: the four-step twiddles come as 16 LDS.128 (two per load), the
 // transposed reads as 2 x 16 LDS.64 (row stride 34 words keeps them 8-byte aligned and
 // conflict-free: half-warp lanes hit banks 2*lane, 2*lane + 1).
+// J = 2 / 4: J transforms of 1024 / J points side by side.  In: lane n2, register block j holds transform j's rows
+// (32 / J of them) after its span-1 stage.  Out: lane j * (32 / J) + k1 holds Z_j[k1 + (32 / J) * k2] at index k2; the
+// twiddle table is W_(1024 / J)^(n2 * k1) for the lane's k1.
+template <int J = 1>
 __device__ __forceinline__ void warp_fft1024_tail(float (&re)[32], float (&im)[32],
                                                   const float4* __restrict__ s_tw4,
                                                   float* __restrict__ scr, int lane) {
-  dft32_dit_tail(re, im);  // index k1 holds Y[k1][n2 = lane]
+  dft32_dit_tail_jobs<J>(re, im);  // index k1 (+ block j) holds Y_j[k1][n2 = lane]
   float tr[32], ti[32];
   {
     const float2* row = reinterpret_cast<const float2*>(scr + lane * kScrStride);

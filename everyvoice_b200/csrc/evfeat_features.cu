@@ -52,8 +52,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
   constexpr int kThreads = WARPS * 32;
   constexpr int NFFT = MT::kNfft;
   constexpr int FPJ = MT::kFramesPerJob;
+  constexpr int J = MT::kJobs;        // packed jobs side by side in the warp's register file (n_fft 512: 2, 256: 4)
+  constexpr int R1 = 32 / J;          // first-pass rows of a job = lanes that own a job's bins after the second pass
+  constexpr int FPW = FPJ * J;        // frames a warp owns per tile
+  constexpr bool kPack = (MODE != MODE_HALF);
   constexpr bool kMel = (SPEC == EVF_SPEC_MEL || SPEC == EVF_SPEC_MEL_LIBROSA);
-  constexpr bool kHalf = (MODE != MODE_PACK2);          // n_fft 2048: one frame per FFT + real-FFT split
+  constexpr bool kHalf = (MODE == MODE_HALF);           // n_fft 2048: one frame per FFT + real-FFT split
   using SlotT = typename MT::SlotT;                      // {rise a, rise b, fall a, fall b} or {rise, fall}
 
   extern __shared__ __align__(16) float smem[];
@@ -70,7 +74,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
   const int lane = tid & 31;
   const int warp = tid >> 5;
   float* scr = smem + p.off_warp + warp * p.warp_words;  // transpose scratch; the P column aliases it
-  SlotT* slots = reinterpret_cast<SlotT*>(scr + 32 * kScrStride);
+  // the P columns of J > 1 jobs (each padded to the walk's n_chunk * 32 bins) may outgrow the transpose scratch
+  const int scr_words = (J == 1) ? 32 * kScrStride : p.scr_words;
+  SlotT* slots = reinterpret_cast<SlotT*>(scr + scr_words);
   const int nbuf = p.nbuf;
 
   // ---- one-time setup: mbarriers, tables, zeroed scratch / slots ---------------------------
@@ -138,14 +144,53 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
     const TileInfo fut = tile_info(min(tile + 2 * G, p.n_tiles - 1));
     const int nvalid = cur.nvalid;
     const long long out_frame0 = cur.out_frame0;
-    const bool active = warp * FPJ < nvalid;
+    const bool active = warp * FPW < nvalid;
 
     mbar_wait(&s_bar[b], parity);
 
     float re[32], im[32];
     if (active) {
       // ---- samples -> registers, window fused into the first butterfly stage -------------
-      if constexpr (MODE == MODE_PACK2) {
+      if constexpr (J > 1) {
+        // J packed jobs of R1 rows: register block jj holds job jj (frames FPW * warp + 2 * jj, + 1 as re / im);
+        // window pairs {w[32 * r + lane], w[32 * (r + R1 / 2) + lane]} at [r][lane], r < R1 / 2
+        constexpr int HR = R1 / 2;
+        constexpr int LB = (R1 == 16) ? 3 : 2;  // log2(HR)
+        const SampleT* x0 = s_in + (FPW * warp) * hop + lane;
+        const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
+        if (hop * 4 == NFFT) {
+          // hop = n_fft / 4 = R1 / 4 sample rows: the warp's FPW frames share rows, (FPW - 1) * R1 / 4 + R1 row loads
+          // feed all of them (n_fft 512: 28 instead of 64)
+          constexpr int RH = R1 / 4;
+          constexpr int NV = (FPW - 1) * RH + R1;
+          float v[NV];
+#pragma unroll
+          for (int r = 0; r < NV; ++r) v[r] = to_float(x0[32 * r]);
+#pragma unroll
+          for (int jj = 0; jj < J; ++jj) {
+#pragma unroll
+            for (int r = 0; r < HR; ++r) {
+              const float2 w = wv[32 * r];
+              const int i = jj * R1 + 2 * bitrev_n(r, LB);
+              win_head(re[i], re[i + 1], v[(2 * jj) * RH + r], w.x, v[(2 * jj) * RH + r + HR], w.y);
+              win_head(im[i], im[i + 1], v[(2 * jj + 1) * RH + r], w.x, v[(2 * jj + 1) * RH + r + HR], w.y);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < J; ++jj) {
+            const SampleT* xa = x0 + (2 * jj) * hop;
+            const SampleT* xb = xa + hop;
+#pragma unroll
+            for (int r = 0; r < HR; ++r) {
+              const float2 w = wv[32 * r];
+              const int i = jj * R1 + 2 * bitrev_n(r, LB);
+              win_head(re[i], re[i + 1], to_float(xa[32 * r]), w.x, to_float(xa[32 * (r + HR)]), w.y);
+              win_head(im[i], im[i + 1], to_float(xb[32 * r]), w.x, to_float(xb[32 * (r + HR)]), w.y);
+            }
+          }
+        }
+      } else if constexpr (MODE == MODE_PACK2) {
         // window pairs: s_win holds {w[32*r + lane], w[32*(r + 16) + lane]} at [r][lane] (16 LDS.64): rows r and
         // r + 16 are the two inputs of one first-stage butterfly, which absorbs the window multiplication
         const SampleT* xa = s_in + (2 * warp) * hop + lane;
@@ -212,27 +257,39 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
     }
 
     if (active) {
-      warp_fft1024_tail(re, im, s_tw4, scr, lane);
+      warp_fft1024_tail<J>(re, im, s_tw4, scr, lane);
 
-      // ---- real-FFT separation; the mirrored bin lives in lane (32 - lane) % 32 -------
-      const int src_lane = (32 - lane) & 31;
-      const int fa = warp * FPJ;  // tile-local frame of this job (PACK2: fa and fa + 1)
+      // ---- real-FFT separation; the mirrored bin lives in lane (32 - lane) % 32 (of the job's R1 lanes) -------
+      const int k1 = lane & (R1 - 1);  // bin k = k1 + R1 * j of the lane's job
+      const int jw = lane / R1;        // the lane's job (J > 1)
+      const int src_lane = (lane & ~(R1 - 1)) | ((R1 - k1) & (R1 - 1));
+      const int fa = warp * FPW + FPJ * jw;  // tile-local frame of this lane's job (packed: fa and fa + 1)
       float esum_a = 0.f, esum_b = 0.f;
       float* ga = p.spec_out + (out_frame0 + fa) * (long long)p.row_floats;
       float* gb = ga + p.row_floats;
-      const bool b_valid = (MODE == MODE_PACK2) && (fa + 1 < nvalid);
+      const bool a_valid = (J == 1) || (fa < nvalid);
+      const bool b_valid = kPack && (fa + 1 < nvalid);
       // mel: every bin the walk below reads is rewritten by this job (zero-weight bins past k_used
       // included), so nothing stale -- a NaN of an earlier job -- can leak into this one
       const int kcap = kMel ? min(p.n_chunk * 32, NFFT / 2 + 1) : (NFFT / 2 + 1);
       // the P column of this job: PACK2 float2 {frame a, frame b} per bin, HALF one float per bin
-      float2* P2 = reinterpret_cast<float2*>(scr);
+      const int pstride = kMel ? p.n_chunk * 32 : 0;  // bins between the P columns of a warp's jobs (J > 1)
+      float2* P2 = reinterpret_cast<float2*>(scr) + ((J > 1) ? jw * pstride : 0);
       float* P1 = scr;
+      if constexpr (kMel && J > 1) {
+        // the walk reads n_chunk * 32 bins per job; those past the last bin carry zero weights but must not hold a
+        // NaN of another job's transposed data
+        for (int k = kcap + lane; k < pstride; k += 32) {
+#pragma unroll
+          for (int jj = 0; jj < J; ++jj) reinterpret_cast<float2*>(scr)[jj * pstride + k] = make_float2(0.f, 0.f);
+        }
+      }
 
 #pragma unroll
       for (int j = 0; j <= 16; ++j) {
-        const int k = lane + 32 * j;
+        const int k = k1 + R1 * j;
         // warp-uniform: does any lane of this row own a bin that is consumed?
-        bool need = 32 * j < kcap;
+        bool need = R1 * j < kcap;
         if constexpr (kHalf) need = need || (1024 - 32 * j - 31 < kcap);
         if (need) {
           float zr, zi, pr, pi;
@@ -240,21 +297,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
             zr = re[j];
             zi = im[j];
             // lane 0 is its own partner, with a different register (bin 32*(32-j) instead of 32*(31-j)+32-lane)
-            const float sr = (lane == 0) ? re[(32 - j) & 31] : re[31 - j];
-            const float si = (lane == 0) ? im[(32 - j) & 31] : im[31 - j];
+            const float sr = (k1 == 0) ? re[(32 - j) & 31] : re[31 - j];
+            const float si = (k1 == 0) ? im[(32 - j) & 31] : im[31 - j];
             pr = __shfl_sync(0xffffffffu, sr, src_lane);
             pi = __shfl_sync(0xffffffffu, si, src_lane);
           } else {  // bin 512 (lane 0 only): its own mirror
             zr = pr = re[16];
             zi = pi = im[16];
           }
-          if (j < 16 || lane == 0) {
-            if constexpr (MODE == MODE_PACK2) {
+          if (j < 16 || k1 == 0) {
+            if constexpr (kPack) {
               // window was pre-scaled by 1/2: X_a = Z[k] + conj(Z[N-k]), X_b = (Z[k] - conj(Z[N-k])) / i
               const float ar = zr + pr, ai = zi - pi;
               const float br = zi + pi, bi = pr - zr;
               if constexpr (SPEC == EVF_SPEC_RAW) {
-                reinterpret_cast<float2*>(ga)[k] = make_float2(ar, ai);
+                if (a_valid) reinterpret_cast<float2*>(ga)[k] = make_float2(ar, ai);
                 if (b_valid) reinterpret_cast<float2*>(gb)[k] = make_float2(br, bi);
               } else {
                 float pa = fmaf(ar, ar, ai * ai);
@@ -268,7 +325,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
                 } else {
                   const float va = compress(pa, p.apply_log, p.log_clip);
                   const float vb = compress(pb, p.apply_log, p.log_clip);
-                  ga[k] = va;
+                  if (a_valid) ga[k] = va;
                   esum_a = fmaf(va, va, esum_a);
                   if (b_valid) {
                     gb[k] = vb;
@@ -318,14 +375,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
 
       if constexpr (kMel) {
         // ---- mel step 1: lane = chunk of n bins; two running FMAs per bin and frame ---------
+        // (J > 1: the warp's jobs take turns; the slots are reused, the P columns lie pstride bins apart)
         __syncwarp();
         const int n = p.n_chunk;
+#pragma unroll 1
+        for (int jj = 0; jj < J; ++jj) {
+          const int fj = (J == 1) ? fa : warp * FPW + FPJ * jj;  // first frame of job jj (warp-uniform)
+          if (J > 1 && fj >= nvalid) break;
+          float* gja = (J == 1) ? ga : p.spec_out + (out_frame0 + fj) * (long long)p.row_floats;
+          float* gjb = gja + p.row_floats;
+          const bool jb_valid = (J == 1) ? b_valid : (kPack && fj + 1 < nvalid);
+          float ea = 0.f, eb = 0.f;
         {
           const float2* wp = s_wtab + lane;
           SlotT* dst = slots + (lt & 0xffffu);
           SlotT* dst_next = slots + (lt >> 16);
-          if constexpr (MODE == MODE_PACK2) {
-            const float2* pp = P2 + n * lane;
+          if constexpr (kPack) {
+            const float2* pp = ((J == 1) ? P2 : reinterpret_cast<const float2*>(scr) + jj * pstride) + n * lane;
             float ra = 0.f, rb = 0.f, fa_ = 0.f, fb = 0.f;
 #pragma unroll 4
             for (int i = 0; i < n; ++i, ++pp, wp += 32) {
@@ -370,7 +436,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
         const int m_pad = p.m_pad;
         for (int m = lane; m < n_mels; m += 32) {
           const unsigned* gp = s_gtab + m;
-          if constexpr (MODE == MODE_PACK2) {
+          if constexpr (kPack) {
             float va = 0.f, vb = 0.f;
             for (int c = 0; c <= nh; ++c, gp += m_pad) {
               const unsigned g = *gp;
@@ -383,11 +449,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
             }
             va = compress(va, apply_log, clip);
             vb = compress(vb, apply_log, clip);
-            ga[m] = va;
-            esum_a = fmaf(va, va, esum_a);
-            if (b_valid) {
-              gb[m] = vb;
-              esum_b = fmaf(vb, vb, esum_b);
+            gja[m] = va;
+            ea = fmaf(va, va, ea);
+            if (jb_valid) {
+              gjb[m] = vb;
+              eb = fmaf(vb, vb, eb);
             }
           } else {
             float va = 0.f;
@@ -397,21 +463,40 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
               va += slots[g >> 16].y;
             }
             va = compress(va, apply_log, clip);
-            ga[m] = va;
-            esum_a = fmaf(va, va, esum_a);
+            gja[m] = va;
+            ea = fmaf(va, va, ea);
+          }
+        }
+          if constexpr (J == 1) {
+            esum_a = ea;
+            esum_b = eb;
+          } else {
+            // every lane holds filters of job jj: reduce over the warp, then the next job reuses the slots
+            if (p.energy_out != nullptr) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                ea += __shfl_xor_sync(0xffffffffu, ea, o);
+                eb += __shfl_xor_sync(0xffffffffu, eb, o);
+              }
+              if (lane == 0) {
+                p.energy_out[out_frame0 + fj] = sqrtf(ea);
+                if (jb_valid) p.energy_out[out_frame0 + fj + 1] = sqrtf(eb);
+              }
+            }
+            __syncwarp();
           }
         }
       }
 
-      if constexpr (SPEC != EVF_SPEC_RAW) {
+      if constexpr (SPEC != EVF_SPEC_RAW && !(kMel && J > 1)) {
         if (p.energy_out != nullptr) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
+          for (int o = R1 / 2; o > 0; o >>= 1) {
             esum_a += __shfl_xor_sync(0xffffffffu, esum_a, o);
-            if constexpr (MODE == MODE_PACK2) esum_b += __shfl_xor_sync(0xffffffffu, esum_b, o);
+            if constexpr (kPack) esum_b += __shfl_xor_sync(0xffffffffu, esum_b, o);
           }
-          if (lane == 0) {
-            p.energy_out[out_frame0 + fa] = sqrtf(esum_a);
+          if (k1 == 0) {
+            if (a_valid) p.energy_out[out_frame0 + fa] = sqrtf(esum_a);
             if (b_valid) p.energy_out[out_frame0 + fa + 1] = sqrtf(esum_b);
           }
         }
@@ -455,6 +540,8 @@ int launch_m(int spec, int fmt, const FeatParams& p, int grid, int smem, cudaStr
 int dispatch(int mode, int spec, int fmt, const FeatParams& p, int grid, int smem, cudaStream_t st, bool cfg) {
   if (mode == MODE_PACK2) return launch_m<MODE_PACK2>(spec, fmt, p, grid, smem, st, cfg);
   if (mode == MODE_HALF) return launch_m<MODE_HALF>(spec, fmt, p, grid, smem, st, cfg);
+  if (mode == MODE_PACK2_512) return launch_m<MODE_PACK2_512>(spec, fmt, p, grid, smem, st, cfg);
+  if (mode == MODE_PACK2_256) return launch_m<MODE_PACK2_256>(spec, fmt, p, grid, smem, st, cfg);
   set_error("unknown FFT mode");
   return EVF_ERR_UNSUPPORTED;
 }
@@ -465,16 +552,24 @@ int dispatch(int mode, int spec, int fmt, const FeatParams& p, int grid, int sme
 int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, const PlanTables& t,
                         FeatParams* c) {
   const bool mel = (spec_type == EVF_SPEC_MEL || spec_type == EVF_SPEC_MEL_LIBROSA);
-  const int fpj = (mode == MODE_HALF) ? 1 : 2;  // frames per warp and tile
-  const int fr = warps * fpj;
+  const int fpj = (mode == MODE_HALF) ? 1 : 2;  // frames per job
+  const int jobs = mode_jobs_per_warp(mode);
+  const int fr = warps * mode_frames_per_warp(mode);
   const long long limit = 227 * 1024;  // one CTA per SM
   auto up4 = [](int w) { return (w + 3) & ~3; };
   c->n_chunk = t.n_chunk;
   c->n_heads = t.n_heads;
   c->m_pad = t.m_pad;
   c->n_slots = t.n_slots;
-  // the P column must fit into the transpose scratch it aliases
-  if (mel && t.n_chunk * 32 * fpj > 32 * kScrStride) return -1;
+  // the P column must fit into the transpose scratch it aliases (one job per warp); the padded P columns of several
+  // jobs extend the scratch instead
+  int scr_words = 32 * kScrStride;
+  if (mel) {
+    const int need = jobs * t.n_chunk * 32 * fpj;
+    if (jobs == 1 && need > scr_words) return -1;
+    if (need > scr_words) scr_words = up4(need);
+  }
+  c->scr_words = scr_words;
   // Prefer a ring of two input buffers (the refill of one overlaps the FFTs on the other); fall back
   // to one when the hop is so large that two do not fit.
   for (int nbuf = 2; nbuf >= 1; --nbuf) {
@@ -505,7 +600,7 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
       w += 32;
     }
     c->off_warp = w;
-    c->warp_words = 32 * kScrStride + (mel ? up4(t.n_slots * 2 * fpj) : 0);
+    c->warp_words = scr_words + (mel ? up4(t.n_slots * 2 * fpj) : 0);
     w += warps * c->warp_words;
     const long long bytes = 4ll * w;
     if (bytes <= limit) return (int)bytes;

@@ -106,6 +106,26 @@ EVF_HD void dft32_dit_tail(V (&re)[32], V (&im)[32]) {
   DitG<16, 0>::run(re, im);
 }
 
+// The same for J = 1, 2, 4 independent DFT-(32 / J) on the register blocks [j * 32 / J, (j + 1) * 32 / J): a DIT stage
+// of span H acts on every aligned block of 2H registers alike (its twiddles depend on the position inside the block
+// only), so J smaller transforms side by side are the DFT-32 without its last log2(J) stages.
+// In : block j, index i holds the span-1 output of the pair of rows (bitrev(i & ~1), + 16 / J) of transform j.
+template <int J, typename V>
+EVF_HD void dft32_dit_tail_jobs(V (&re)[32], V (&im)[32]) {
+  static_assert(J == 1 || J == 2 || J == 4, "1, 2 or 4 transforms per register file");
+  DitG<2, 0>::run(re, im);
+  DitG<4, 0>::run(re, im);
+  if constexpr (J <= 2) DitG<8, 0>::run(re, im);
+  if constexpr (J == 1) DitG<16, 0>::run(re, im);
+}
+
+// bit reversal of the low `bits` bits
+__host__ __device__ constexpr int bitrev_n(int x, int bits) {
+  int r = 0;
+  for (int b = 0; b < bits; ++b) r |= ((x >> b) & 1) << (bits - 1 - b);
+  return r;
+}
+
 // Plain first stage (span 1, twiddle 1) for callers without anything to fuse into it.
 // In: index i holds x[bitrev5(i)].
 template <typename V>

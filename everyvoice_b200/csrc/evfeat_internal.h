@@ -18,8 +18,13 @@ enum FftMode : int {
   MODE_PACK2 = 0,  // n_fft == 1024: two real frames packed as re/im of one complex FFT
   MODE_HALF = 1,   // n_fft == 2048: one real frame as a 1024-point complex FFT + split
   MODE_GENERIC = 2,  // any n_fft / hop: shared-memory mixed-radix FFT over frame pairs (evfeat_generic.cu)
+  MODE_PACK2_512 = 3,  // n_fft == 512: a warp runs TWO packed 512-point jobs (4 frames) as 2 x (16 x 32)
+  MODE_PACK2_256 = 4,  // n_fft == 256: a warp runs FOUR packed 256-point jobs (8 frames) as 4 x (8 x 32)
 };
-inline bool mode_is_pack2(int mode) { return mode == MODE_PACK2; }
+inline bool mode_is_pack2(int mode) { return mode == MODE_PACK2 || mode == MODE_PACK2_512 || mode == MODE_PACK2_256; }
+// packed jobs (frame pairs) a warp runs side by side, and frames a warp owns per tile
+inline int mode_jobs_per_warp(int mode) { return mode == MODE_PACK2_512 ? 2 : (mode == MODE_PACK2_256 ? 4 : 1); }
+inline int mode_frames_per_warp(int mode) { return mode == MODE_HALF ? 1 : 2 * mode_jobs_per_warp(mode); }
 
 // One frame tile of one utterance; built on the host by evf_batch_create so that the kernel
 // needs no dependent loads (tile -> utterance -> offsets) to start staging a tile.
@@ -41,8 +46,8 @@ struct FeatParams {
   float* spec_out;
   float* energy_out;
   // plan tables (global memory; copied to shared memory once per CTA)
-  const float* window;   // [n_fft], pre-scaled by 0.5; n_fft 1024: stored as pairs {w[32r + lane], w[32(r+16) + lane]} at [r][lane], r < 16
-  const float4* tw4;     // [16][32] four-step twiddles {t[n][lane], t[n+16][lane]}, t[n2][k1] = W_1024^(n2*k1)
+  const float* window;   // [n_fft], pre-scaled by 0.5; packed modes: stored as pairs {w[32r + lane], w[32(r+R/2) + lane]} at [r][lane], r < R/2, R = n_fft/32
+  const float4* tw4;     // [16][32] four-step twiddles {t[n][lane], t[n+16][lane]}, t[n2][lane] = W_N^(n2*k1), N = min(n_fft, 1024), k1 = lane % (N/32)
   const float2* wpost;   // MODE_HALF: exp(-2 pi i k / n_fft), k = 0..512
   // mel projection (per-warp bin walk, see evfeat_features.cu):
   const float2* wtab;    // [n_chunk][32] {rising weight (sign bit = flush after this bin), falling weight} of bin n_chunk*lane + i
@@ -62,6 +67,7 @@ struct FeatParams {
   // shared-memory carve-up, in 4-byte words from the start of dynamic shared memory
   int off_bar, off_in, off_in2, off_win, off_tw, off_wpost, off_wtab, off_gtab, off_ltab, off_warp;
   int warp_words;        // per-warp region: transpose scratch (aliased by the P column) + partial-sum slots
+  int scr_words;         // words of that region before the slots (32 * kScrStride unless several jobs' P columns need more)
   int nbuf;              // input tile buffers in the ring (2 or 1)
   int in_words;          // capacity of one input tile
 };

@@ -38,7 +38,7 @@ CONFIGS = {
     "B": (44100, 2048, 2048, 512, 128, 0, 8000),
     "Bfull": (44100, 2048, 2048, 512, 128, 0, 22050),
     "W": (22050, 1024, 800, 200, 80, 0, 8000),  # win_length < n_fft (window centre-padded)
-    # ---- the rest of the config-field domain (any-size FFT kernel) ----
+    # ---- the rest of the config-field domain (n_fft 512 / 256: warp kernel with 2 / 4 packed jobs; others: any-size kernel) ----
     "S512": (16000, 512, 512, 128, 80, 0, 8000),      # 16 kHz corpora
     "W512": (16000, 512, 400, 160, 80, 0, 8000),      # win < n_fft, hop not a power of two
     "R3": (16000, 3072, 3072, 768, 80, 0, 8000),      # "output" transform of a 16 -> 48 kHz vocoder config: 1024 * 3
@@ -51,6 +51,8 @@ CONFIGS = {
     "O1001": (22050, 1001, 1001, 250, 40, 0, 8000),   # odd n_fft = 7 * 11 * 13: direct-DFT stages, 1 + (L - 1) // hop frames
     "BigHop": (22050, 1024, 1024, 1024, 80, 0, 8000), # hop = n_fft: the warp kernel's input ring does not fit
     "Gap": (22050, 512, 512, 700, 80, 0, 8000),       # hop > n_fft: samples between frames are skipped
+    "S256": (8000, 256, 256, 64, 40, 0, 4000),        # 8 kHz telephone speech: four packed jobs per warp
+    "W256": (8000, 256, 200, 80, 40, 0, 3800),        # win < n_fft, hop not a power of two
 }
 SPEC_TYPES = ("mel", "mel-librosa", "linear", "raw")
 

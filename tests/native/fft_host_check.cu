@@ -11,7 +11,80 @@
 
 using namespace evf;
 
+// J packed transforms of N = 1024 / J points in one simulated warp (n_fft 512: J = 2, 256: J = 4): the index arithmetic
+// of features_kernel's J > 1 branch -- register block jj = job jj in the first pass, lane (jj, k1) afterwards.
+template <int J>
+int check_jobs() {
+  constexpr int N = 1024 / J, R1 = 32 / J, HR = R1 / 2, LB = (R1 == 16) ? 3 : 2;
+  std::vector<double> xr(J * N), xi(J * N), w(N);
+  srand(99 + J);
+  for (int n = 0; n < J * N; ++n) {
+    xr[n] = rand() / (double)RAND_MAX * 2 - 1;
+    xi[n] = rand() / (double)RAND_MAX * 2 - 1;
+  }
+  for (int n = 0; n < N; ++n) w[n] = 0.5 - 0.5 * std::cos(2 * M_PI * n / N);
+  static float Yr[32][32], Yi[32][32];  // [register][lane]
+  for (int lane = 0; lane < 32; ++lane) {
+    float re[32], im[32];
+    for (int jj = 0; jj < J; ++jj)
+      for (int r = 0; r < HR; ++r) {
+        const int i = jj * R1 + 2 * bitrev_n(r, LB);
+        const int na = 32 * r + lane, nb = 32 * (r + HR) + lane;
+        win_head(re[i], re[i + 1], (float)xr[jj * N + na], (float)w[na], (float)xr[jj * N + nb], (float)w[nb]);
+        win_head(im[i], im[i + 1], (float)xi[jj * N + na], (float)w[na], (float)xi[jj * N + nb], (float)w[nb]);
+      }
+    dft32_dit_tail_jobs<J>(re, im);
+    for (int p = 0; p < 32; ++p) {
+      Yr[p][lane] = re[p];
+      Yi[p][lane] = im[p];
+    }
+  }
+  std::vector<double> Zr(J * N), Zi(J * N);
+  for (int lane = 0; lane < 32; ++lane) {
+    const int jj = lane / R1, k1 = lane % R1;
+    float re[32], im[32], tr[32], ti[32];
+    for (int n2 = 0; n2 < 32; ++n2) {
+      tr[n2] = Yr[lane][n2];
+      ti[n2] = Yi[lane][n2];
+    }
+    for (int n = 0; n < 16; ++n) {
+      float c[2], s[2];
+      for (int h = 0; h < 2; ++h) {
+        const double ang = -2 * M_PI * ((k1 * (n + 16 * h)) % N) / N;
+        c[h] = (float)std::cos(ang);
+        s[h] = (float)std::sin(ang);
+      }
+      const int i = bitrev5(n);
+      if (n == 0)
+        tw_head<true>(re[i], im[i], re[i + 1], im[i + 1], tr[n], ti[n], c[0], s[0], tr[n + 16], ti[n + 16], c[1], s[1]);
+      else
+        tw_head<false>(re[i], im[i], re[i + 1], im[i + 1], tr[n], ti[n], c[0], s[0], tr[n + 16], ti[n + 16], c[1], s[1]);
+    }
+    dft32_dit_tail(re, im);
+    for (int k2 = 0; k2 < 32; ++k2) {
+      Zr[jj * N + k1 + R1 * k2] = re[k2];
+      Zi[jj * N + k1 + R1 * k2] = im[k2];
+    }
+  }
+  double worst = 0, scale = 0;
+  for (int jj = 0; jj < J; ++jj)
+    for (int k = 0; k < N; ++k) {
+      double ar = 0, ai = 0;
+      for (int n = 0; n < N; ++n) {
+        const double a = -2 * M_PI * ((long long)k * n % N) / N;
+        const double vr = xr[jj * N + n] * w[n], vi = xi[jj * N + n] * w[n];
+        ar += vr * std::cos(a) - vi * std::sin(a);
+        ai += vr * std::sin(a) + vi * std::cos(a);
+      }
+      worst = std::fmax(worst, std::fmax(std::fabs(ar - Zr[jj * N + k]), std::fabs(ai - Zi[jj * N + k])));
+      scale = std::fmax(scale, std::hypot(ar, ai));
+    }
+  printf("%d x fft%d max abs err %.3e (max |Z| %.3f)\n", J, N, worst, scale);
+  return worst < 2e-4 * (scale / 30 + 1) ? 0 : 1;
+}
+
 int main() {
+  if (check_jobs<2>() || check_jobs<4>()) return 1;
   const int N = 1024;
   std::vector<double> xr(N), xi(N), w(N);
   srand(1234);

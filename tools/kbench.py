@@ -23,14 +23,16 @@ WORK = {
     "melB": ("mel", 44100, 2048, 2048, 512, 128, 0, 8000),
     "librosaA": ("mel-librosa", 22050, 1024, 1024, 256, 80, 0, 8000),
     "melA_s16": ("mel", 22050, 1024, 1024, 256, 80, 0, 8000),
-    "mel512": ("mel", 16000, 512, 512, 128, 80, 0, 8000),        # any-size kernel
+    "mel512": ("mel", 16000, 512, 512, 128, 80, 0, 8000),        # warp kernel, two packed jobs per warp
+    "lin512": ("linear", 16000, 512, 512, 128, 80, 0, 8000),
+    "mel256": ("mel", 8000, 256, 256, 64, 40, 0, 4000),          # warp kernel, four packed jobs per warp
     "mel4096": ("mel", 44100, 4096, 4096, 1024, 128, 0, 8000),   # any-size kernel
 }
 
 
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-    names = sys.argv[2].split(",") if len(sys.argv) > 2 else [n for n in WORK if not n.startswith("mel5") and not n.startswith("mel4")]
+    names = sys.argv[2].split(",") if len(sys.argv) > 2 else [n for n in WORK if "512" not in n and "256" not in n and "4096" not in n]
     dev = torch.device("cuda", 0)
     tag = os.environ.get("EVF_TAG", Path(os.environ.get("EVF_LIB", "default")).stem)
     for name in names:
