@@ -27,9 +27,10 @@ EVF_ERR_OUT_OF_MEMORY = 7
 # evf_spec_type  (everyvoice/config/preprocessing_config.py:18-22)
 SPEC_TYPES = {"mel": 0, "mel-librosa": 1, "linear": 2, "raw": 3}
 SAMPLES_F32, SAMPLES_S16 = 0, 1
+GRAD_FRAME_MAJOR, GRAD_BIN_MAJOR = 0, 1   # evf_features_backward_ex: layout of the incoming gradient
 FFT_AUTO, FFT_GENERIC = 0, 1
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 
 class evf_config(C.Structure):
@@ -77,6 +78,7 @@ PROTOTYPES = {
     # backward of the transform / of the log compression (training through the mel, hfgl/model.py:581-590)
     "evf_features_backward_scratch_floats": (C.c_int64, [_P, _P]),
     "evf_features_backward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "evf_features_backward_ex": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, _P, _P]),
     "evf_log_compress_backward": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, _P]),
     "evf_pitch_fill_unvoiced": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
     # pitch tracking (DIO + StoneMask, restated from WORLD; parity unpinned)

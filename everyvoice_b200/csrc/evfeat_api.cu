@@ -781,20 +781,46 @@ int64_t evf_features_backward_scratch_floats(const evf_plan* plan, const evf_bat
 
 int evf_features_backward(const evf_plan* plan, const evf_batch* batch, const float* samples_dev,
                           const float* grad_spec_dev, float* scratch_dev, float* grad_samples_dev, void* stream) {
+  if (plan && plan->cfg.apply_log) {
+    set_error("evf_features_backward: needs a linear-domain plan (apply_log = 0; the log has its own backward, "
+              "evf_log_compress_backward, or is folded in by evf_features_backward_ex)");
+    return EVF_ERR_UNSUPPORTED;
+  }
+  return evf_features_backward_ex(plan, batch, samples_dev, grad_spec_dev, EVF_GRAD_FRAME_MAJOR, nullptr, scratch_dev,
+                                  grad_samples_dev, stream);
+}
+
+int evf_features_backward_ex(const evf_plan* plan, const evf_batch* batch, const float* samples_dev,
+                             const float* grad_spec_dev, int32_t grad_layout, const float* log_spec_dev,
+                             float* scratch_dev, float* grad_samples_dev, void* stream) {
   if (!plan || !batch || batch->device != plan->device) {
     set_error("evf_features_backward: invalid plan / batch");
     return EVF_ERR_INVALID_ARGUMENT;
   }
-  if (plan->cfg.sample_format != EVF_SAMPLES_F32 || plan->cfg.apply_log || plan->cfg.spec_type == EVF_SPEC_RAW) {
-    set_error("evf_features_backward: needs float32 samples, a linear-domain plan (apply_log = 0; the log has its own "
-              "backward, evf_log_compress_backward) and a real spec_type");
+  if (plan->cfg.sample_format != EVF_SAMPLES_F32 || plan->cfg.spec_type == EVF_SPEC_RAW) {
+    set_error("evf_features_backward: needs float32 samples and a real spec_type");
     return EVF_ERR_UNSUPPORTED;
+  }
+  if (grad_layout != EVF_GRAD_FRAME_MAJOR && grad_layout != EVF_GRAD_BIN_MAJOR) {
+    set_error("evf_features_backward_ex: unknown grad_layout");
+    return EVF_ERR_INVALID_ARGUMENT;
+  }
+  if (plan->cfg.apply_log && !log_spec_dev) {
+    set_error("evf_features_backward_ex: a plan with apply_log = 1 needs the forward's log output (log_spec_dev)");
+    return EVF_ERR_INVALID_ARGUMENT;
   }
   if (batch->n_tiles == 0) return EVF_OK;
   if (!samples_dev || !grad_spec_dev || !scratch_dev || !grad_samples_dev) {
     set_error("evf_features_backward: null pointer");
     return EVF_ERR_INVALID_ARGUMENT;
   }
+  GradSrc gs{};
+  gs.grad = grad_spec_dev;
+  gs.log_spec = log_spec_dev;
+  gs.log_clip = plan->cfg.log_clip;
+  gs.bin_major = (grad_layout == EVF_GRAD_BIN_MAJOR);
+  gs.keep_last = plan->cfg.keep_last_frame;
+  gs.row = plan->row_floats;
   DeviceGuard guard(plan->device);
   if (plan->mode == MODE_GENERIC || plan->has_gen) {  // any n_fft / hop / mel basis: the shared-memory mixed-radix kernels
     GenParams g = plan->gen;
@@ -804,7 +830,7 @@ int evf_features_backward(const evf_plan* plan, const evf_batch* batch, const fl
     g.apply_log = 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int cap = plan->num_sms * plan->gen_grid_per_sm;
-    int rc = generic_backward_launch(plan->cfg.spec_type, g, grad_spec_dev, scratch_dev, plan->d_jk, plan->k_used,
+    int rc = generic_backward_launch(plan->cfg.spec_type, g, gs, scratch_dev, plan->d_jk, plan->k_used,
                                      g.n_tiles < cap ? g.n_tiles : cap, plan->gen_smem_bytes, st);
     if (rc != EVF_OK) return rc;
     return overlap_add_launch(scratch_dev, batch->d_sample_off, batch->d_frame_off, batch->n_utts, batch->max_len,
@@ -814,7 +840,7 @@ int evf_features_backward(const evf_plan* plan, const evf_batch* batch, const fl
   p.samples = samples_dev;
   p.tiles = batch->d_tiles;
   p.n_tiles = batch->n_tiles;
-  p.grad_spec = grad_spec_dev;
+  p.gs = gs;
   p.frame_grad = scratch_dev;
   p.grad_samples = grad_samples_dev;
   p.window = plan->d_window;

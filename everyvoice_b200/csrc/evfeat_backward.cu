@@ -13,9 +13,14 @@
 //   3. dL/d(windowed frame)[n] = Re sum_{k=0}^{N/2} G[k] e^{+2 pi i k n / N}: the one-sided spectra of both frames are
 //      Hermitian-extended and packed as C = C_a + i C_b, whose unnormalised inverse DFT is r_a + i r_b; the inverse
 //      runs through the SAME forward FFT code with real and imaginary parts swapped on the way in and out;
-//   4. times the window -> one row of 1024 frame gradients per frame (scratch);
-// then overlap_add_kernel gathers, for every sample, the <= n_fft / hop frame rows that cover it, plus the rows that
-// cover its mirror images in the reflect padding.  No atomics; the result is deterministic.
+//   4. times the window -> one row of n_fft frame gradients per frame.
+// The rows of a tile (32 / 16 consecutive frames of one utterance) overlap; they are summed INSIDE the tile, in shared
+// memory, in rounds of frames that do not overlap (frame t takes part in round t mod ceil(n_fft / hop); a barrier
+// between rounds: no atomics, a fixed order), and only the tile's span of (frames - 1) * hop + n_fft sums goes to the
+// scratch (3.7x less than the rows for hop = n_fft / 4).  tile_overlap_add_kernel then gathers, for every sample, the
+// <= 2 tile sums that cover it, plus those that cover its mirror images in the reflect padding.  Deterministic.
+// Hops so large or so small that the tile's span does not fit beside the FFT scratch (or that need more than 16
+// rounds) keep the per-frame rows and overlap_add_kernel (kTileSum = false).
 #include "evfeat_fft.cuh"
 #include "evfeat_internal.h"
 
@@ -25,7 +30,9 @@ namespace {
 
 #include "evfeat_device.cuh"
 
-constexpr int kBwdWarps = 16;
+// A CTA of 8 warps handles HALF a forward tile (16 / 8 frames); two CTAs share an SM, so that one's barrier rounds and
+// copy-out overlap the other's FFTs.
+constexpr int kBwdWarps = 8;
 constexpr int kGmStride = 128;  // n_mels <= 128 gradient values per frame in shared memory
 
 // MODE_PACK2 (n_fft 1024): two frames per job as real / imaginary part.  MODE_HALF (n_fft 2048): one frame per job as
@@ -33,8 +40,8 @@ constexpr int kGmStride = 128;  // n_mels <= 128 gradient values per frame in sh
 // inverse: with Y = G / 2 (Y_0 = Re G_0, Y_1024 = Re G_1024),  A[k] = Y[k] + conj(Y[M - k]),
 // B[k] = (Y[k] - conj(Y[M - k])) e^{+2 pi i k / 2048},  Zin[k] = A[k] + i B[k] (k < M = 1024; Zin[M - k] =
 // conj(A[k]) + i conj(B[k])), and the unnormalised inverse DFT of Zin is  g_v[2m] + i g_v[2m + 1].
-template <int MODE, int SPEC>
-__global__ void __launch_bounds__(kBwdWarps * 32, 1) features_backward_kernel(const BwdParams p) {
+template <int MODE, int SPEC, bool kTileSum>
+__global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(const BwdParams p) {
   constexpr bool kHalf = (MODE == MODE_HALF);
   constexpr int NFFT = kHalf ? 2048 : 1024;
   constexpr int FPJ = kHalf ? 1 : 2;
@@ -45,26 +52,58 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) features_backward_kernel(co
   float2* s_wpost = reinterpret_cast<float2*>(smem + NFFT + 2 * kFftSize);   // MODE_HALF: (cos, -sin)(2 pi k / 2048)
   float* s_warp = smem + NFFT + 2 * kFftSize + (kHalf ? 1028 : 0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* scr = s_warp + warp * (32 * kScrStride + 2 * kGmStride);
-  float* gm = scr + 32 * kScrStride;                                 // [2][kGmStride] mel gradients of frames a, b
+  float* scr = s_warp + warp * (32 * kScrStride + 4 * kGmStride);
+  float* gm = scr + 32 * kScrStride;                                 // [2][kGmStride] mel gradients of frames a, b (+ [2][kGmStride] log values)
+  float* s_acc = s_warp + kBwdWarps * (32 * kScrStride + 4 * kGmStride);  // kTileSum: the tile's span of summed rows
 
   for (int i = tid; i < NFFT; i += kBwdWarps * 32) s_win[i] = p.window[i];
   for (int i = tid; i < kFftSize / 2; i += kBwdWarps * 32) s_tw4[i] = p.tw4[i];
   if constexpr (kHalf)
     for (int i = tid; i <= 512; i += kBwdWarps * 32) s_wpost[i] = p.wpost[i];
-  for (int i = tid; i < kBwdWarps * (32 * kScrStride + 2 * kGmStride); i += kBwdWarps * 32) s_warp[i] = 0.f;
+  for (int i = tid; i < kBwdWarps * (32 * kScrStride + 4 * kGmStride); i += kBwdWarps * 32) s_warp[i] = 0.f;
+  TileDesc ti = p.tiles[blockIdx.x >> 1];
+  const int hop = p.hop;
+  {  // this CTA's half of the tile: frames [half * FPT, half * FPT + FPT)
+    constexpr int FPT = FPJ * kBwdWarps;
+    const int half = blockIdx.x & 1;
+    ti.nvalid -= half * FPT;
+    if (ti.nvalid <= 0) return;
+    if (ti.nvalid > FPT) ti.nvalid = FPT;
+    ti.start += half * FPT * hop;
+    ti.out_frame0 += half * FPT;
+  }
+  const int span_valid = (ti.nvalid - 1) * hop + NFFT;  // padded positions the CTA's frames cover
+  if constexpr (kTileSum)
+    for (int i = tid; i < span_valid; i += kBwdWarps * 32) s_acc[i] = 0.f;
   __syncthreads();
 
-  const TileDesc ti = p.tiles[blockIdx.x];
   const int fa = FPJ * warp;
-  if (fa >= ti.nvalid) return;
+  const bool a_valid = fa < ti.nvalid;
+  const GradView gv(p.gs, ti, NFFT, hop);
+  if (!kTileSum && !a_valid) return;
   const bool b_valid = !kHalf && (fa + 1 < ti.nvalid);
-  const int hop = p.hop;
+  float re[32], im[32];
+  if (a_valid) {
+  // mel gradients (and, fused log, the forward's log output) of the warp's frames: copied global -> shared
+  // asynchronously now, consumed after the forward FFT (the scattered [F][T] layout autograd hands back would
+  // otherwise stall the warp for a DRAM round trip per filter)
+  float* gy = gm + 2 * kGmStride;  // [2][kGmStride] raw log values
+  if constexpr (kMel) {
+    for (int m = lane; m < p.n_mels; m += 32) {
+#pragma unroll
+      for (int f = 0; f < FPJ; ++f) {
+        if (f == 0 || b_valid) {
+          cp_async4(gm + f * kGmStride + m, gv.g + gv.g_index(fa + f, m));
+          if (gv.y != nullptr) cp_async4(gy + f * kGmStride + m, gv.y + gv.y_index(fa + f, m));
+        }
+      }
+    }
+    cp_async_commit();
+  }
   const float* xs = p.samples + ti.s_off;
   const long long frame_a = ti.out_frame0 + fa;
 
   // ---- forward recomputation: samples -> window-fused first stage -> FFT ------------------------------
-  float re[32], im[32];
   if constexpr (!kHalf) {
     const int ua = ti.start + fa * hop + lane, ub = ua + hop;
     const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
@@ -93,11 +132,18 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) features_backward_kernel(co
   warp_fft1024_tail(re, im, s_tw4, scr, lane);
 
   // ---- mel gradients of the frame(s) -> shared memory ----------------------------------------------------
-  const float* ga = p.grad_spec + frame_a * p.row_floats;
   if constexpr (kMel) {
-    for (int m = lane; m < p.n_mels; m += 32) {
-      gm[m] = __ldg(ga + m);
-      gm[kGmStride + m] = b_valid ? __ldg(ga + p.row_floats + m) : 0.f;
+    cp_async_wait_all();
+    for (int m = lane; m < p.n_mels; m += 32) {  // every lane finishes the words it copied itself
+#pragma unroll
+      for (int f = 0; f < FPJ; ++f) {
+        float v = 0.f;
+        if (f == 0 || b_valid) {
+          v = gm[f * kGmStride + m];
+          if (gv.y != nullptr) v = gv.chain(v, gy[f * kGmStride + m]);
+        }
+        gm[f * kGmStride + m] = v;
+      }
     }
     __syncwarp();
   }
@@ -111,7 +157,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) features_backward_kernel(co
       const float wr = (jj < p.n_mels) ? w.x : 0.f, wf = (jj >= 1) ? w.y : 0.f;
       return fmaf(wr, gm[f * kGmStride + m_r], wf * gm[f * kGmStride + m_f]);
     } else {
-      return (f == 0 || b_valid) ? __ldg(ga + f * p.row_floats + k) : 0.f;
+      return (f == 0 || b_valid) ? gv.at(fa + f, k) : 0.f;
     }
   };
   // mel-librosa: mel = basis @ sqrt(P + 1e-9), dM/dP = 1 / (2 sqrt(P + 1e-9))
@@ -219,23 +265,138 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 1) features_backward_kernel(co
   // FFT(swap(C)) = swap(y): real part of the inverse = im, imaginary part = re; element n = lane + 32 k2
 
   // ---- times the (true) window -> frame-gradient rows --------------------------------------------------------
-  float* fg_a = p.frame_grad + frame_a * NFFT;
-  if constexpr (!kHalf) {
-    const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
+  if constexpr (!kTileSum) {
+    float* fg_a = p.frame_grad + frame_a * NFFT;
+    if constexpr (!kHalf) {
+      const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
 #pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2) {
-      const float2 wp = wv[32 * (k2 & 15)];
-      const float w = 2.f * ((k2 < 16) ? wp.x : wp.y);
-      fg_a[lane + 32 * k2] = w * im[k2];
-      if (b_valid) fg_a[NFFT + lane + 32 * k2] = w * re[k2];
+      for (int k2 = 0; k2 < 32; ++k2) {
+        const float2 wp = wv[32 * (k2 & 15)];
+        const float w = 2.f * ((k2 < 16) ? wp.x : wp.y);
+        fg_a[lane + 32 * k2] = w * im[k2];
+        if (b_valid) fg_a[NFFT + lane + 32 * k2] = w * re[k2];
+      }
+    } else {
+      const float2* w2 = reinterpret_cast<const float2*>(s_win) + lane;
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) {
+        const float2 w = w2[32 * k2];  // {w[2m], w[2m + 1]} / 2, m = lane + 32 k2
+        reinterpret_cast<float2*>(fg_a)[lane + 32 * k2] = make_float2(2.f * w.x * im[k2], 2.f * w.y * re[k2]);
+      }
     }
   } else {
-    const float2* w2 = reinterpret_cast<const float2*>(s_win) + lane;
+    // keep the windowed rows in the FFT registers: im = frame a (MODE_HALF: even samples), re = frame b (odd samples)
+    if constexpr (!kHalf) {
+      const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
 #pragma unroll
-    for (int k2 = 0; k2 < 32; ++k2) {
-      const float2 w = w2[32 * k2];  // {w[2m], w[2m + 1]} / 2, m = lane + 32 k2
-      reinterpret_cast<float2*>(fg_a)[lane + 32 * k2] = make_float2(2.f * w.x * im[k2], 2.f * w.y * re[k2]);
+      for (int k2 = 0; k2 < 32; ++k2) {
+        const float2 wp = wv[32 * (k2 & 15)];
+        const float w = 2.f * ((k2 < 16) ? wp.x : wp.y);
+        im[k2] *= w;
+        re[k2] *= w;
+      }
+    } else {
+      const float2* w2 = reinterpret_cast<const float2*>(s_win) + lane;
+#pragma unroll
+      for (int k2 = 0; k2 < 32; ++k2) {
+        const float2 w = w2[32 * k2];
+        im[k2] *= 2.f * w.x;
+        re[k2] *= 2.f * w.y;
+      }
     }
+  }
+  }  // a_valid
+
+  if constexpr (kTileSum) {
+    // ---- overlap-add inside the tile: frames t, t + n_round, ... do not overlap and add side by side --------------
+    const int n_round = (NFFT + hop - 1) / hop;
+    for (int r = 0; r < n_round; ++r) {
+      if constexpr (!kHalf) {
+        if (a_valid && fa % n_round == r) {
+          float* acc = s_acc + fa * hop + lane;
+#pragma unroll
+          for (int k2 = 0; k2 < 32; ++k2) acc[32 * k2] += im[k2];
+        }
+        if (n_round == 1) __syncwarp();  // frames a and b of a warp do not overlap either, but keep the order fixed
+        if (b_valid && (fa + 1) % n_round == r) {
+          float* acc = s_acc + (fa + 1) * hop + lane;
+#pragma unroll
+          for (int k2 = 0; k2 < 32; ++k2) acc[32 * k2] += re[k2];
+        }
+      } else {
+        if (a_valid && fa % n_round == r) {
+          float2* acc = reinterpret_cast<float2*>(s_acc + fa * hop) + lane;  // hop is even in this mode
+#pragma unroll
+          for (int k2 = 0; k2 < 32; ++k2) {
+            float2 v = acc[32 * k2];
+            v.x += im[k2];
+            v.y += re[k2];
+            acc[32 * k2] = v;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // the tile's sums: scratch row of the tile's first frame onwards ((nvalid - 1) * hop + n_fft <= nvalid * n_fft)
+    float* dst = p.frame_grad + ti.out_frame0 * NFFT;
+    const int n4 = span_valid >> 2;
+    for (int i = tid; i < n4; i += kBwdWarps * 32)
+      reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_acc)[i];
+    for (int i = 4 * n4 + tid; i < span_valid; i += kBwdWarps * 32) dst[i] = s_acc[i];
+  }
+}
+
+// d loss / d x[s] from the tile sums: tile i of an utterance (frames [FR i, FR i + nv)) holds the sums of the padded
+// positions [FR i hop, FR i hop + (nv - 1) hop + n_fft) at scratch row (first frame of the tile); a position lies in
+// the tile that starts at or before it and, near the tile's head, in the tail of the one(s) before.
+__global__ void __launch_bounds__(256) tile_overlap_add_kernel(const float* __restrict__ tile_sum,
+                                                               const long long* __restrict__ sample_off,
+                                                               const long long* __restrict__ frame_off, int n_fft,
+                                                               int hop, int frames_per_tile,
+                                                               float* __restrict__ grad_x) {
+  const int b = blockIdx.y;
+  const long long s0 = sample_off[b];
+  const int L = (int)(sample_off[b + 1] - s0);   // utterances are shorter than 2^31 samples (evf_batch_create)
+  const long long f0 = frame_off[b];
+  const int T = (int)(frame_off[b + 1] - f0);
+  const int sa = 4 * (blockIdx.x * blockDim.x + threadIdx.x);  // this thread's four consecutive samples
+  if (sa >= L) return;
+  const int H = n_fft / 2;
+  const unsigned tile_hop = (unsigned)frames_per_tile * (unsigned)hop;
+  const int n_tiles = (T + frames_per_tile - 1) / frames_per_tile;
+  // sum of the tile sums that cover padded position pp, from the last tile that starts at or before it downwards
+  auto at = [&](int pp) -> float {
+    if (n_tiles == 0) return 0.f;
+    int ti = (int)((unsigned)pp / tile_hop);
+    if (ti > n_tiles - 1) ti = n_tiles - 1;
+    long long o = (long long)pp - (long long)ti * tile_hop;
+    float g = 0.f;
+    for (; ti >= 0; --ti, o += tile_hop) {
+      const int nv = min(frames_per_tile, T - ti * frames_per_tile);
+      if (o >= (long long)(nv - 1) * hop + n_fft) break;
+      g += __ldg(tile_sum + (f0 + (long long)ti * frames_per_tile) * n_fft + o);
+    }
+    return g;
+  };
+  float g[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int s = sa + j;
+    g[j] = 0.f;
+    if (s < L) {
+      g[j] = at(s + H);
+      // the mirror images of x[s] in the left / right reflect margin
+      if (s >= 1 && s <= H) g[j] += at(H - s);
+      if (s <= L - 2 && s >= L - 1 - H) g[j] += at(H + 2 * (L - 1) - s);
+    }
+  }
+  float* dst = grad_x + s0 + sa;
+  if (sa + 3 < L && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    *reinterpret_cast<float4*>(dst) = make_float4(g[0], g[1], g[2], g[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (sa + j < L) dst[j] = g[j];
   }
 }
 
@@ -278,17 +439,19 @@ __global__ void __launch_bounds__(256) log_compress_backward_kernel(const float*
   }
 }
 
-template <int MODE, int SPEC>
+template <int MODE, int SPEC, bool kTileSum>
 int launch_bwd_t(const BwdParams& p, int smem, cudaStream_t st) {
-  auto k = features_backward_kernel<MODE, SPEC>;
+  auto k = features_backward_kernel<MODE, SPEC, kTileSum>;
   EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k<<<p.n_tiles, kBwdWarps * 32, smem, st>>>(p);
+  k<<<2 * p.n_tiles, kBwdWarps * 32, smem, st>>>(p);
   EVF_CUDA(cudaGetLastError());
   return EVF_OK;
 }
 template <int SPEC>
-int launch_bwd(const BwdParams& p, int smem, cudaStream_t st) {
-  return p.n_fft == 2048 ? launch_bwd_t<MODE_HALF, SPEC>(p, smem, st) : launch_bwd_t<MODE_PACK2, SPEC>(p, smem, st);
+int launch_bwd(const BwdParams& p, int smem, bool tile_sum, cudaStream_t st) {
+  if (p.n_fft == 2048)
+    return tile_sum ? launch_bwd_t<MODE_HALF, SPEC, true>(p, smem, st) : launch_bwd_t<MODE_HALF, SPEC, false>(p, smem, st);
+  return tile_sum ? launch_bwd_t<MODE_PACK2, SPEC, true>(p, smem, st) : launch_bwd_t<MODE_PACK2, SPEC, false>(p, smem, st);
 }
 
 }  // namespace
@@ -299,19 +462,34 @@ int features_backward_launch(const BwdParams& p, cudaStream_t st) {
     set_error("evf_features_backward: more than 128 mel filters are not supported");
     return EVF_ERR_UNSUPPORTED;
   }
-  const int smem = (p.n_fft + 2 * kFftSize + (p.n_fft == 2048 ? 1028 : 0) +
-                    kBwdWarps * (32 * kScrStride + 2 * kGmStride)) * (int)sizeof(float);
+  int smem = (p.n_fft + 2 * kFftSize + (p.n_fft == 2048 ? 1028 : 0) +
+              kBwdWarps * (32 * kScrStride + 4 * kGmStride)) * (int)sizeof(float);
+  // overlap-add inside the tile when its span fits beside the FFT scratch and the rounds stay few
+  const int frames_per_tile = (p.n_fft == 2048) ? kBwdWarps : 2 * kBwdWarps;  // of a CTA: half a forward tile
+  const long long span_bytes = 4ll * (((long long)(frames_per_tile - 1) * p.hop + p.n_fft + 3) & ~3ll);
+  const bool tile_sum = (p.n_fft + p.hop - 1) / p.hop <= 16 && smem + span_bytes <= 227 * 1024;
+  if (tile_sum) smem += (int)span_bytes;
   int rc;
   switch (p.spec_type) {
-    case EVF_SPEC_MEL: rc = launch_bwd<EVF_SPEC_MEL>(p, smem, st); break;
-    case EVF_SPEC_MEL_LIBROSA: rc = launch_bwd<EVF_SPEC_MEL_LIBROSA>(p, smem, st); break;
-    case EVF_SPEC_LINEAR: rc = launch_bwd<EVF_SPEC_LINEAR>(p, smem, st); break;
+    case EVF_SPEC_MEL: rc = launch_bwd<EVF_SPEC_MEL>(p, smem, tile_sum, st); break;
+    case EVF_SPEC_MEL_LIBROSA: rc = launch_bwd<EVF_SPEC_MEL_LIBROSA>(p, smem, tile_sum, st); break;
+    case EVF_SPEC_LINEAR: rc = launch_bwd<EVF_SPEC_LINEAR>(p, smem, tile_sum, st); break;
     default:
       set_error("evf_features_backward: spec_type has no backward (raw is complex)");
       return EVF_ERR_UNSUPPORTED;
   }
   if (rc != EVF_OK) return rc;
-  return overlap_add_launch(p.frame_grad, p.sample_off, p.frame_off, p.n_utts, p.max_len, p.n_fft, p.hop, p.grad_samples, st);
+  if (!tile_sum)
+    return overlap_add_launch(p.frame_grad, p.sample_off, p.frame_off, p.n_utts, p.max_len, p.n_fft, p.hop,
+                              p.grad_samples, st);
+  if (p.max_len <= 0) return EVF_OK;
+  for (int y0 = 0; y0 < p.n_utts; y0 += 65535) {  // gridDim.y limit: slices of utterances
+    const dim3 grid((unsigned)((p.max_len + 1023) / 1024), (unsigned)(p.n_utts - y0 < 65535 ? p.n_utts - y0 : 65535));
+    tile_overlap_add_kernel<<<grid, 256, 0, st>>>(p.frame_grad, p.sample_off + y0, p.frame_off + y0, p.n_fft, p.hop,
+                                                  frames_per_tile, p.grad_samples);
+    EVF_CUDA(cudaGetLastError());
+  }
+  return EVF_OK;
 }
 
 int overlap_add_launch(const float* frame_grad, const long long* sample_off, const long long* frame_off, int n_utts,

@@ -125,6 +125,47 @@ __device__ __forceinline__ float fast_sqrt(float x) {
   return r;
 }
 
+// d loss / d spectrogram of one tile for the backward kernels: frame-major rows or the per-utterance [row][T_b] layout
+// autograd hands back, with the log compression's backward folded in when the forward's log output is given.
+struct GradView {
+  const float* g;
+  const float* y;
+  long long fm_base, bm_base;  // element index of (tile frame 0, bin 0) frame-major / of the utterance bin-major
+  int Tb, t0, row;
+  float thr;                   // log(clip) exactly as the forward computes it: clamped outputs compare equal
+  bool bin_major;
+  __device__ __forceinline__ GradView(const GradSrc& s, const TileDesc& ti, int n_fft, int hop) {
+    g = s.grad;
+    y = s.log_spec;
+    row = s.row;
+    bin_major = s.bin_major != 0;
+    const int half = n_fft / 2;         // torch.stft pads n_fft / 2 on both sides (odd n_fft included)
+    t0 = (ti.start + half) / hop;       // utterance-relative index of the tile's first frame
+    Tb = s.keep_last ? (int)(((long long)ti.L + 2 * half - n_fft) / hop) + 1 : (int)(ti.L / hop);
+    fm_base = ti.out_frame0 * (long long)row;
+    bm_base = (ti.out_frame0 - t0) * (long long)row;
+    thr = compress(s.log_clip, 1, s.log_clip);
+  }
+  // element indices of (tile frame f, bin m) in the gradient / in the log output
+  __device__ __forceinline__ long long g_index(int f, int m) const {
+    return bin_major ? bm_base + (long long)m * Tb + (t0 + f) : fm_base + (long long)f * row + m;
+  }
+  __device__ __forceinline__ long long y_index(int f, int m) const { return fm_base + (long long)f * row + m; }
+  // gradient w.r.t. the linear-domain value from the raw gradient and (fused log) the forward's log output
+  __device__ __forceinline__ float chain(float v, float yy) const {
+    return (yy > thr) ? v * __expf(-yy) : ((yy != yy) ? yy : 0.f);
+  }
+  // gradient w.r.t. the LINEAR-domain value of bin / filter m of tile frame f
+  __device__ __forceinline__ float at(int f, int m) const {
+    float v = bin_major ? __ldg(g + bm_base + (long long)m * Tb + (t0 + f)) : __ldg(g + fm_base + (long long)f * row + m);
+    if (y != nullptr) {
+      const float yy = __ldg(y + fm_base + (long long)f * row + m);
+      v = (yy > thr) ? v * __expf(-yy) : ((yy != yy) ? yy : 0.f);
+    }
+    return v;
+  }
+};
+
 // ---- mbarrier / bulk-copy (TMA 1-D) primitives ----------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -172,6 +213,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+
+// 4-byte asynchronous global -> shared copies (SASS: LDGSTS)
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ int reflect_index(int j, int L) {
   j = (j < 0) ? -j : j;

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_kernel(const Gen
 // mel-librosa), Hermitian extension packed as C = C_a + i C_b, inverse DFT through the FORWARD Stockham stages with
 // real and imaginary parts swapped on the way in and out, times the window.
 template <int SPEC>
-__global__ void __launch_bounds__(kGenThreads) features_generic_backward_kernel(const GenParams p, const float* __restrict__ grad_spec,
+__global__ void __launch_bounds__(kGenThreads) features_generic_backward_kernel(const GenParams p, const GradSrc gsrc,
                                                                                 float* __restrict__ frame_grad,
                                                                                 const int* __restrict__ jk, int k_used) {
   constexpr bool kMel = (SPEC == EVF_SPEC_MEL || SPEC == EVF_SPEC_MEL_LIBROSA);
@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_backward_kernel(
     const bool a_valid = fa < ti.nvalid, b_valid = fa + 1 < ti.nvalid;
     const float* src = samples + ti.s_off;
     const long long fr_a = ti.out_frame0 + fa;
+    const GradView gv(gsrc, ti, N, hop);
     if (a_valid) {
       const int s0 = ti.start + fa * hop;
       for (int n = lt; n < N; n += ts) {
@@ -341,10 +342,9 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_backward_kernel(
         bufA[n] = make_float2(w * xa, w * xb);
       }
       if constexpr (kMel) {
-        const float* ga = grad_spec + fr_a * (long long)p.row_floats;
         for (int m = lt; m < n_mels; m += ts) {
-          s_gm[m] = __ldg(ga + m);
-          s_gm[n_mels + m] = b_valid ? __ldg(ga + p.row_floats + m) : 0.f;
+          s_gm[m] = gv.at(fa, m);
+          s_gm[n_mels + m] = b_valid ? gv.at(fa + 1, m) : 0.f;
         }
       }
     }
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(kGenThreads) features_generic_backward_kernel(
           const float wr = (jj < n_mels) ? w.x : 0.f, wf = (jj >= 1) ? w.y : 0.f;
           return fmaf(wr, gm[min(jj, n_mels - 1)], wf * gm[max(jj - 1, 0)]);
         } else {
-          return (f == 0 || b_valid) ? __ldg(grad_spec + (fr_a + f) * (long long)p.row_floats + k) : 0.f;
+          return (f == 0 || b_valid) ? gv.at(fa + f, k) : 0.f;
         }
       };
       for (int k = lt; k < n_freq; k += ts) {
@@ -485,7 +485,7 @@ int generic_launch(int spec_type, int sample_format, const GenParams& p, int gri
   return dispatch_generic(spec_type, sample_format, p, grid, smem_bytes, stream, false);
 }
 
-int generic_backward_launch(int spec_type, const GenParams& p, const float* grad_spec, float* frame_grad, const int* jk,
+int generic_backward_launch(int spec_type, const GenParams& p, const GradSrc& grad_spec, float* frame_grad, const int* jk,
                             int k_used, int grid, int smem_bytes, cudaStream_t st) {
   // + [pairs][2][n_mels] mel gradients behind the FFT buffers
   const int smem = smem_bytes + p.pairs * 2 * (p.n_mels > 0 ? p.n_mels : 0) * (int)sizeof(float);

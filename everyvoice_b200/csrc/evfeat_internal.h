@@ -142,7 +142,16 @@ int generic_factorize(int n_fft, GenStages* st, bool* needs_tw64);
 int generic_smem_bytes(int n_fft, int* pairs_out);
 int generic_configure(int spec_type, int sample_format, int smem_bytes);
 int generic_launch(int spec_type, int sample_format, const GenParams& p, int grid, int smem_bytes, cudaStream_t stream);
-int generic_backward_launch(int spec_type, const GenParams& p, const float* grad_spec, float* frame_grad, const int* jk,
+// Where the backward kernels read d loss / d spectrogram from (evf_features_backward_ex)
+struct GradSrc {
+  const float* grad;       // frame-major [total_frames][row] or, bin_major, per utterance [row][T_b]
+  const float* log_spec;   // NULL, or the forward's log output (frame-major): grad is w.r.t. the log
+  float log_clip;          // the forward's clip value
+  int bin_major;
+  int keep_last;           // frames of an utterance: L / hop (+ 1)
+  int row;                 // row_floats
+};
+int generic_backward_launch(int spec_type, const GenParams& p, const GradSrc& gs, float* frame_grad, const int* jk,
                             int k_used, int grid, int smem_bytes, cudaStream_t st);
 // evfeat_backward.cu: folds the per-frame gradient rows back onto the samples (reflect padding included)
 int overlap_add_launch(const float* frame_grad, const long long* sample_off, const long long* frame_off, int n_utts,
@@ -153,7 +162,7 @@ struct BwdParams {
   const float* samples;          // packed float32 audio
   const TileDesc* tiles;
   int n_tiles;
-  const float* grad_spec;        // [total_frames][row_floats] d loss / d (linear-domain) spectrogram, time-major
+  GradSrc gs;                    // d loss / d spectrogram: layout, optional fused log
   float* frame_grad;             // scratch [total_frames][n_fft]
   float* grad_samples;           // out, packed like samples
   const float* window;           // plan tables (MODE_PACK2 layouts)

@@ -157,40 +157,68 @@ class _SpectralFn(torch.autograd.Function):
     """Differentiable linear-domain transform for training through the spectrogram (HiFiGAN's mel loss on generated
     audio, hfgl/model.py:581-590, 719-721).  Forward: the fused feature kernel; backward: ``evf_features_backward``
     (transposed mel projection, inverse FFT through the forward FFT code, windowed overlap-add with the reflect
-    padding folded back)."""
+    padding folded back).
+
+    The output is the ``[B, F, T]`` VIEW of the kernel's time-major result; the gradient autograd hands back is
+    read in whichever of the two layouts it arrives (``[B, F, T]`` contiguous -- bin-major per utterance -- or the
+    view's own), so neither direction copies.  With ``fused_log`` the kernel's epilogue applies
+    ``log(clamp(., 1e-5))`` (utils/heavy.py:39-40) and the backward multiplies by its derivative from the saved
+    output: no separate log kernels, no linear-domain intermediate."""
 
     @staticmethod
-    def forward(ctx, x2d: torch.Tensor, tf: "SpectralTransform", keep_last: bool):
+    def forward(ctx, x2d: torch.Tensor, tf: "SpectralTransform", keep_last: bool, fused_log: bool = False):
         B, L = x2d.shape
-        batch = tf.uniform_batch(B, L, x2d.device, apply_log=False, keep_last=keep_last)
+        batch = tf.uniform_batch(B, L, x2d.device, apply_log=fused_log, keep_last=keep_last)
         spec, _ = tf.run(batch, x2d.reshape(-1), want_energy=False)
         T = tf.num_frames(L, keep_last)
-        ctx.save_for_backward(x2d)
-        ctx.batch, ctx.dims = batch, (B, L, T)
+        ctx.save_for_backward(x2d, spec) if fused_log else ctx.save_for_backward(x2d)
+        ctx.batch, ctx.dims, ctx.fused_log = batch, (B, L, T), fused_log
         return spec.view(B, T, tf.n_rows).transpose(1, 2)
 
     @staticmethod
     def backward(ctx, grad_out: torch.Tensor):
-        (x2d,) = ctx.saved_tensors
+        x2d = ctx.saved_tensors[0]
+        log_spec = ctx.saved_tensors[1] if ctx.fused_log else None
         batch, (B, L, T) = ctx.batch, ctx.dims
         plan = batch.plan
-        g = grad_out.transpose(1, 2).to(torch.float32).contiguous().view(B * T, -1)
+        g = grad_out.to(torch.float32)
+        if g.transpose(1, 2).is_contiguous():      # the layout of the forward output
+            layout = _lib.GRAD_FRAME_MAJOR
+        else:                                      # [B, F, T] contiguous: per utterance [F][T]
+            g, layout = g.contiguous(), _lib.GRAD_BIN_MAJOR
         lib = plan._lib
         n = int(lib.evf_features_backward_scratch_floats(plan.handle, batch.handle))
         scratch = torch.empty(max(n, 1), dtype=torch.float32, device=x2d.device)
         gx = torch.empty_like(x2d)
         with torch.cuda.device(x2d.device):
-            _lib.check(lib.evf_features_backward(plan.handle, batch.handle, _ptr(x2d), _ptr(g), _ptr(scratch), _ptr(gx),
-                                                 _stream_ptr(x2d.device)))
-        return gx, None, None
+            _lib.check(lib.evf_features_backward_ex(plan.handle, batch.handle, _ptr(x2d), _ptr(g), layout,
+                                                    _ptr(log_spec), _ptr(scratch), _ptr(gx), _stream_ptr(x2d.device)))
+        return gx, None, None, None
+
+
+def _is_dense(x: torch.Tensor) -> bool:
+    """True if ``x`` covers its storage without gaps or overlaps in SOME dimension order (a contiguous tensor, or a
+    permuted view of one such as the ``[B, F, T]`` view of the time-major spectrogram): an elementwise kernel may then
+    walk the storage in memory order and ``torch.empty_like`` reproduces the strides."""
+    if x.is_contiguous():
+        return True
+    order = sorted(range(x.dim()), key=lambda d: (-x.stride(d), -x.shape[d]))
+    return x.permute(order).is_contiguous()
+
+
+def _as_dense_f32(x: torch.Tensor) -> torch.Tensor:
+    x = x.to(torch.float32)
+    return x if _is_dense(x) else x.contiguous()
 
 
 class _LogCompressFn(torch.autograd.Function):
-    """``log(clamp(x, min=clip) * C)`` with its gradient ``1 / x`` where the clamp passes (utils/heavy.py:39-40)."""
+    """``log(clamp(x, min=clip) * C)`` with its gradient ``1 / x`` where the clamp passes (utils/heavy.py:39-40).
+    Elementwise, so any dense layout is processed in memory order and kept (no copy of the transposed view the
+    transform returns)."""
 
     @staticmethod
     def forward(ctx, x: torch.Tensor, C: float, clip_val: float):
-        out = torch.empty_like(x)
+        out = torch.empty_like(x)   # preserve_format: the strides of a dense x
         lib = _lib.load()
         with torch.cuda.device(x.device):
             _lib.check(lib.evf_log_compress(_ptr(x), _ptr(out), x.numel(), float(C), float(clip_val), _stream_ptr(x.device)))
@@ -201,7 +229,9 @@ class _LogCompressFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out: torch.Tensor):
         (x,) = ctx.saved_tensors
-        g = grad_out.to(torch.float32).contiguous()
+        g = grad_out.to(torch.float32)
+        if g.stride() != x.stride():   # the kernel pairs x and g element by element in memory order
+            g = torch.empty_like(x).copy_(g)
         gi = torch.empty_like(x)
         lib = _lib.load()
         with torch.cuda.device(x.device):
@@ -367,9 +397,8 @@ class SpectralTransform:
             # training through the transform: custom autograd functions over the same kernels
             if self.is_complex:
                 raise NotImplementedError("the complex ('raw') transform has no backward")
-            out = _SpectralFn.apply(xd.view(B, L), self, bool(keep_last))     # [B, F, T], linear domain
-            if normalize:
-                out = _LogCompressFn.apply(out.contiguous(), 1.0, 1e-5)
+            # [B, F, T]; the log (normalize) is fused into the kernel's epilogue and into its backward
+            out = _SpectralFn.apply(xd.view(B, L), self, bool(keep_last), bool(normalize))
             out = out.reshape(*lead, self.n_rows, out.shape[-1])
             return out if src_device == device else out.to(src_device)
         offsets = np.arange(B + 1, dtype=np.int64) * L
@@ -422,7 +451,7 @@ def dynamic_range_compression_torch(x: torch.Tensor, C=1, clip_val=1e-5) -> torc
     """Reference: ``everyvoice/utils/heavy.py:39-40`` -- ``log(clamp(x, min=clip_val) * C)``
     as a stand-alone operator (the fused kernels do this in their epilogue)."""
     device = x.device if x.is_cuda else _require_cuda(None)
-    xd = x.to(device=device, dtype=torch.float32).contiguous()
+    xd = _as_dense_f32(x.to(device=device))
     if x.requires_grad and torch.is_grad_enabled():
         out = _LogCompressFn.apply(xd, float(C), float(clip_val))
         return out if x.is_cuda else out.to(x.device)

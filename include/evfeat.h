@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define EVF_ABI_VERSION 10
+#define EVF_ABI_VERSION 11
 
 #if defined(__GNUC__)
 #define EVF_API __attribute__((visibility("default")))
@@ -229,6 +229,20 @@ EVF_API int64_t evf_features_backward_scratch_floats(const evf_plan* plan, const
 EVF_API int evf_features_backward(const evf_plan* plan, const evf_batch* batch, const float* samples_dev,
                                   const float* grad_spec_dev, float* scratch_dev, float* grad_samples_dev,
                                   void* stream);
+/* The same with the two steps that surround it in HiFiGAN's loss folded in (hfgl/model.py:719-721:
+ * dynamic_range_compression_torch(transform(wav))[:, :, 1:] against the target mel):
+ *   grad_layout   EVF_GRAD_FRAME_MAJOR: grad_dev is laid out like the forward output ([total_frames][row_floats]);
+ *                 EVF_GRAD_BIN_MAJOR: per utterance [row_floats][T_b], utterance b at frame_offset[b] * row_floats --
+ *                 what autograd hands back for the [B, F, T] tensor the transform returns (no transposing copy);
+ *   log_spec_dev  NULL, or the log output of evf_features_run for the same batch (frame-major; the plan may then have
+ *                 apply_log == 1): grad_dev is d loss / d log-spectrogram and is multiplied by d log / d spec =
+ *                 exp(-log_spec) where log_spec > log(log_clip), 0 where the clamp was active (an element exactly AT
+ *                 the clip value counts as clamped), NaN where log_spec is NaN. */
+#define EVF_GRAD_FRAME_MAJOR 0
+#define EVF_GRAD_BIN_MAJOR 1
+EVF_API int evf_features_backward_ex(const evf_plan* plan, const evf_batch* batch, const float* samples_dev,
+                                     const float* grad_dev, int32_t grad_layout, const float* log_spec_dev,
+                                     float* scratch_dev, float* grad_samples_dev, void* stream);
 /* backward of dynamic_range_compression_torch (utils/heavy.py:39-40): grad_in = grad_out / x where x >= clip_val,
  * else 0 (the clamp blocks the gradient) */
 EVF_API int evf_log_compress_backward(const float* in_dev, const float* grad_out_dev, float* grad_in_dev, int64_t n,

@@ -73,7 +73,10 @@ def test_hifigan_mel_loss_backward(cuda_device, spec_type):
     xg2 = torch.tensor(x, device=cuda_device, requires_grad=True)
     y2 = tf.features(xg2, normalize=True, keep_last=True)
     (torch.nn.functional.l1_loss(y2, target.to(cuda_device)) * 45).backward()
-    assert torch.equal(y2, y) and torch.equal(xg2.grad, xg.grad)
+    # (the log sits in the kernel's epilogue -- one MUFU.LG2 -- and its derivative exp(-y) in the backward's gradient
+    # load: the same numbers as the two-step composition up to float32 round-off)
+    assert float((y2 - y).detach().abs().max()) <= 2e-6 * float(y.detach().abs().max())
+    assert float((xg2.grad - xg.grad).abs().max()) <= 1e-5 * float(xg.grad.abs().max())
 
 
 def test_log_compression_backward_and_clamp_mask(cuda_device):
@@ -242,10 +245,11 @@ def test_hifigan_training_mel_drops_the_first_frame(cuda_device):
         scale = float(xr.grad.abs().max())
         assert float((xg.grad.cpu() - xr.grad).abs().max()) <= RTOL_GRAD * scale
         xg2 = torch.tensor(x, device=cuda_device, requires_grad=True)
-        y2 = tf.training_mel(xg2)
-        assert torch.equal(y2, y)
+        y2 = tf.training_mel(xg2)                                                 # log fused forward and backward
+        assert float((y2 - y).detach().abs().max()) <= 2e-6 * float(y.detach().abs().max())
         ((y2 - target.to(cuda_device)) ** 2).mean().backward()
-        assert torch.equal(xg2.grad, xg.grad)
+        assert float((xg2.grad - xg.grad).abs().max()) <= 1e-5 * float(xg.grad.abs().max())
+        assert float((xg2.grad.cpu() - xr.grad).abs().max()) <= RTOL_GRAD * scale
 
 
 def test_full_size_backward_with_a_smooth_loss(cuda_device):

@@ -58,6 +58,12 @@ def main():
             (torch.nn.functional.l1_loss(y, target) * 45).backward()
             return xg.grad
 
+        def ours_fused():   # log fused into the forward epilogue and into the backward (SpectralTransform.training_mel)
+            xg = x.detach().requires_grad_(True)
+            y = tf.features(xg, normalize=True, keep_last=True)
+            (torch.nn.functional.l1_loss(y, target) * 45).backward()
+            return xg.grad
+
         def torch_gpu():
             xg = x.detach().requires_grad_(True)
             y = torch.log(torch.clamp(otf(xg), min=1e-5))
@@ -73,8 +79,13 @@ def main():
             rel, t_ref = None, (None, None)
             out.setdefault("torch_gpu_error", repr(e)[:200])
         t_ours = timed(ours, reps)
+        g3 = ours_fused()
+        rel_fused = float((g3 - g1).abs().max() / g1.abs().max())
+        t_fused = timed(ours_fused, reps)
         audio_s = B * L / 22050
         out["cases"].append({"case": name, "batch": B, "samples": L, "ours_ms": t_ours[0], "ours_ms_min": t_ours[1],
+                             "ours_fused_log_ms": t_fused[0], "ours_fused_log_ms_min": t_fused[1],
+                             "fused_vs_two_step_max_rel_grad_diff": rel_fused,
                              "torch_gpu_ms": t_ref[0], "torch_gpu_ms_min": t_ref[1], "max_rel_grad_diff": rel,
                              "ours_audio_s_per_s": audio_s / (t_ours[0] / 1e3)})
     print(json.dumps(out))
