@@ -122,6 +122,34 @@ def test_loudness_batch_matches_oracle(cuda_device):
             assert abs(float(got[b]) - want) <= ATOL_LOUDNESS, (sr, b, float(got[b]), want)
 
 
+@pytest.mark.parametrize("sr", [8000, 11025, 32000, 48000, 96000])
+def test_loudness_scan_long_utterances_and_chunk_geometries(cuda_device, sr):
+    """The fast pass is a scan over the biquad states (csrc/evfeat_audio.cu, loudness_scan_kernel): a warp owns 8 steps
+    after a run-in step and walks them in pieces of 32 chunks.  Utterances long enough for several warps, sampling
+    rates with one / several pieces per step and a short last piece, a DC offset (the hard case for the 38 Hz
+    high-pass' double pole), lengths that end inside a step, float32 and int16 input."""
+    from everyvoice_b200 import loudness_batch, synth
+    from oracle import ev_oracle as O
+
+    step = round(round(0.4 * sr) * 0.25)
+    lens = [int(sr * 3.3) + 7, 17 * step, 9 * step - 1, int(sr * 0.43), 8 * step + 2]
+    xs = []
+    for i, L in enumerate(lens):
+        x = synth.speech_like(L, sr, seed=300 + i) * np.float32((0.6, 0.08, 0.3, 0.9, 0.02)[i])
+        if i == 2:
+            x = x + np.float32(0.1)
+        xs.append(x.astype(np.float32))
+    packed, off = synth.pack_ragged(xs)
+    got = loudness_batch(torch.from_numpy(packed).to(cuda_device), off, sr).cpu().numpy()
+    pcm = np.clip(np.rint(packed * 32768.0), -32768, 32767).astype(np.int16)
+    got16 = loudness_batch(torch.from_numpy(pcm).to(cuda_device), off, sr).cpu().numpy()
+    for b, x in enumerate(xs):
+        want = O.loudness(x, sr)
+        assert abs(float(got[b]) - want) <= ATOL_LOUDNESS, (sr, b, float(got[b]), want)
+        want16 = O.loudness(pcm[off[b]:off[b + 1]].astype(np.float32) / np.float32(32768.0), sr)
+        assert abs(float(got16[b]) - want16) <= ATOL_LOUDNESS, (sr, b, float(got16[b]), want16)
+
+
 def test_process_audio_file_mirror(cuda_device, tmp_path):
     """The single-file surface: (audio, sr) / (None, None), ValueError without hop_size (the reference's
     test_process_audio, everyvoice/tests/test_preprocessing.py:356-383)."""
