@@ -459,8 +459,9 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
     std::vector<int> jk(t.jk.begin(), t.jk.begin() + t.k_used);
     if (rc == EVF_OK) rc = upload(jk, &p->d_jk);
   }
-  // n_fft 512 / 256: the backward runs in the any-size kernels (own tables, own tiles: evf_batch_create)
-  if (rc == EVF_OK && mode_jobs_per_warp(p->mode) > 1) rc = create_generic_plan(p, window_host, nullptr, t);
+  // n_fft 256: the backward runs in the any-size kernels (own tables, own tiles: evf_batch_create); n_fft 512 has the
+  // packed-job layout in the warp backward as well
+  if (rc == EVF_OK && p->mode == MODE_PACK2_256) rc = create_generic_plan(p, window_host, nullptr, t);
   if (rc != EVF_OK) {
     free_plan_tables(p);
     delete p;

@@ -42,9 +42,15 @@ constexpr int kGmStride = 128;  // n_mels <= 128 gradient values per frame in sh
 // conj(A[k]) + i conj(B[k])), and the unnormalised inverse DFT of Zin is  g_v[2m] + i g_v[2m + 1].
 template <int MODE, int SPEC, bool kTileSum>
 __global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(const BwdParams p) {
+  using MT = ModeTraits<MODE>;
   constexpr bool kHalf = (MODE == MODE_HALF);
-  constexpr int NFFT = kHalf ? 2048 : 1024;
-  constexpr int FPJ = kHalf ? 1 : 2;
+  constexpr int NFFT = MT::kNfft;
+  constexpr int FPJ = MT::kFramesPerJob;
+  constexpr int J = MT::kJobs;      // n_fft 512: two packed jobs side by side in the warp's register file (evfeat_features.cu)
+  constexpr int R1 = 32 / J;        // first-pass rows of a job = lanes that own a job's bins / samples after a transform
+  constexpr int FPW = FPJ * J;      // frames of a warp
+  constexpr int kWarpWords = 32 * kScrStride + 2 * FPW * kGmStride;  // transpose scratch + gradients / log values of the frames
+  static_assert(J == 1 || J == 2, "the register re-layout between the two transforms is written for one or two jobs");
   constexpr bool kMel = (SPEC == EVF_SPEC_MEL || SPEC == EVF_SPEC_MEL_LIBROSA);
   extern __shared__ __align__(16) float smem[];
   float* s_win = smem;                                              // forward layout of the mode, pre-scaled by 1/2
@@ -52,19 +58,19 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(co
   float2* s_wpost = reinterpret_cast<float2*>(smem + NFFT + 2 * kFftSize);   // MODE_HALF: (cos, -sin)(2 pi k / 2048)
   float* s_warp = smem + NFFT + 2 * kFftSize + (kHalf ? 1028 : 0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* scr = s_warp + warp * (32 * kScrStride + 4 * kGmStride);
-  float* gm = scr + 32 * kScrStride;                                 // [2][kGmStride] mel gradients of frames a, b (+ [2][kGmStride] log values)
-  float* s_acc = s_warp + kBwdWarps * (32 * kScrStride + 4 * kGmStride);  // kTileSum: the tile's span of summed rows
+  float* scr = s_warp + warp * kWarpWords;
+  float* gm = scr + 32 * kScrStride;                                 // [FPW][kGmStride] mel gradients of the warp's frames (+ as many log values)
+  float* s_acc = s_warp + kBwdWarps * kWarpWords;                    // kTileSum: the tile's span of summed rows
 
   for (int i = tid; i < NFFT; i += kBwdWarps * 32) s_win[i] = p.window[i];
   for (int i = tid; i < kFftSize / 2; i += kBwdWarps * 32) s_tw4[i] = p.tw4[i];
   if constexpr (kHalf)
     for (int i = tid; i <= 512; i += kBwdWarps * 32) s_wpost[i] = p.wpost[i];
-  for (int i = tid; i < kBwdWarps * (32 * kScrStride + 4 * kGmStride); i += kBwdWarps * 32) s_warp[i] = 0.f;
+  for (int i = tid; i < kBwdWarps * kWarpWords; i += kBwdWarps * 32) s_warp[i] = 0.f;
   TileDesc ti = p.tiles[blockIdx.x >> 1];
   const int hop = p.hop;
   {  // this CTA's half of the tile: frames [half * FPT, half * FPT + FPT)
-    constexpr int FPT = FPJ * kBwdWarps;
+    constexpr int FPT = FPW * kBwdWarps;
     const int half = blockIdx.x & 1;
     ti.nvalid -= half * FPT;
     if (ti.nvalid <= 0) return;
@@ -77,8 +83,12 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(co
     for (int i = tid; i < span_valid; i += kBwdWarps * 32) s_acc[i] = 0.f;
   __syncthreads();
 
-  const int fa = FPJ * warp;
-  const bool a_valid = fa < ti.nvalid;
+  const int fw = FPW * warp;            // first frame of the warp (tile-relative)
+  const bool a_valid = fw < ti.nvalid;  // warp-uniform: the warp has work
+  const int k1 = lane & (R1 - 1);       // the lane inside its job's R1 lanes
+  const int jw = lane / R1;             // the lane's job (J > 1)
+  const int fa = fw + FPJ * jw;         // first frame of the lane's job
+  const bool la_valid = (J == 1) ? a_valid : (fa < ti.nvalid);
   const GradView gv(p.gs, ti, NFFT, hop);
   if (!kTileSum && !a_valid) return;
   const bool b_valid = !kHalf && (fa + 1 < ti.nvalid);
@@ -87,14 +97,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(co
   // mel gradients (and, fused log, the forward's log output) of the warp's frames: copied global -> shared
   // asynchronously now, consumed after the forward FFT (the scattered [F][T] layout autograd hands back would
   // otherwise stall the warp for a DRAM round trip per filter)
-  float* gy = gm + 2 * kGmStride;  // [2][kGmStride] raw log values
+  float* gy = gm + FPW * kGmStride;  // [FPW][kGmStride] raw log values
   if constexpr (kMel) {
     for (int m = lane; m < p.n_mels; m += 32) {
 #pragma unroll
-      for (int f = 0; f < FPJ; ++f) {
-        if (f == 0 || b_valid) {
-          cp_async4(gm + f * kGmStride + m, gv.g + gv.g_index(fa + f, m));
-          if (gv.y != nullptr) cp_async4(gy + f * kGmStride + m, gv.y + gv.y_index(fa + f, m));
+      for (int f = 0; f < FPW; ++f) {
+        if (fw + f < ti.nvalid) {
+          cp_async4(gm + f * kGmStride + m, gv.g + gv.g_index(fw + f, m));
+          if (gv.y != nullptr) cp_async4(gy + f * kGmStride + m, gv.y + gv.y_index(fw + f, m));
         }
       }
     }
@@ -104,7 +114,24 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(co
   const long long frame_a = ti.out_frame0 + fa;
 
   // ---- forward recomputation: samples -> window-fused first stage -> FFT ------------------------------
-  if constexpr (!kHalf) {
+  if constexpr (J > 1) {
+    constexpr int HR = R1 / 2;
+    constexpr int LB = (R1 == 16) ? 3 : 2;
+    const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
+#pragma unroll
+    for (int jj = 0; jj < J; ++jj) {
+      const int ua = ti.start + (fw + FPJ * jj) * hop + lane, ub = ua + hop;
+#pragma unroll
+      for (int r = 0; r < HR; ++r) {
+        const float2 w = wv[32 * r];
+        const int i = jj * R1 + 2 * bitrev_n(r, LB);
+        win_head(re[i], re[i + 1], __ldg(xs + reflect_index(ua + 32 * r, ti.L)), w.x,
+                 __ldg(xs + reflect_index(ua + 32 * (r + HR), ti.L)), w.y);
+        win_head(im[i], im[i + 1], __ldg(xs + reflect_index(ub + 32 * r, ti.L)), w.x,
+                 __ldg(xs + reflect_index(ub + 32 * (r + HR), ti.L)), w.y);
+      }
+    }
+  } else if constexpr (!kHalf) {
     const int ua = ti.start + fa * hop + lane, ub = ua + hop;
     const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
 #pragma unroll
@@ -129,16 +156,16 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(co
                __ldg(xs + reflect_index(ib + 1, ti.L)), wb.y);
     }
   }
-  warp_fft1024_tail(re, im, s_tw4, scr, lane);
+  warp_fft1024_tail<J>(re, im, s_tw4, scr, lane);
 
   // ---- mel gradients of the frame(s) -> shared memory ----------------------------------------------------
   if constexpr (kMel) {
     cp_async_wait_all();
     for (int m = lane; m < p.n_mels; m += 32) {  // every lane finishes the words it copied itself
 #pragma unroll
-      for (int f = 0; f < FPJ; ++f) {
+      for (int f = 0; f < FPW; ++f) {
         float v = 0.f;
-        if (f == 0 || b_valid) {
+        if (fw + f < ti.nvalid) {
           v = gm[f * kGmStride + m];
           if (gv.y != nullptr) v = gv.chain(v, gy[f * kGmStride + m]);
         }
@@ -155,9 +182,10 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(co
       const int jj = __ldg(p.jk + k);
       const int m_r = min(jj, p.n_mels - 1), m_f = max(jj - 1, 0);
       const float wr = (jj < p.n_mels) ? w.x : 0.f, wf = (jj >= 1) ? w.y : 0.f;
-      return fmaf(wr, gm[f * kGmStride + m_r], wf * gm[f * kGmStride + m_f]);
+      const float* gf = gm + (FPJ * jw + f) * kGmStride;  // the lane's job, frame f of it
+      return fmaf(wr, gf[m_r], wf * gf[m_f]);
     } else {
-      return (f == 0 || b_valid) ? gv.at(fa + f, k) : 0.f;
+      return ((f == 0) ? la_valid : b_valid) ? gv.at(fa + f, k) : 0.f;
     }
   };
   // mel-librosa: mel = basis @ sqrt(P + 1e-9), dM/dP = 1 / (2 sqrt(P + 1e-9))
@@ -170,23 +198,23 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(co
   // element e = lane + 32 q; ck: this lane's elements k = lane + 32 j (j <= 15, and k = 512 for lane 0);
   // cm: the mirror elements 1024 - k, fetched below by the lane that owns them
   float ck_r[17], ck_i[17], cm_r[17], cm_i[17];
-  const int src_lane = (32 - lane) & 31;
+  const int src_lane = (lane & ~(R1 - 1)) | ((R1 - k1) & (R1 - 1));  // owner of the mirrored bin, inside the job's lanes
 #pragma unroll
   for (int j = 0; j <= 16; ++j) {
-    const int k = lane + 32 * j;
+    const int k = k1 + R1 * j;
     float zr, zi, pr, pi;
     if (j < 16) {
       zr = re[j];
       zi = im[j];
-      const float sr = (lane == 0) ? re[(32 - j) & 31] : re[31 - j];
-      const float si = (lane == 0) ? im[(32 - j) & 31] : im[31 - j];
+      const float sr = (k1 == 0) ? re[(32 - j) & 31] : re[31 - j];
+      const float si = (k1 == 0) ? im[(32 - j) & 31] : im[31 - j];
       pr = __shfl_sync(0xffffffffu, sr, src_lane);
       pi = __shfl_sync(0xffffffffu, si, src_lane);
     } else {
       zr = pr = re[16];
       zi = pi = im[16];
     }
-    const bool own = (j < 16) || (lane == 0);
+    const bool own = (j < 16) || (k1 == 0);
     if constexpr (!kHalf) {
       // window was pre-scaled by 1/2: X_a = Z[k] + conj(Z[N-k]), X_b = (Z[k] - conj(Z[N-k])) / i
       const float ar = zr + pr, ai = zi - pi;
@@ -194,7 +222,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(co
       const float gpa = own ? librosa(g_power(k, 0), ar, ai) : 0.f;
       const float gpb = own ? librosa(g_power(k, 1), br, bi) : 0.f;
       const float ur = gpa * ar, ui = gpa * ai, vr = gpb * br, vi = gpb * bi;  // u = G_a / 2, v = G_b / 2
-      if (j == 16 || (j == 0 && lane == 0)) {
+      if (j == 16 || (j == 0 && k1 == 0)) {
         // k = 0 and k = N/2: the spectrum is real there; C = Re G_a + i Re G_b, no mirror
         ck_r[j] = 2.f * ur;
         ck_i[j] = 2.f * vr;
@@ -246,35 +274,63 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(co
   }
 
   // ---- inverse DFT through the forward FFT: swap real and imaginary parts on the way in and out -------------
-  // position bitrev5(q) of the DIT arrays holds element q
+  // J = 1: position bitrev5(q) of the DIT arrays holds element k1 + 32 q.  J = 2: the lane holds elements k1 + 16 q of
+  // ITS job, but the transform wants lane n2 to hold rows n1 of BOTH jobs: element k1 + 16 (2 n1 + b) is row n1 of
+  // column k1 + 16 b, so it is parked at position b * 16 + bitrev4(n1) (b as the block) and the values with b != job
+  // change lane halves below.
+  auto pos = [](int q) { return (J == 1) ? bitrev5(q) : ((q & 1) * 16 + bitrev_n(q >> 1, 4)); };
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
-    re[bitrev5(q)] = ck_i[q];
-    im[bitrev5(q)] = ck_r[q];
+    re[pos(q)] = ck_i[q];
+    im[pos(q)] = ck_r[q];
   }
 #pragma unroll
   for (int q = 16; q < 32; ++q) {
-    // element lane + 32 q > 512 (or == 512 for lane 0, q == 16): the mirror of element 1024 - e, owned by src_lane
-    const float sr = (lane == 0) ? cm_r[(32 - q) & 31] : cm_r[31 - q];
-    const float si = (lane == 0) ? cm_i[(32 - q) & 31] : cm_i[31 - q];
-    re[bitrev5(q)] = __shfl_sync(0xffffffffu, si, src_lane);
-    im[bitrev5(q)] = __shfl_sync(0xffffffffu, sr, src_lane);
+    // element k1 + R1 q > N / 2 (or == N / 2 for k1 == 0, q == 16): the mirror of element N - e, owned by src_lane
+    const float sr = (k1 == 0) ? cm_r[(32 - q) & 31] : cm_r[31 - q];
+    const float si = (k1 == 0) ? cm_i[(32 - q) & 31] : cm_i[31 - q];
+    re[pos(q)] = __shfl_sync(0xffffffffu, si, src_lane);
+    im[pos(q)] = __shfl_sync(0xffffffffu, sr, src_lane);
+  }
+  if constexpr (J == 2) {
+    // lower lanes (job 0) keep their b = 0 values as block 0 and receive job 1's b = 0 values as block 1; upper lanes
+    // (job 1) keep b = 1 as block 1 and receive job 0's b = 1 values as block 0
+    const bool upper = lane >= 16;
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) {
+      const int p0 = bitrev_n(n1, 4), p1 = 16 + p0;
+      const float gr = __shfl_xor_sync(0xffffffffu, upper ? re[p0] : re[p1], 16);
+      const float gi = __shfl_xor_sync(0xffffffffu, upper ? im[p0] : im[p1], 16);
+      if (upper) {
+        re[p0] = gr;
+        im[p0] = gi;
+      } else {
+        re[p1] = gr;
+        im[p1] = gi;
+      }
+    }
   }
   dft32_dit_head(re, im);
-  warp_fft1024_tail(re, im, s_tw4, scr, lane);
-  // FFT(swap(C)) = swap(y): real part of the inverse = im, imaginary part = re; element n = lane + 32 k2
+  warp_fft1024_tail<J>(re, im, s_tw4, scr, lane);
+  // FFT(swap(C)) = swap(y): real part of the inverse = im, imaginary part = re; the lane holds samples
+  // n = k1 + R1 * k2 of its job's two frames
+  // window of sample n: pair table entry [row % (R1 / 2)][column], .x / .y for the lower / upper half of the rows
+  const float2* s_win2 = reinterpret_cast<const float2*>(s_win);
+  auto win_of = [&](int k2) -> float {
+    const int row = k2 / J, col = k1 + R1 * (k2 % J);
+    const float2 wp = s_win2[32 * (row % (R1 / 2)) + col];
+    return 2.f * ((row < R1 / 2) ? wp.x : wp.y);
+  };
 
   // ---- times the (true) window -> frame-gradient rows --------------------------------------------------------
   if constexpr (!kTileSum) {
     float* fg_a = p.frame_grad + frame_a * NFFT;
     if constexpr (!kHalf) {
-      const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
 #pragma unroll
       for (int k2 = 0; k2 < 32; ++k2) {
-        const float2 wp = wv[32 * (k2 & 15)];
-        const float w = 2.f * ((k2 < 16) ? wp.x : wp.y);
-        fg_a[lane + 32 * k2] = w * im[k2];
-        if (b_valid) fg_a[NFFT + lane + 32 * k2] = w * re[k2];
+        const float w = win_of(k2);
+        if (la_valid) fg_a[k1 + R1 * k2] = w * im[k2];
+        if (b_valid) fg_a[NFFT + k1 + R1 * k2] = w * re[k2];
       }
     } else {
       const float2* w2 = reinterpret_cast<const float2*>(s_win) + lane;
@@ -287,11 +343,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(co
   } else {
     // keep the windowed rows in the FFT registers: im = frame a (MODE_HALF: even samples), re = frame b (odd samples)
     if constexpr (!kHalf) {
-      const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
 #pragma unroll
       for (int k2 = 0; k2 < 32; ++k2) {
-        const float2 wp = wv[32 * (k2 & 15)];
-        const float w = 2.f * ((k2 < 16) ? wp.x : wp.y);
+        const float w = win_of(k2);
         im[k2] *= w;
         re[k2] *= w;
       }
@@ -312,16 +366,16 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(co
     const int n_round = (NFFT + hop - 1) / hop;
     for (int r = 0; r < n_round; ++r) {
       if constexpr (!kHalf) {
-        if (a_valid && fa % n_round == r) {
-          float* acc = s_acc + fa * hop + lane;
+        if (la_valid && fa % n_round == r) {
+          float* acc = s_acc + fa * hop + k1;
 #pragma unroll
-          for (int k2 = 0; k2 < 32; ++k2) acc[32 * k2] += im[k2];
+          for (int k2 = 0; k2 < 32; ++k2) acc[R1 * k2] += im[k2];
         }
         if (n_round == 1) __syncwarp();  // frames a and b of a warp do not overlap either, but keep the order fixed
         if (b_valid && (fa + 1) % n_round == r) {
-          float* acc = s_acc + (fa + 1) * hop + lane;
+          float* acc = s_acc + (fa + 1) * hop + k1;
 #pragma unroll
-          for (int k2 = 0; k2 < 32; ++k2) acc[32 * k2] += re[k2];
+          for (int k2 = 0; k2 < 32; ++k2) acc[R1 * k2] += re[k2];
         }
       } else {
         if (a_valid && fa % n_round == r) {
@@ -449,6 +503,9 @@ int launch_bwd_t(const BwdParams& p, int smem, cudaStream_t st) {
 }
 template <int SPEC>
 int launch_bwd(const BwdParams& p, int smem, bool tile_sum, cudaStream_t st) {
+  if (p.n_fft == 512)
+    return tile_sum ? launch_bwd_t<MODE_PACK2_512, SPEC, true>(p, smem, st)
+                    : launch_bwd_t<MODE_PACK2_512, SPEC, false>(p, smem, st);
   if (p.n_fft == 2048)
     return tile_sum ? launch_bwd_t<MODE_HALF, SPEC, true>(p, smem, st) : launch_bwd_t<MODE_HALF, SPEC, false>(p, smem, st);
   return tile_sum ? launch_bwd_t<MODE_PACK2, SPEC, true>(p, smem, st) : launch_bwd_t<MODE_PACK2, SPEC, false>(p, smem, st);
@@ -462,10 +519,11 @@ int features_backward_launch(const BwdParams& p, cudaStream_t st) {
     set_error("evf_features_backward: more than 128 mel filters are not supported");
     return EVF_ERR_UNSUPPORTED;
   }
+  const int fpw = (p.n_fft == 2048) ? 1 : (p.n_fft == 512 ? 4 : 2);  // frames of a warp
   int smem = (p.n_fft + 2 * kFftSize + (p.n_fft == 2048 ? 1028 : 0) +
-              kBwdWarps * (32 * kScrStride + 4 * kGmStride)) * (int)sizeof(float);
+              kBwdWarps * (32 * kScrStride + 2 * fpw * kGmStride)) * (int)sizeof(float);
   // overlap-add inside the tile when its span fits beside the FFT scratch and the rounds stay few
-  const int frames_per_tile = (p.n_fft == 2048) ? kBwdWarps : 2 * kBwdWarps;  // of a CTA: half a forward tile
+  const int frames_per_tile = fpw * kBwdWarps;  // of a CTA: half a forward tile
   const long long span_bytes = 4ll * (((long long)(frames_per_tile - 1) * p.hop + p.n_fft + 3) & ~3ll);
   const bool tile_sum = (p.n_fft + p.hop - 1) / p.hop <= 16 && smem + span_bytes <= 227 * 1024;
   if (tile_sum) smem += (int)span_bytes;

@@ -83,8 +83,90 @@ int check_jobs() {
   return worst < 2e-4 * (scale / 30 + 1) ? 0 : 1;
 }
 
+// The backward's second transform for two packed jobs (evfeat_backward.cu): after the first transform lane (j, k1)
+// holds elements k1 + 16 q of ITS job; the inverse (run through the forward code) wants lane n2 to hold rows n1 of BOTH
+// jobs.  Element k1 + 16 (2 n1 + b) is parked at position b * 16 + bitrev4(n1); the values with b != job change lane
+// halves.  Checked: the transform of two arbitrary 512-point complex inputs laid out that way is their DFT.
+int check_relayout_two_jobs() {
+  constexpr int J = 2, N = 512, R1 = 16;
+  std::vector<double> cr(J * N), ci(J * N);
+  srand(4242);
+  for (int n = 0; n < J * N; ++n) {
+    cr[n] = rand() / (double)RAND_MAX * 2 - 1;
+    ci[n] = rand() / (double)RAND_MAX * 2 - 1;
+  }
+  static float re[32][32], im[32][32];  // [lane][position]
+  auto pos = [](int q) { return (q & 1) * 16 + bitrev_n(q >> 1, 4); };
+  for (int lane = 0; lane < 32; ++lane) {
+    const int j = lane / R1, k1 = lane % R1;
+    for (int q = 0; q < 32; ++q) {
+      re[lane][pos(q)] = (float)cr[j * N + k1 + R1 * q];
+      im[lane][pos(q)] = (float)ci[j * N + k1 + R1 * q];
+    }
+  }
+  for (int n1 = 0; n1 < 16; ++n1) {  // the exchange (a __shfl_xor by 16 on the device)
+    const int p0 = bitrev_n(n1, 4), p1 = 16 + p0;
+    float sr[32], si[32];
+    for (int lane = 0; lane < 32; ++lane) {
+      const bool upper = lane >= 16;
+      sr[lane] = upper ? re[lane][p0] : re[lane][p1];
+      si[lane] = upper ? im[lane][p0] : im[lane][p1];
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+      const bool upper = lane >= 16;
+      (upper ? re[lane][p0] : re[lane][p1]) = sr[lane ^ 16];
+      (upper ? im[lane][p0] : im[lane][p1]) = si[lane ^ 16];
+    }
+  }
+  static float Yr[32][32], Yi[32][32];
+  for (int lane = 0; lane < 32; ++lane) {
+    dft32_dit_head(re[lane], im[lane]);
+    dft32_dit_tail_jobs<J>(re[lane], im[lane]);
+    for (int p = 0; p < 32; ++p) {
+      Yr[p][lane] = re[lane][p];
+      Yi[p][lane] = im[lane][p];
+    }
+  }
+  double worst = 0, scale = 0;
+  for (int lane = 0; lane < 32; ++lane) {
+    const int jj = lane / R1, k1 = lane % R1;
+    float xr[32], xi[32], tr[32], ti[32];
+    for (int n2 = 0; n2 < 32; ++n2) {
+      tr[n2] = Yr[lane][n2];
+      ti[n2] = Yi[lane][n2];
+    }
+    for (int n = 0; n < 16; ++n) {
+      float c[2], sn[2];
+      for (int h = 0; h < 2; ++h) {
+        const double ang = -2 * M_PI * ((k1 * (n + 16 * h)) % N) / N;
+        c[h] = (float)std::cos(ang);
+        sn[h] = (float)std::sin(ang);
+      }
+      const int i = bitrev5(n);
+      if (n == 0)
+        tw_head<true>(xr[i], xi[i], xr[i + 1], xi[i + 1], tr[n], ti[n], c[0], sn[0], tr[n + 16], ti[n + 16], c[1], sn[1]);
+      else
+        tw_head<false>(xr[i], xi[i], xr[i + 1], xi[i + 1], tr[n], ti[n], c[0], sn[0], tr[n + 16], ti[n + 16], c[1], sn[1]);
+    }
+    dft32_dit_tail(xr, xi);
+    for (int k2 = 0; k2 < 32; ++k2) {
+      const int k = k1 + R1 * k2;
+      double ar = 0, ai = 0;
+      for (int n = 0; n < N; ++n) {
+        const double a = -2 * M_PI * ((long long)k * n % N) / N;
+        ar += cr[jj * N + n] * std::cos(a) - ci[jj * N + n] * std::sin(a);
+        ai += cr[jj * N + n] * std::sin(a) + ci[jj * N + n] * std::cos(a);
+      }
+      worst = std::fmax(worst, std::fmax(std::fabs(ar - xr[k2]), std::fabs(ai - xi[k2])));
+      scale = std::fmax(scale, std::hypot(ar, ai));
+    }
+  }
+  printf("re-layout + 2 x fft512 max abs err %.3e (max |Z| %.3f)\n", worst, scale);
+  return worst < 2e-4 * (scale / 30 + 1) ? 0 : 1;
+}
+
 int main() {
-  if (check_jobs<2>() || check_jobs<4>()) return 1;
+  if (check_jobs<2>() || check_jobs<4>() || check_relayout_two_jobs()) return 1;
   const int N = 1024;
   std::vector<double> xr(N), xi(N), w(N);
   srand(1234);

@@ -134,7 +134,7 @@ def test_n_fft_2048_backward_matches_autograd(cuda_device, spec_type, win, hop, 
 # ------------------------------------------------------------------------------------------------------------------
 # every other transform size (any-size kernels), and the warp kernel cross-checked against them
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("config", ["S512", "W512", "R3", "N400", "O1001", "OddHop", "BigHop", "Gap"])
+@pytest.mark.parametrize("config", ["S512", "W512", "S256", "W256", "R3", "N400", "O1001", "OddHop", "BigHop", "Gap"])
 @pytest.mark.parametrize("spec_type", ["mel", "mel-librosa", "linear"])
 def test_any_size_backward_matches_autograd(cuda_device, config, spec_type):
     """d/dx of sum(R * transform(x)) for n_fft 512 / 3072 / 400 / 1001 (odd: 7 * 11 * 13, float64 direct-DFT stages),
@@ -159,6 +159,34 @@ def test_any_size_backward_matches_autograd(cuda_device, config, spec_type):
     (y * R.to(cuda_device)).sum().backward()
     scale = float(xr.grad.abs().max())
     assert float((xg.grad.cpu() - xr.grad).abs().max()) <= RTOL_GRAD * scale
+
+
+@pytest.mark.parametrize("win,hop,n_mels", [(512, 128, 80), (240, 50, 128), (400, 160, 80), (512, 512, 40)])
+@pytest.mark.parametrize("spec_type", ["mel", "linear"])
+def test_packed_job_backward_agrees_with_the_any_size_backward(cuda_device, spec_type, win, hop, n_mels):
+    """n_fft 512: the warp backward runs two packed jobs per warp (register re-layout between the recomputed forward
+    and the inverse transform, csrc/evfeat_backward.cu) -- against the any-size kernels on batches of several tiles,
+    with the tile-sum overlap-add (4 to 11 rounds) and without overlap (hop = n_fft), two-step and fused-log paths."""
+    import everyvoice_b200 as ev
+
+    sr = 24000
+    B, L = 3, 512 * 41 + 77
+    g = torch.Generator(device="cpu").manual_seed(win + hop)
+    x = (torch.rand(B, L, generator=g) * 1.6 - 0.8).to(cuda_device)
+    fast = ev.SpectralTransform(spec_type, 512, win, hop, sr, n_mels, 0, 8000)
+    slow = ev.SpectralTransform(spec_type, 512, win, hop, sr, n_mels, 0, 8000, fft_path="generic")
+    grads = []
+    for tf in (fast, slow):
+        for fused in (False, True):
+            xg = x.clone().requires_grad_(True)
+            y = tf.features(xg, normalize=True, keep_last=True) if fused else ev.dynamic_range_compression_torch(tf(xg))
+            R = torch.sin(torch.arange(y.numel(), device=cuda_device, dtype=torch.float32) * 0.37).view_as(y)
+            (y * R).sum().backward()
+            grads.append(xg.grad)
+    scale = float(grads[2].abs().max())
+    diffs = [float((gq - grads[2]).abs().max()) / scale for gq in (grads[0], grads[1], grads[3])]
+    # [warp two-step, warp fused, any-size fused] against any-size two-step: two float32 FFTs through 1 / x
+    assert max(diffs) <= 2e-4 and diffs[2] <= 2e-5, diffs
 
 
 @pytest.mark.parametrize("n_fft,win,hop,sr,n_mels", [(1024, 1024, 256, 22050, 80), (2048, 1200, 300, 16000, 80)])
