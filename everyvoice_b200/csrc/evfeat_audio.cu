@@ -228,9 +228,21 @@ constexpr int kLdRec = 5;  // scratch floats per step: sum of z^2, z^2 of its fi
 constexpr int kLdWarps = 1;        // warps per block: a warp is independent, and the ragged grid packs best in single warps
 constexpr int kLdSteps = 8;        // steps per warp
 constexpr int kLdMaxChunk = 80;    // samples per lane and piece (the host aims at <= 72)
+// A 2 x 2 matrix as a float32 value plus a float32 correction (hi + lo of the float64 entry).  The high-pass' state
+// transition has a DOUBLE pole at 1 - 2*pi*38/sr, i.e. it is a defective matrix, whose eigenvalues move with the square
+// root of a perturbation: entries rounded to float32 alone (relative 6e-8 of entries of size 50) split the poles by
+// 1e-3 and bias every step energy by 1e-3 at 96 kHz.  With the correction term the bias is below 1e-6.
 struct Mat2 {
   float m00, m01, m10, m11;
+  float l00, l01, l10, l11;
 };
+// M v + e, small terms first
+__device__ __forceinline__ void mat_apply(const Mat2& M, float v1, float v2, float& e1, float& e2) {
+  const float t1 = fmaf(M.l00, v1, fmaf(M.l01, v2, e1));
+  const float t2 = fmaf(M.l10, v1, fmaf(M.l11, v2, e2));
+  e1 = fmaf(M.m00, v1, fmaf(M.m01, v2, t1));
+  e2 = fmaf(M.m10, v1, fmaf(M.m11, v2, t2));
+}
 struct LoudnessScan {
   int C, K;                        // chunk length (odd), pieces per step (K - 1 of 32 * C samples, then the rest)
   int n_act, c_last;               // last piece of a step: lanes that own samples, samples of the last of them
@@ -243,18 +255,12 @@ struct LoudnessScan {
 // state_end[l] = M state_end[l - 1] + E[l] over the lanes of a warp (carry = state before lane 0); returns the state
 // at the START of every lane's chunk in (e1, e2)
 __device__ __forceinline__ void scan_states(const Mat2 (&Mp)[5], float c1, float c2, float& e1, float& e2, int lane) {
-  if (lane == 0) {
-    e1 = fmaf(Mp[0].m00, c1, fmaf(Mp[0].m01, c2, e1));
-    e2 = fmaf(Mp[0].m10, c1, fmaf(Mp[0].m11, c2, e2));
-  }
+  if (lane == 0) mat_apply(Mp[0], c1, c2, e1, e2);
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     const float p1 = __shfl_up_sync(0xffffffffu, e1, 1 << k);
     const float p2 = __shfl_up_sync(0xffffffffu, e2, 1 << k);
-    if (lane >= (1 << k)) {
-      e1 = fmaf(Mp[k].m00, p1, fmaf(Mp[k].m01, p2, e1));
-      e2 = fmaf(Mp[k].m10, p1, fmaf(Mp[k].m11, p2, e2));
-    }
+    if (lane >= (1 << k)) mat_apply(Mp[k], p1, p2, e1, e2);
   }
   const float i1 = __shfl_up_sync(0xffffffffu, e1, 1);
   const float i2 = __shfl_up_sync(0xffffffffu, e2, 1);
@@ -405,8 +411,8 @@ __global__ void __launch_bounds__(kLdWarps * 32) loudness_scan_kernel(const Samp
         e1 = z1;
         e2 = z2;
         scan_states(S.Ms, cs1, cs2, e1, e2, lane);
-        const float n1 = fmaf(Ml.m00, e1, fmaf(Ml.m01, e2, z1));  // the piece's end state, on its last lane
-        const float n2 = fmaf(Ml.m10, e1, fmaf(Ml.m11, e2, z2));
+        float n1 = z1, n2 = z2;  // the piece's end state, on its last lane
+        mat_apply(Ml, e1, e2, n1, n2);
         cs1 = __shfl_sync(0xffffffffu, n1, n_act - 1);
         cs2 = __shfl_sync(0xffffffffu, n2, n_act - 1);
       }
@@ -437,8 +443,8 @@ __global__ void __launch_bounds__(kLdWarps * 32) loudness_scan_kernel(const Samp
         f1 = z1;
         f2 = z2;
         scan_states(S.Mh, ch1, ch2, f1, f2, lane);
-        const float n1 = fmaf(Ml.m00, f1, fmaf(Ml.m01, f2, z1));
-        const float n2 = fmaf(Ml.m10, f1, fmaf(Ml.m11, f2, z2));
+        float n1 = z1, n2 = z2;
+        mat_apply(Ml, f1, f2, n1, n2);
         ch1 = __shfl_sync(0xffffffffu, n1, n_act - 1);
         ch2 = __shfl_sync(0xffffffffu, n2, n_act - 1);
       }
@@ -503,18 +509,28 @@ static void mat_mul(const double (&a)[4], const double (&b)[4], double (&c)[4]) 
                        a[2] * b[1] + a[3] * b[3]};
   for (int i = 0; i < 4; ++i) c[i] = r[i];
 }
+static Mat2 mat_split(const double (&P)[4]) {
+  Mat2 M;
+  float* hi = &M.m00;
+  float* lo = &M.l00;
+  for (int i = 0; i < 4; ++i) {
+    hi[i] = (float)P[i];
+    lo[i] = (float)(P[i] - (double)hi[i]);
+  }
+  return M;
+}
 static void scan_tables(const Biquad& q, int C, int c_last, Mat2 (&Mp)[5], Mat2& M_last, float2* g) {
   // zero input: u0 = s1; s1' = -a1 u0 + s2; s2' = -a2 u0  ->  state' = A state, output i = row 0 of A^i
   const double A[4] = {-(double)q.a1, 1.0, -(double)q.a2, 0.0};
   double P[4] = {1.0, 0.0, 0.0, 1.0};
   for (int i = 0; i < C; ++i) {
     g[i] = make_float2((float)P[0], (float)P[1]);
-    if (i == c_last) M_last = Mat2{(float)P[0], (float)P[1], (float)P[2], (float)P[3]};
+    if (i == c_last) M_last = mat_split(P);
     mat_mul(A, P, P);
   }
-  if (c_last == C) M_last = Mat2{(float)P[0], (float)P[1], (float)P[2], (float)P[3]};
+  if (c_last == C) M_last = mat_split(P);
   for (int k = 0; k < 5; ++k) {
-    Mp[k] = Mat2{(float)P[0], (float)P[1], (float)P[2], (float)P[3]};
+    Mp[k] = mat_split(P);
     mat_mul(P, P, P);
   }
 }

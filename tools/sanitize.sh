@@ -12,5 +12,5 @@ run() {
 run python -m pytest -x -q -m gpu tests/test_gpu_parity.py -k "test_golden_log_spec_and_energy and (A or S512 or S256 or W512 or B-) and mel"
 run python -m pytest -x -q -m gpu tests/test_gpu_parity.py -k "test_ragged_batch_matches_oracle and (S512 or W256 or ST2 or N400) and mel-librosa"
 run python -m pytest -x -q -m gpu tests/test_gpu_frontend.py -k "loudness_batch_matches_oracle or loudness_scan or gate_decisions"
-run python -m pytest -x -q -m gpu tests/test_gpu_backward.py -k "hifigan or styletts2 or deterministic"
+run python -m pytest -x -q -m gpu tests/test_gpu_backward.py -k "hifigan or styletts2 or deterministic or packed_job"
 grep -E "^=== |ERROR SUMMARY|passed|failed|Error|error" $out | head -60
