@@ -105,24 +105,15 @@ class Preprocessor:
     def process_audio(self, wav_path, normalize=True, resample_rate=None, sox_effects=None, hop_size=None,
                       update_counters=True):
         """Reference: preprocessor.py:131-218, same arguments and return value ``(audio[L] float32, sr)`` or
-        ``(None, None)`` when a gate skips the file.  Reads PCM wav files (8/16/32 bit) with the standard library;
+        ``(None, None)`` when a gate skips the file.  Reads wav files (PCM 8 / 16 / 24 / 32 bit, IEEE float 32 / 64 bit:
+        ``wavio.read_wav``, scaled like ``torchaudio.load``);
         ``sox_effects`` must be empty (sox stays with the reference)."""
-        import wave
+        from .wavio import read_wav
 
         if sox_effects:
             raise NotImplementedError("sox effects are applied by the reference before this call")
-        with wave.open(str(wav_path), "rb") as w:
-            sr, ch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
-            raw = w.readframes(n)
-        if width == 2:
-            a = np.frombuffer(raw, dtype="<i2").copy()  # stays int16: converted on the device as s / 32768 (torchaudio.load)
-        elif width == 4:
-            a = (np.frombuffer(raw, dtype="<i4").astype(np.float64) / 2147483648.0).astype(np.float32)
-        elif width == 1:
-            a = (np.frombuffer(raw, dtype=np.uint8).astype(np.float32) - 128.0) / 128.0
-        else:
-            raise ValueError(f"unsupported PCM sample width {width}")
-        audio = torch.from_numpy(np.ascontiguousarray(a.reshape(-1, ch).T))  # [C, L]
+        a, sr = read_wav(wav_path)   # [C, L]: int16 for 16-bit PCM (converted on the device), float32 otherwise
+        audio = torch.from_numpy(a)
         res = self.process_audio_batch([audio], sr, normalize, resample_rate, hop_size, torch.float32,
                                        update_counters, [wav_path])
         if not res.kept:
