@@ -747,6 +747,44 @@ def test_config5_rank_shard_of_100h_corpus(cuda_device):
     assert float((back - feats.energy).abs().max()) <= 1e-4 * float(feats.energy.abs().max())
 
 
+@pytest.mark.parametrize("config", ["S512", "W512", "S256"])
+@pytest.mark.parametrize("spec_type", ["mel", "linear"])
+def test_nan_samples_stay_local_with_packed_jobs(cuda_device, config, spec_type):
+    """n_fft 512 / 256: two / four packed jobs share a warp (register file, transpose scratch, the zero-padded power
+    columns of the mel walk).  A NaN sample may reach the partner frame of its own job (frames 2j, 2j + 1) and nothing
+    else -- in particular not the other jobs of the same warp."""
+    from everyvoice_b200 import synth
+    from oracle import ev_oracle as O
+
+    sr, n_fft, win, hop, n_mels, f_min, f_max = CONFIGS[config]
+    tf, _ = _transform(config, spec_type)
+    otf, _ = _oracle_transform(config, spec_type)
+    xs = [synth.speech_like(hop * n + 3, sr, seed=700 + i) for i, n in enumerate((150, 37, 260))]
+    xs[0][hop * 41 + 5] = np.nan           # frames around 41: jobs 20 / 21, a warp's second / third job
+    xs[2][hop * 130 + 1] = np.inf          # a later tile
+    xs[2][3] = np.nan                      # reflected left margin
+    packed, off = synth.pack_ragged(xs)
+    feats = tf.features_ragged(torch.from_numpy(packed).to(cuda_device), off)
+    for b, x in enumerate(xs):
+        o_spec, o_energy, _ = O.features_one(torch.from_numpy(x), otf, hop)
+        spec, energy = feats.utterance(b).cpu(), feats.utterance_energy(b).cpu()
+        bad_o = ~torch.isfinite(o_spec).all(dim=0)
+        bad = ~torch.isfinite(spec).all(dim=0)
+        allowed = bad_o.clone()
+        T = len(bad_o)
+        for t in bad_o.nonzero().flatten().tolist():
+            allowed[min(t ^ 1, T - 1)] = True
+        assert bool((bad >= bad_o).all()) and bool((bad <= allowed).all()), (b, bad.nonzero().flatten().tolist(),
+                                                                             bad_o.nonzero().flatten().tolist())
+        assert torch.equal(~torch.isfinite(energy), bad)
+        good = ~bad
+        truth = O.truth_features(x, spec_type, n_fft, win, hop, sr, n_mels, f_min, f_max)[0] if spec_type == "linear" else None
+        if truth is not None:
+            truth = truth[:, good.numpy()]
+        assert_log_spec_close(spec[:, good], o_spec[:, good], truth, spec_type)
+        assert float((energy[good] - o_energy[good]).abs().max()) <= (ATOL_LOG if spec_type == "mel" else 2e-2)
+
+
 def test_nan_and_inf_samples_stay_local(cuda_device):
     """A NaN / Inf sample poisons the frames whose window covers it (like torch.stft does) plus, for n_fft 1024, the
     partner frame of the same FFT job (frames 2j and 2j + 1 ride as real and imaginary part of one complex FFT, so a
