@@ -18,7 +18,8 @@ with the CPU oracle on EVERY utterance of rank 0's shard (`parity` key; tests/pa
 (float32 input is reported next to it), against the box's measured host<->device copy bound.
 
 `extra` holds the device-timed lines of the other BASELINE configs (44.1 kHz / n_fft 2048, linear, the 100 h corpus,
-and two more transform sizes: n_fft 512 in the warp kernel with two packed jobs per warp, 4096 in the any-size kernel).
+and two more transform sizes: n_fft 512 in the warp kernel with two packed jobs per warp, 4096 as four phase-stream
+transforms of 1024 points plus a combine).
 
 `--impl reference` times the CPU implementation of the same path (the oracle port of the
 reference, which on CPU is bit-identical to it; /root/reference itself cannot travel to
@@ -51,7 +52,7 @@ WORKLOADS = {
     # configs[4]: a 100 h corpus (65 455 utterances, seed 1238) sharded by utterance over the N ranks with the greedy
     # longest-first partition: STRONG scaling (the corpus is fixed, a rank holds 1/N of it)
     "mel80_22k_100h_corpus": ("mel", 22050, 1024, 1024, 256, 80, 0, 8000, 65455, 1.0, 10.0),
-    # the rest of the config-field domain: 16 kHz corpora (n_fft 512: warp kernel) and 4096-point vocoder targets (any-size kernel)
+    # the rest of the config-field domain: 16 kHz corpora (n_fft 512: warp kernel) and 4096-point vocoder targets (phase streams)
     "mel80_16k_nfft512": ("mel", 16000, 512, 512, 128, 80, 0, 8000, 1000, 1.0, 10.0),
     "mel128_44k_nfft4096": ("mel", 44100, 4096, 4096, 1024, 128, 0, 8000, 1000, 1.0, 10.0),
 }
@@ -536,7 +537,12 @@ def roofline_block(job, feat_ms, step_ms):
                 traffic = rec
         except Exception:
             traffic = None
-    kernel = "features_kernel" if n_fft in (256, 512, 1024, 2048) else "features_generic_kernel"
+    if n_fft in (256, 512, 1024, 2048):
+        kernel = "features_kernel"
+    elif n_fft in (3072, 4096) and hop % (n_fft // 1024) == 0:
+        kernel = "deinterleave_kernel + features_kernel (raw, per phase stream) + combine_kernel"
+    else:
+        kernel = "features_generic_kernel"
     return {
         "bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_frame": bpf,

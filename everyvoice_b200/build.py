@@ -13,7 +13,7 @@ PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libevfeat.so"
-SOURCES = ["evfeat_api.cu", "evfeat_features.cu", "evfeat_generic.cu", "evfeat_aux.cu", "evfeat_audio.cu", "evfeat_backward.cu", "evfeat_pitch.cu"]
+SOURCES = ["evfeat_api.cu", "evfeat_features.cu", "evfeat_generic.cu", "evfeat_decimated.cu", "evfeat_aux.cu", "evfeat_audio.cu", "evfeat_backward.cu", "evfeat_pitch.cu"]
 HEADERS = ["evfeat_internal.h", "evfeat_fft.cuh", "evfeat_device.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

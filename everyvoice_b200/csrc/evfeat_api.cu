@@ -40,6 +40,13 @@ struct evf_plan {
   double2* d_tw64 = nullptr;
   int* d_kstart = nullptr;
   float* d_fb_dense = nullptr;
+  // MODE_DECIMATED (evfeat_decimated.cu): n_fft = dec_r * 1024 as dec_r phase-stream transforms + a combine
+  int dec_r = 0;
+  int dec_hop = 0;                // hop / dec_r: the hop of the phase streams
+  int dec_smem_bytes = 0;
+  evf::FeatParams dec_carve{};    // shared-memory carve-up of features_kernel<MODE_PACK2, raw> at dec_hop
+  float* d_dec_windows = nullptr; // [dec_r][1024] pair layout of w_r[m] = w[dec_r * m + r] / 2
+  float2* d_dec_wcomb = nullptr;  // [513] W_N^k
 };
 
 struct evf_batch {
@@ -56,6 +63,9 @@ struct evf_batch {
   // tiles of the any-size kernels when the plan's forward uses other tiles (n_fft 512 / 256: backward only)
   int n_gen_tiles = 0;
   evf::TileDesc* d_gen_tiles = nullptr;
+  // MODE_DECIMATED: offsets of the utterances' phase streams inside one plane (padded to 4 words), host and device
+  std::vector<long long> dec_stream_off;
+  long long* d_dec_stream_off = nullptr;
 };
 
 namespace evf {
@@ -221,6 +231,8 @@ void free_plan_tables(evf_plan* p) {
   cudaFree(p->d_kstart);
   cudaFree(p->d_fb_dense);
   cudaFree(p->d_gen_window);
+  cudaFree(p->d_dec_windows);
+  cudaFree(p->d_dec_wcomb);
 }
 
 // frames of an utterance of L samples: torch.stft(center=True) yields 1 + (L + 2 * (n_fft / 2) - n_fft) / hop
@@ -367,6 +379,11 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
                         : (cfg->n_fft == 1024 ? MODE_PACK2
                                               : (cfg->n_fft == 512 ? MODE_PACK2_512
                                                                    : (cfg->n_fft == 256 ? MODE_PACK2_256 : MODE_HALF)));
+  // n_fft = R * 1024 (R = 3, 4: the "output" transform of a configuration with a sampling-rate change) with a hop
+  // divisible by R: R phase-stream transforms of 1024 points in the warp kernel + a combine (evfeat_decimated.cu)
+  if (cfg->fft_path == EVF_FFT_AUTO && (cfg->n_fft == 3072 || cfg->n_fft == 4096) &&
+      cfg->hop_length % (cfg->n_fft / 1024) == 0 && cfg->hop_length <= cfg->n_fft)
+    p->mode = MODE_DECIMATED;
   p->n_freq = cfg->n_fft / 2 + 1;
   p->warps = kMaxWarps;  // one CTA per SM
   p->frames_per_tile = p->warps * mode_frames_per_warp(p->mode);  // n_fft 1024: 16 jobs of two frames
@@ -378,7 +395,7 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   int rc = EVF_OK;
   if (mel) {
     rc = compress_filterbank(mel_fb_host, p->n_freq, cfg->n_mels, &t);
-    if (rc == EVF_OK && p->mode != MODE_GENERIC) rc = build_walk_tables(cfg->n_mels, &t);
+    if (rc == EVF_OK && p->mode != MODE_GENERIC && p->mode != MODE_DECIMATED) rc = build_walk_tables(cfg->n_mels, &t);
     if (rc != EVF_OK) {  // not a bank of adjacent triangular filters (or too many of them): dense projection
       triangular = false;
       p->mode = MODE_GENERIC;
@@ -386,7 +403,13 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
     }
     p->k_used = t.k_used;
   }
-  if (p->mode != MODE_GENERIC) {
+  if (p->mode == MODE_DECIMATED) {
+    p->dec_r = cfg->n_fft / kFftSize;
+    p->dec_hop = cfg->hop_length / p->dec_r;
+    PlanTables none;
+    p->dec_smem_bytes = features_smem_bytes(MODE_PACK2, EVF_SPEC_RAW, p->warps, p->dec_hop, kFftSize, none, &p->dec_carve);
+    if (p->dec_smem_bytes < 0) p->mode = MODE_GENERIC;
+  } else if (p->mode != MODE_GENERIC) {
     // does the carve-up fit?  (large hops: two or even one input tile of (frames - 1) * hop + n_fft samples do not)
     FeatParams probe{};
     if (features_smem_bytes(p->mode, cfg->spec_type, p->warps, cfg->hop_length, cfg->n_fft, t, &probe) < 0)
@@ -401,6 +424,56 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
     }
     p->smem_bytes = p->gen_smem_bytes;
     p->frames_per_tile = p->gen_frames_per_tile;
+    *plan_out = p;
+    return EVF_OK;
+  }
+  if (p->mode == MODE_DECIMATED) {
+    // the any-size plan rides along: its kernels run the backward, and its tables (melw, kstart, jk) serve the combine
+    rc = create_generic_plan(p, window_host, nullptr, t);
+    const int R = p->dec_r;
+    std::vector<float> wins((size_t)R * kFftSize);
+    for (int r = 0; r < R; ++r)
+      for (int q = 0; q < 16; ++q)
+        for (int lane = 0; lane < 32; ++lane) {  // pair layout of the 1024-point kernel, window w_r[m] = w[R m + r] / 2
+          wins[(size_t)r * kFftSize + (q * 32 + lane) * 2 + 0] = 0.5f * window_host[R * (32 * q + lane) + r];
+          wins[(size_t)r * kFftSize + (q * 32 + lane) * 2 + 1] = 0.5f * window_host[R * (32 * (q + 16) + lane) + r];
+        }
+    std::vector<float2> wcomb(513);
+    std::vector<float4> tw4(kFftSize / 2);
+    const double two_pi_d = 6.283185307179586476925286766559;
+    for (int k = 0; k <= 512; ++k) {
+      const double ang = -two_pi_d * (double)k / (double)cfg->n_fft;
+      wcomb[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    }
+    for (int n = 0; n < 16; ++n)
+      for (int lane = 0; lane < 32; ++lane) {
+        float c[2], sn[2];
+        for (int h = 0; h < 2; ++h) {
+          const double ang = -two_pi_d * (double)((lane * (n + 16 * h)) % kFftSize) / (double)kFftSize;
+          c[h] = (float)std::cos(ang);
+          sn[h] = (float)std::sin(ang);
+        }
+        tw4[n * 32 + lane] = make_float4(c[0], sn[0], c[1], sn[1]);
+      }
+    if (rc == EVF_OK) rc = features_configure(MODE_PACK2, EVF_SPEC_RAW, EVF_SAMPLES_F32, p->dec_smem_bytes);
+    if (rc == EVF_OK) rc = upload(wins, &p->d_dec_windows);
+    if (rc == EVF_OK) rc = upload(wcomb, &p->d_dec_wcomb);
+    if (rc == EVF_OK) rc = upload(tw4, &p->d_tw4);
+    if (rc == EVF_OK) {  // the scratch of a run is allocated stream-ordered: keep it in the pool between runs
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      cudaGetLastError();
+    }
+    if (rc != EVF_OK) {
+      free_plan_tables(p);
+      delete p;
+      return rc;
+    }
+    p->frames_per_tile = 2 * p->warps;  // tiles of the phase streams: 16 jobs of two frames
+    p->smem_bytes = p->dec_smem_bytes;
     *plan_out = p;
     return EVF_OK;
   }
@@ -505,8 +578,10 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
   std::vector<TileDesc> tiles, gen_tiles;
   std::vector<int> tile_start(n_utts + 1, 0);
   // frames a warp (any-size kernel: a team) loads together: the span of a tile covers whole groups
-  const int fpj = (plan->mode == MODE_GENERIC) ? 2 : mode_frames_per_warp(plan->mode);
+  const bool dec = plan->mode == MODE_DECIMATED;
+  const int fpj = (plan->mode == MODE_GENERIC || dec) ? 2 : mode_frames_per_warp(plan->mode);
   const bool want_gen_tiles = plan->mode != MODE_GENERIC && plan->has_gen;
+  std::vector<long long> stream_off(dec ? n_utts + 1 : 0, 0);
   for (int b = 0; b < n_utts; ++b) {
     tile_start[b] = (int)tiles.size();
     const int64_t L = sample_offsets_host[b + 1] - sample_offsets_host[b];
@@ -528,6 +603,25 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
       return EVF_ERR_INVALID_ARGUMENT;
     }
     f_off[b + 1] = f_off[b] + T;
+    if (dec) {
+      // tiles of the utterance's phase streams (the same list serves every stream: the planes have one layout):
+      // 1024-point frames, hop / R apart, no padding (the streams are cut from the padded signal)
+      const int hs = plan->dec_hop;
+      const long long need = T > 0 ? (T - 1) * hs + kFftSize : 0;
+      const long long Ls = (need + 3) & ~3ll;
+      stream_off[b + 1] = stream_off[b] + Ls;
+      for (int64_t f0 = 0; f0 < T; f0 += fr) {
+        TileDesc d;
+        d.s_off = stream_off[b];
+        d.out_frame0 = f_off[b] + f0;
+        d.L = (int)Ls;
+        d.start = (int)(f0 * hs);
+        d.nvalid = (int)((T - f0 < fr) ? (T - f0) : fr);
+        const int njobs = (d.nvalid + 1) / 2;
+        d.span = (njobs * 2 - 1) * hs + kFftSize;
+        tiles.push_back(d);
+      }
+    } else
     for (int64_t f0 = 0; f0 < T; f0 += fr) {
       TileDesc d;
       d.s_off = sample_offsets_host[b];
@@ -589,6 +683,14 @@ int evf_batch_create(const evf_plan* plan, const int64_t* sample_offsets_host, i
   bt->d_frame_off = reinterpret_cast<long long*>(d_blob + off_bytes);
   bt->d_tiles = reinterpret_cast<evf::TileDesc*>(d_blob + 2 * off_bytes);  // 16 * (n_utts + 1) bytes in: 16-byte aligned
   bt->d_gen_tiles = reinterpret_cast<evf::TileDesc*>(d_blob + 2 * off_bytes + tile_bytes);
+  if (dec) {
+    bt->dec_stream_off = stream_off;
+    rc = upload(stream_off, &bt->d_dec_stream_off);
+    if (rc != EVF_OK) {
+      evf_batch_destroy(bt);
+      return rc;
+    }
+  }
   *batch_out = bt;
   return EVF_OK;
 }
@@ -597,6 +699,7 @@ int evf_batch_destroy(evf_batch* batch) {
   if (!batch) return EVF_OK;
   DeviceGuard guard(batch->device);
   cudaFree(batch->d_sample_off);  // the single block
+  cudaFree(batch->d_dec_stream_off);
   delete batch;
   return EVF_OK;
 }
@@ -667,6 +770,69 @@ static int features_run_tiles(const evf_plan* plan, const evf_batch* batch, int 
                          static_cast<cudaStream_t>(stream));
 }
 
+// MODE_DECIMATED: utterances [u0, u1) in chunks whose scratch (the phase streams and R half spectra per frame, about
+// R * 4 KB per frame) stays below ~1 GiB; the scratch is allocated and freed in stream order.
+static int features_run_decimated(const evf_plan* plan, const evf_batch* batch, int u0, int u1, const void* samples_dev,
+                                  float* spec_out_dev, float* energy_out_dev, void* stream) {
+  DeviceGuard guard(plan->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int R = plan->dec_r;
+  const long long row_raw = 2 * (kFftSize / 2 + 1);  // 1026 floats: Y_r[0..512] as (re, im)
+  const long long budget_frames = (1ll << 30) / (R * row_raw * 4);
+  const std::vector<long long>& so = batch->dec_stream_off;
+  const std::vector<int64_t>& fo = batch->frame_off;
+  int c0 = u0;
+  while (c0 < u1) {
+    int c1 = c0 + 1;
+    while (c1 < u1 && fo[c1 + 1] - fo[c0] <= budget_frames) ++c1;
+    const long long n_f = fo[c1] - fo[c0];
+    const long long plane_len = so[c1] - so[c0];
+    if (n_f > 0) {
+      long long max_ls = 0;
+      for (int b = c0; b < c1; ++b) max_ls = so[b + 1] - so[b] > max_ls ? so[b + 1] - so[b] : max_ls;
+      float* planes = nullptr;
+      float* raw = nullptr;
+      EVF_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&planes), (size_t)R * plane_len * sizeof(float), st));
+      cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&raw), (size_t)R * n_f * row_raw * sizeof(float), st);
+      if (e != cudaSuccess) {
+        cudaFreeAsync(planes, st);
+        return cuda_fail(e, "cudaMallocAsync (scratch of the decimated transform)");
+      }
+      int rc = decimated_deinterleave(samples_dev, plan->cfg.sample_format, batch->d_sample_off, batch->d_dec_stream_off,
+                                      c0, c1 - c0, so[c0], plane_len, max_ls, R, plan->cfg.n_fft, planes, st);
+      const int t0 = batch->tile_start[c0], t1 = batch->tile_start[c1];
+      for (int r = 0; r < R && rc == EVF_OK; ++r) {
+        FeatParams p = plan->dec_carve;
+        p.samples = planes + (long long)r * plane_len - so[c0];   // the tiles carry absolute stream offsets
+        p.tiles = batch->d_tiles + t0;
+        p.n_tiles = t1 - t0;
+        p.spec_out = raw + (long long)r * n_f * row_raw - fo[c0] * row_raw;  // ... and absolute frame indices
+        p.energy_out = nullptr;
+        p.window = plan->d_dec_windows + (size_t)r * kFftSize;
+        p.tw4 = plan->d_tw4;
+        p.hop = plan->dec_hop;
+        p.n_freq = kFftSize / 2 + 1;
+        p.row_floats = (int)row_raw;
+        p.apply_log = 0;
+        p.log_clip = 0.f;
+        const int grid = p.n_tiles < plan->num_sms ? p.n_tiles : plan->num_sms;
+        rc = features_launch(MODE_PACK2, EVF_SPEC_RAW, EVF_SAMPLES_F32, p, grid, plan->dec_smem_bytes, st);
+      }
+      if (rc == EVF_OK)
+        rc = decimated_combine(R, plan->cfg.spec_type, raw, n_f * row_raw, n_f,
+                               spec_out_dev + fo[c0] * (long long)plan->row_floats,
+                               energy_out_dev ? energy_out_dev + fo[c0] : nullptr, plan->d_dec_wcomb, plan->d_melw,
+                               plan->d_kstart, plan->cfg.n_mels, plan->n_freq, plan->k_used, plan->row_floats, plan->cfg.apply_log,
+                               plan->cfg.log_clip, plan->num_sms, st);
+      cudaFreeAsync(raw, st);
+      cudaFreeAsync(planes, st);
+      if (rc != EVF_OK) return rc;
+    }
+    c0 = c1;
+  }
+  return EVF_OK;
+}
+
 int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* samples_dev,
                      float* spec_out_dev, float* energy_out_dev, void* stream) {
   if (!plan || !batch) {
@@ -682,6 +848,8 @@ int evf_features_run(const evf_plan* plan, const evf_batch* batch, const void* s
     set_error("evf_features_run: null sample or output pointer");
     return EVF_ERR_INVALID_ARGUMENT;
   }
+  if (plan->mode == MODE_DECIMATED)
+    return features_run_decimated(plan, batch, 0, batch->n_utts, samples_dev, spec_out_dev, energy_out_dev, stream);
   return features_run_tiles(plan, batch, 0, batch->n_tiles, samples_dev, spec_out_dev, energy_out_dev, stream);
 }
 
@@ -705,6 +873,9 @@ int evf_features_run_range(const evf_plan* plan, const evf_batch* batch, int32_t
     set_error("evf_features_run_range: null sample or output pointer");
     return EVF_ERR_INVALID_ARGUMENT;
   }
+  if (plan->mode == MODE_DECIMATED)
+    return features_run_decimated(plan, batch, utt_begin, utt_end, samples_base_dev, spec_base_dev, energy_base_dev,
+                                  stream);
   return features_run_tiles(plan, batch, batch->tile_start[utt_begin], batch->tile_start[utt_end],
                             samples_base_dev, spec_base_dev, energy_base_dev, stream);
 }

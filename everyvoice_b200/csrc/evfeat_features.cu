@@ -511,7 +511,10 @@ template <int MODE, int SPEC, typename SampleT>
 int launch_t(const FeatParams& p, int grid, int smem, cudaStream_t stream, bool configure_only) {
   auto kern = features_kernel<MODE, SPEC, SampleT, kMaxWarps>;
   if (configure_only) {
-    EVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // the attribute belongs to the kernel, not to a plan: plans of the same instantiation with different carve-ups
+    // (hops) coexist, so it is set to the opt-in maximum once instead of to this plan's size
+    (void)smem;
+    EVF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     return EVF_OK;
   }
   kern<<<grid, kMaxWarps * 32, smem, stream>>>(p);

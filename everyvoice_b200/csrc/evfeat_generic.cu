@@ -413,14 +413,14 @@ int launch_generic_s(int fmt, const GenParams& p, int grid, int smem, cudaStream
   if (fmt == EVF_SAMPLES_S16) {
     auto k = features_generic_kernel<SPEC, short>;
     if (cfg) {
-      EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       return EVF_OK;
     }
     k<<<grid, kGenThreads, smem, st>>>(p);
   } else {
     auto k = features_generic_kernel<SPEC, float>;
     if (cfg) {
-      EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       return EVF_OK;
     }
     k<<<grid, kGenThreads, smem, st>>>(p);

@@ -20,6 +20,7 @@ enum FftMode : int {
   MODE_GENERIC = 2,  // any n_fft / hop: shared-memory mixed-radix FFT over frame pairs (evfeat_generic.cu)
   MODE_PACK2_512 = 3,  // n_fft == 512: a warp runs TWO packed 512-point jobs (4 frames) as 2 x (16 x 32)
   MODE_PACK2_256 = 4,  // n_fft == 256: a warp runs FOUR packed 256-point jobs (8 frames) as 4 x (8 x 32)
+  MODE_DECIMATED = 5,  // n_fft == 3072 / 4096 with hop % (n_fft / 1024) == 0: phase streams through MODE_PACK2 + a combine
 };
 inline bool mode_is_pack2(int mode) { return mode == MODE_PACK2 || mode == MODE_PACK2_512 || mode == MODE_PACK2_256; }
 // packed jobs (frame pairs) a warp runs side by side, and frames a warp owns per tile
@@ -153,6 +154,15 @@ struct GradSrc {
 };
 int generic_backward_launch(int spec_type, const GenParams& p, const GradSrc& gs, float* frame_grad, const int* jk,
                             int k_used, int grid, int smem_bytes, cudaStream_t st);
+// evfeat_decimated.cu: n_fft = R * 1024 (R = 3, 4) as R phase-stream transforms of 1024 points + a radix-R combine
+int decimated_deinterleave(const void* samples, int sample_format, const long long* sample_off_dev,
+                           const long long* stream_off_dev, int utt0, int n_utts, long long chunk_soff0,
+                           long long plane_stride, long long max_stream_len, int R, int n_fft, float* planes,
+                           cudaStream_t st);
+int decimated_combine(int R, int spec_type, const float* raw, long long plane_stride, long long n_frames,
+                      float* spec_out, float* energy_out, const float2* wcomb, const float2* melw, const int* kstart,
+                      int n_mels, int n_freq, int k_used, int row_floats, int apply_log, float log_clip, int num_sms,
+                      cudaStream_t st);
 // evfeat_backward.cu: folds the per-frame gradient rows back onto the samples (reflect padding included)
 int overlap_add_launch(const float* frame_grad, const long long* sample_off, const long long* frame_off, int n_utts,
                        long long max_len, int n_fft, int hop, float* grad_samples, cudaStream_t st);

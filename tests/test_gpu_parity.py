@@ -161,7 +161,7 @@ def test_ragged_batch_matches_oracle(cuda_device, config, spec_type):
     assert worst_e <= ATOL_LOG, worst_e
 
 
-@pytest.mark.parametrize("config", ["A", "B", "W", "ST2", "S512", "W512", "S256", "W256"])
+@pytest.mark.parametrize("config", ["A", "B", "W", "ST2", "S512", "W512", "S256", "W256", "R3", "W3072", "H4096"])
 @pytest.mark.parametrize("spec_type", SPEC_TYPES)
 def test_warp_kernel_and_any_size_kernel_agree(cuda_device, config, spec_type):
     """Two independent FFT implementations behind one plan interface (evf_fft_path): the warp-per-FFT kernel and the

@@ -26,13 +26,14 @@ WORK = {
     "mel512": ("mel", 16000, 512, 512, 128, 80, 0, 8000),        # warp kernel, two packed jobs per warp
     "lin512": ("linear", 16000, 512, 512, 128, 80, 0, 8000),
     "mel256": ("mel", 8000, 256, 256, 64, 40, 0, 4000),          # warp kernel, four packed jobs per warp
-    "mel4096": ("mel", 44100, 4096, 4096, 1024, 128, 0, 8000),   # any-size kernel
+    "mel4096": ("mel", 44100, 4096, 4096, 1024, 128, 0, 8000),   # four phase-stream transforms of 1024 points + combine
+    "mel3072": ("mel", 48000, 3072, 3072, 768, 80, 0, 8000),     # three phase streams (16 -> 48 kHz vocoder output transform)
 }
 
 
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-    names = sys.argv[2].split(",") if len(sys.argv) > 2 else [n for n in WORK if "512" not in n and "256" not in n and "4096" not in n]
+    names = sys.argv[2].split(",") if len(sys.argv) > 2 else [n for n in WORK if "512" not in n and "256" not in n and "4096" not in n and "3072" not in n]
     dev = torch.device("cuda", 0)
     tag = os.environ.get("EVF_TAG", Path(os.environ.get("EVF_LIB", "default")).stem)
     for name in names:
