@@ -483,6 +483,57 @@ def test_corpus_pipeline_equals_single_batch(cuda_device, dtype):
         _same_with_nans(h_phone, phone.cpu(), atol=0.0)
 
 
+@pytest.mark.parametrize("k", [3, 4])
+@pytest.mark.parametrize("dtype", ["f32", "s16"])
+def test_output_transform_with_a_sampling_rate_change(cuda_device, k, dtype):
+    """preprocessor.py:94-121: the "output" transform of a vocoder configuration multiplies n_fft / win / hop by
+    output_sr // input_sr (16 kHz input -> 48 / 64 kHz output: 3072 / 768 and 4096 / 1024) and keeps the input rate for
+    the mel basis.  These sizes run as phase streams through the 1024-point kernel plus a combine
+    (csrc/evfeat_decimated.cu): one resident batch against the oracle, and the chunked host pipeline (utterance
+    ranges, scratch allocated per chunk on the pipeline's stream) against the resident batch, bit for bit."""
+    import everyvoice_b200 as ev
+    from everyvoice_b200 import synth
+    from oracle import ev_oracle as O
+
+    sr_in = 16000
+    ac = ev.AudioConfig(spec_type="mel", input_sampling_rate=sr_in, output_sampling_rate=sr_in * k)
+    pre = ev.Preprocessor(ac, device=cuda_device)
+    tf = pre.output_spectral_transform
+    assert (tf.n_fft, tf.win_length, tf.hop_length, tf.sample_rate) == (1024 * k, 1024 * k, 256 * k, sr_in)
+    hop = 256 * k
+    lens = synth.utterance_lengths(23, sr_in * k, hop, 9, 0.3, 1.5)
+    lens[2] += 11
+    if dtype == "s16":
+        rng = np.random.default_rng(4)
+        xs = [(synth.speech_like(int(L), sr_in * k, seed=400 + i) * 20000).astype(np.int16) for i, L in enumerate(lens)]
+        tdt = torch.int16
+        as_float = [x.astype(np.float32) / np.float32(32768.0) for x in xs]
+    else:
+        xs = [synth.speech_like(int(L), sr_in * k, seed=400 + i) for i, L in enumerate(lens)]
+        tdt = torch.float32
+        as_float = xs
+    packed, off = synth.pack_ragged(xs)
+    feats = pre.process_spec_batch(torch.from_numpy(packed).to(cuda_device), off, output=True)
+    otf = O.get_spectral_transform("mel", 1024 * k, 1024 * k, hop, sr_in, ac.n_mels, ac.f_min, ac.f_max)
+    assert np.array_equal(np.diff(feats.frame_offsets), lens // hop)
+    for b in (0, 2, 7, 22):
+        o_spec, o_energy, _ = O.features_one(torch.from_numpy(as_float[b]), otf, hop)
+        assert float((feats.utterance(b).cpu() - o_spec).abs().max()) <= ATOL_LOG
+        assert float((feats.utterance_energy(b).cpu() - o_energy).abs().max()) <= ATOL_LOG
+    durs = [synth.synthetic_durations(int(L) // hop, seed=90 + i) for i, L in enumerate(lens)]
+    d_packed, p_off = synth.pack_ragged(durs)
+    host = torch.from_numpy(packed).pin_memory()
+    pipe = pre.make_corpus_pipeline(off, tdt, torch.from_numpy(d_packed.astype(np.int64)), p_off, output=True,
+                                    chunk_bytes=400_000)
+    assert len(pipe.chunks) >= 3
+    h_spec = torch.empty((pipe.total_frames, ac.n_mels), dtype=torch.float32).pin_memory()
+    h_energy = torch.empty(pipe.total_frames, dtype=torch.float32).pin_memory()
+    h_phone = torch.empty(pipe.n_phones, dtype=torch.float32).pin_memory()
+    pipe.run(host, h_spec, h_energy, h_phone)
+    torch.cuda.synchronize()
+    assert torch.equal(h_spec, feats.spec.cpu()) and torch.equal(h_energy, feats.energy.cpu())
+
+
 # ------------------------------------------------------------------------------------------
 # reference test-suite invariants (everyvoice/tests/test_preprocessing.py:385-435, 496-568)
 # ------------------------------------------------------------------------------------------
