@@ -55,11 +55,12 @@ WORKLOADS = {
     # the rest of the config-field domain: 16 kHz corpora (n_fft 512: warp kernel) and 4096-point vocoder targets (phase streams)
     "mel80_16k_nfft512": ("mel", 16000, 512, 512, 128, 80, 0, 8000, 1000, 1.0, 10.0),
     "mel128_44k_nfft4096": ("mel", 44100, 4096, 4096, 1024, 128, 0, 8000, 1000, 1.0, 10.0),
+    "mel80_48k_nfft3072": ("mel", 48000, 3072, 3072, 768, 80, 0, 8000, 1000, 1.0, 10.0),   # the sizes a 16 -> 48 kHz configuration gives its output transform
 }
 CORPUS_WORKLOADS = {"mel80_22k_100h_corpus": 1238}  # name -> seed of the global utterance list
 DEFAULT_WORKLOAD = "mel80_22k_1k_ragged"
 EXTRA_WORKLOADS = ["mel128_44k_1k_ragged", "linear_22k_1k_ragged", "mel80_22k_100h_corpus", "mel80_16k_nfft512",
-                   "mel128_44k_nfft4096"]
+                   "mel128_44k_nfft4096", "mel80_48k_nfft3072"]
 METRIC = "audio-sec/sec (log-mel+energy+phone-avg)"
 UNIT = "audio-s/s"
 STEP_DESC = ("features(log-spec+energy) -> phone averaging -> stats -> all-gather of the 5-number summaries (N>1) "

@@ -181,16 +181,6 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-#ifdef EVF_EXP_BOUNDED_WAIT
-  for (int spin = 0; spin < 2000000; ++spin) {
-    uint32_t ok;
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (ok) return;
-  }
-  return;
-#endif
   asm volatile(
       "{\n"
       ".reg .pred p;\n"

@@ -325,3 +325,50 @@ def test_full_size_backward_with_a_smooth_loss(cuda_device):
     rel_same_sign = float((xg2.grad - xr2.grad).abs().max()) / float(xr2.grad.abs().max())
     assert rel_same_sign <= RTOL_GRAD, rel_same_sign
     assert int(flips.sum()) > 0 or rel_l1 <= RTOL_GRAD   # any excess of rel_l1 over rel_same_sign is the flipped signs
+
+
+def test_backward_ex_argument_checks_and_layouts(cuda_device):
+    """evf_features_backward_ex through the C ABI: both gradient layouts give the same gradient, with and without the
+    folded log; a plan with apply_log needs the forward's log output; unknown layouts and the plain entry point on a
+    log plan are refused with a status, nothing is launched."""
+    import ctypes as C
+
+    import everyvoice_b200 as ev
+    from everyvoice_b200 import _lib
+    from everyvoice_b200.heavy import _ptr, _stream_ptr
+
+    tf = ev.get_spectral_transform("mel", 1024, 1024, 256, 22050, 80, 0, 8000).to(cuda_device)
+    B, L = 3, 6000
+    x = (torch.rand(B, L, device=cuda_device) * 1.6 - 0.8).contiguous()
+    lib = _lib.load()
+    outs = {}
+    for apply_log in (False, True):
+        batch = tf.uniform_batch(B, L, cuda_device, apply_log=apply_log, keep_last=True)
+        plan = batch.plan
+        spec, _ = tf.run(batch, x.reshape(-1), want_energy=False)          # [B * T, 80] frame-major
+        T = spec.shape[0] // B
+        g_fm = torch.cos(torch.arange(spec.numel(), device=cuda_device, dtype=torch.float32) * 0.11).view_as(spec)
+        g_bm = g_fm.view(B, T, 80).transpose(1, 2).contiguous()            # per utterance [F][T]
+        n = int(lib.evf_features_backward_scratch_floats(plan.handle, batch.handle))
+        scratch = torch.empty(n, dtype=torch.float32, device=cuda_device)
+        res = []
+        for g, layout in ((g_fm, _lib.GRAD_FRAME_MAJOR), (g_bm, _lib.GRAD_BIN_MAJOR)):
+            gx = torch.empty_like(x)
+            rc = lib.evf_features_backward_ex(plan.handle, batch.handle, _ptr(x), _ptr(g), layout,
+                                              _ptr(spec if apply_log else None), _ptr(scratch), _ptr(gx),
+                                              _stream_ptr(cuda_device))
+            assert rc == 0, lib.evf_last_error()
+            res.append(gx)
+        assert torch.equal(res[0], res[1])                                  # the layout only changes the addressing
+        outs[apply_log] = res[0]
+        gx = torch.empty_like(x)
+        if apply_log:
+            assert lib.evf_features_backward_ex(plan.handle, batch.handle, _ptr(x), _ptr(g_fm), 0, C.c_void_p(0),
+                                                _ptr(scratch), _ptr(gx), _stream_ptr(cuda_device)) == _lib.EVF_ERR_INVALID_ARGUMENT
+            assert lib.evf_features_backward(plan.handle, batch.handle, _ptr(x), _ptr(g_fm), _ptr(scratch), _ptr(gx),
+                                             _stream_ptr(cuda_device)) == _lib.EVF_ERR_UNSUPPORTED
+        assert lib.evf_features_backward_ex(plan.handle, batch.handle, _ptr(x), _ptr(g_fm), 7, C.c_void_p(0),
+                                            _ptr(scratch), _ptr(gx), _stream_ptr(cuda_device)) == _lib.EVF_ERR_INVALID_ARGUMENT
+    # d loss / d log-mel folded in == d loss / d mel of the same upstream gradient divided by the mel where it passes
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[True]).all() and float(outs[True].abs().max()) > 0
