@@ -765,7 +765,7 @@ static int features_run_tiles(const evf_plan* plan, const evf_batch* batch, int 
   p.row_floats = plan->row_floats;
   p.apply_log = (plan->cfg.spec_type == EVF_SPEC_RAW) ? 0 : plan->cfg.apply_log;
   p.log_clip = plan->cfg.log_clip;
-  const int grid = p.n_tiles < plan->num_sms ? p.n_tiles : plan->num_sms;
+  const int grid = p.n_tiles < plan->num_sms * kCtasPerSm ? p.n_tiles : plan->num_sms * kCtasPerSm;
   return features_launch(plan->mode, plan->cfg.spec_type, plan->cfg.sample_format, p, grid, plan->smem_bytes,
                          static_cast<cudaStream_t>(stream));
 }
@@ -815,7 +815,7 @@ static int features_run_decimated(const evf_plan* plan, const evf_batch* batch, 
         p.row_floats = (int)row_raw;
         p.apply_log = 0;
         p.log_clip = 0.f;
-        const int grid = p.n_tiles < plan->num_sms ? p.n_tiles : plan->num_sms;
+        const int grid = p.n_tiles < plan->num_sms * kCtasPerSm ? p.n_tiles : plan->num_sms * kCtasPerSm;
         rc = features_launch(MODE_PACK2, EVF_SPEC_RAW, EVF_SAMPLES_F32, p, grid, plan->dec_smem_bytes, st);
       }
       if (rc == EVF_OK)

@@ -33,6 +33,8 @@ namespace {
 // A CTA of 8 warps handles HALF a forward tile (16 / 8 frames); two CTAs share an SM, so that one's barrier rounds and
 // copy-out overlap the other's FFTs.
 constexpr int kBwdWarps = 8;
+constexpr int kBwdSplit = kMaxWarps / kBwdWarps;  // backward CTAs per forward tile
+static_assert(kBwdSplit >= 1 && kBwdSplit * kBwdWarps == kMaxWarps, "a forward tile is a whole number of backward CTAs");
 constexpr int kGmStride = 128;  // n_mels <= 128 gradient values per frame in shared memory
 
 // MODE_PACK2 (n_fft 1024): two frames per job as real / imaginary part.  MODE_HALF (n_fft 2048): one frame per job as
@@ -67,11 +69,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32, 2) features_backward_kernel(co
   if constexpr (kHalf)
     for (int i = tid; i <= 512; i += kBwdWarps * 32) s_wpost[i] = p.wpost[i];
   for (int i = tid; i < kBwdWarps * kWarpWords; i += kBwdWarps * 32) s_warp[i] = 0.f;
-  TileDesc ti = p.tiles[blockIdx.x >> 1];
+  TileDesc ti = p.tiles[blockIdx.x / kBwdSplit];
   const int hop = p.hop;
-  {  // this CTA's half of the tile: frames [half * FPT, half * FPT + FPT)
+  {  // this CTA's part of the forward tile: frames [half * FPT, half * FPT + FPT)
     constexpr int FPT = FPW * kBwdWarps;
-    const int half = blockIdx.x & 1;
+    const int half = blockIdx.x % kBwdSplit;
     ti.nvalid -= half * FPT;
     if (ti.nvalid <= 0) return;
     if (ti.nvalid > FPT) ti.nvalid = FPT;
@@ -497,7 +499,7 @@ template <int MODE, int SPEC, bool kTileSum>
 int launch_bwd_t(const BwdParams& p, int smem, cudaStream_t st) {
   auto k = features_backward_kernel<MODE, SPEC, kTileSum>;
   EVF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k<<<2 * p.n_tiles, kBwdWarps * 32, smem, st>>>(p);
+  k<<<kBwdSplit * p.n_tiles, kBwdWarps * 32, smem, st>>>(p);
   EVF_CUDA(cudaGetLastError());
   return EVF_OK;
 }
@@ -523,7 +525,7 @@ int features_backward_launch(const BwdParams& p, cudaStream_t st) {
   int smem = (p.n_fft + 2 * kFftSize + (p.n_fft == 2048 ? 1028 : 0) +
               kBwdWarps * (32 * kScrStride + 2 * fpw * kGmStride)) * (int)sizeof(float);
   // overlap-add inside the tile when its span fits beside the FFT scratch and the rounds stay few
-  const int frames_per_tile = fpw * kBwdWarps;  // of a CTA: half a forward tile
+  const int frames_per_tile = fpw * kBwdWarps;  // of a CTA: 1 / kBwdSplit of a forward tile
   const long long span_bytes = 4ll * (((long long)(frames_per_tile - 1) * p.hop + p.n_fft + 3) & ~3ll);
   const bool tile_sum = (p.n_fft + p.hop - 1) / p.hop <= 16 && smem + span_bytes <= 227 * 1024;
   if (tile_sum) smem += (int)span_bytes;

@@ -47,7 +47,7 @@ namespace {
 using TileInfo = TileDesc;  // host-built, 32 bytes, one per tile (evfeat_internal.h)
 
 template <int MODE, int SPEC, typename SampleT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParams p) {
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const FeatParams p) {
   using MT = ModeTraits<MODE>;
   constexpr int kThreads = WARPS * 32;
   constexpr int NFFT = MT::kNfft;
@@ -144,7 +144,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
     const TileInfo fut = tile_info(min(tile + 2 * G, p.n_tiles - 1));
     const int nvalid = cur.nvalid;
     const long long out_frame0 = cur.out_frame0;
-    const bool active = warp * FPW < nvalid;
+    // the warp's job slot rotates with the iteration: the idle slots of partial tiles (utterance ends) are spread over
+    // the warps instead of always hitting the high-numbered ones
+    const int slot = (warp + it) & (WARPS - 1);
+    const bool active = slot * FPW < nvalid;
 
     mbar_wait(&s_bar[b], parity);
 
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
         // window pairs {w[32 * r + lane], w[32 * (r + R1 / 2) + lane]} at [r][lane], r < R1 / 2
         constexpr int HR = R1 / 2;
         constexpr int LB = (R1 == 16) ? 3 : 2;  // log2(HR)
-        const SampleT* x0 = s_in + (FPW * warp) * hop + lane;
+        const SampleT* x0 = s_in + (FPW * slot) * hop + lane;
         const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
         if (hop * 4 == NFFT) {
           // hop = n_fft / 4 = R1 / 4 sample rows: the warp's FPW frames share rows, (FPW - 1) * R1 / 4 + R1 row loads
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
       } else if constexpr (MODE == MODE_PACK2) {
         // window pairs: s_win holds {w[32*r + lane], w[32*(r + 16) + lane]} at [r][lane] (16 LDS.64): rows r and
         // r + 16 are the two inputs of one first-stage butterfly, which absorbs the window multiplication
-        const SampleT* xa = s_in + (2 * warp) * hop + lane;
+        const SampleT* xa = s_in + (2 * slot) * hop + lane;
         const float2* wv = reinterpret_cast<const float2*>(s_win) + lane;
         if (hop == 256) {
           // the two frames of the job overlap by 768 samples: sample rows 8..31 of frame a ARE rows
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
           }
         }
       } else {
-        const SampleT* x2 = s_in + warp * hop + 2 * lane;
+        const SampleT* x2 = s_in + slot * hop + 2 * lane;
         const float2* w2 = reinterpret_cast<const float2*>(s_win) + lane;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
       const int k1 = lane & (R1 - 1);  // bin k = k1 + R1 * j of the lane's job
       const int jw = lane / R1;        // the lane's job (J > 1)
       const int src_lane = (lane & ~(R1 - 1)) | ((R1 - k1) & (R1 - 1));
-      const int fa = warp * FPW + FPJ * jw;  // tile-local frame of this lane's job (packed: fa and fa + 1)
+      const int fa = slot * FPW + FPJ * jw;  // tile-local frame of this lane's job (packed: fa and fa + 1)
       float esum_a = 0.f, esum_b = 0.f;
       float* ga = p.spec_out + (out_frame0 + fa) * (long long)p.row_floats;
       float* gb = ga + p.row_floats;
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) features_kernel(const FeatParam
         const int n = p.n_chunk;
 #pragma unroll 1
         for (int jj = 0; jj < J; ++jj) {
-          const int fj = (J == 1) ? fa : warp * FPW + FPJ * jj;  // first frame of job jj (warp-uniform)
+          const int fj = (J == 1) ? fa : slot * FPW + FPJ * jj;  // first frame of job jj (warp-uniform)
           if (J > 1 && fj >= nvalid) break;
           float* gja = (J == 1) ? ga : p.spec_out + (out_frame0 + fj) * (long long)p.row_floats;
           float* gjb = gja + p.row_floats;
@@ -558,7 +561,7 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
   const int fpj = (mode == MODE_HALF) ? 1 : 2;  // frames per job
   const int jobs = mode_jobs_per_warp(mode);
   const int fr = warps * mode_frames_per_warp(mode);
-  const long long limit = 227 * 1024;  // one CTA per SM
+  const long long limit = (228 * 1024) / kCtasPerSm - 1024;  // one CTA per SM: 227 KB
   auto up4 = [](int w) { return (w + 3) & ~3; };
   c->n_chunk = t.n_chunk;
   c->n_heads = t.n_heads;

@@ -10,7 +10,11 @@
 
 namespace evf {
 
-constexpr int kMaxWarps = 16;        // warps per CTA (one CTA per SM); one FFT job per warp per tile
+// warps per CTA of the warp-per-FFT kernel; one FFT job per warp per tile.  Two CTAs of 8 warps per SM instead of one
+// of 16: the same 16 resident warps, but tiles of 16 frames (less idle job slots at utterance ends) and two rings that
+// drift independently: 0.689 -> 0.663 ms on configs[1] (profiles/r02y_kbench_cta_shape.txt)
+constexpr int kMaxWarps = 8;
+constexpr int kCtasPerSm = 16 / kMaxWarps;
 constexpr int kFftSize = 1024;       // complex points per warp-level FFT
 constexpr int kScrStride = 34;       // padded row stride of the per-warp transpose scratch (even: LDS.64 rows)
 
