@@ -25,7 +25,7 @@ struct evf_plan {
   float4* d_tw4 = nullptr;
   float2* d_wpost = nullptr;
   float2* d_wtab = nullptr;
-  unsigned* d_gtab = nullptr;
+  uint2* d_gtab = nullptr;
   unsigned* d_ltab = nullptr;
   float2* d_melw = nullptr;  // per-bin {rising, falling} weights and interval index: the backward's transposed mel
   int* d_jk = nullptr;
@@ -161,9 +161,10 @@ int compress_filterbank(const float* fb, int n_freq, int n_mels, PlanTables* t) 
 //   wtab     : per (i, lane) the two weights of bin n * lane + i; the sign bit of the rising weight
 //              says "flush after this bin" (last bin of an interval, of the chunk, or of all bins)
 //   ltab     : per lane the slot of its first flush and of its second (later ones are consecutive)
-//   gtab     : per filter m and c = 0 .. n_heads: (slot of the c-th partial of interval m) |
-//              (slot of the c-th partial of interval m + 1) << 16, the zero slot where there is none
-int build_walk_tables(int n_mels, PlanTables* t) {
+//   gtab     : per filter m and c = 0 .. n_heads, ready to use as byte offsets into the warp's slot area (no decoding
+//              in the gather): .x = c-th partial of interval m (its rising sums, the slot's first half), .y = c-th
+//              partial of interval m + 1 (its falling sums, the slot's second half); the zero slot where there is none
+int build_walk_tables(int n_mels, int slot_bytes, PlanTables* t) {
   const int k_used = t->k_used;
   int n = (k_used + 31) / 32;
   if (n < 1) n = 1;
@@ -207,12 +208,12 @@ int build_walk_tables(int n_mels, PlanTables* t) {
   for (int j = 0; j < n_int; ++j) most = parts[j].size() > most ? parts[j].size() : most;
   t->n_heads = (int)most - 1;
   t->m_pad = (n_mels + 31) & ~31;
-  t->gtab.assign((size_t)(t->n_heads + 1) * t->m_pad, (unsigned)zero | ((unsigned)zero << 16));
+  t->gtab.assign((size_t)(t->n_heads + 1) * t->m_pad, make_uint2((unsigned)(zero * slot_bytes), (unsigned)(zero * slot_bytes + slot_bytes / 2)));
   for (int m = 0; m < n_mels; ++m)
     for (int c = 0; c <= t->n_heads; ++c) {
       const unsigned r = c < (int)parts[m].size() ? parts[m][c] : zero;
       const unsigned f = c < (int)parts[m + 1].size() ? parts[m + 1][c] : zero;
-      t->gtab[(size_t)c * t->m_pad + m] = r | (f << 16);
+      t->gtab[(size_t)c * t->m_pad + m] = make_uint2(r * slot_bytes, f * slot_bytes + slot_bytes / 2);
     }
   return EVF_OK;
 }
@@ -385,8 +386,8 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
       cfg->hop_length % (cfg->n_fft / 1024) == 0 && cfg->hop_length <= cfg->n_fft)
     p->mode = MODE_DECIMATED;
   p->n_freq = cfg->n_fft / 2 + 1;
-  p->warps = kMaxWarps;  // one CTA per SM
-  p->frames_per_tile = p->warps * mode_frames_per_warp(p->mode);  // n_fft 1024: 16 jobs of two frames
+  p->warps = kMaxWarps;  // kCtasPerSm CTAs per SM
+  p->frames_per_tile = p->warps * mode_frames_per_warp(p->mode);  // n_fft 1024: 8 jobs of two frames
   p->num_sms = prop.multiProcessorCount;
   p->row_floats = mel ? cfg->n_mels : (cfg->spec_type == EVF_SPEC_RAW ? 2 * p->n_freq : p->n_freq);
 
@@ -395,7 +396,7 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
   int rc = EVF_OK;
   if (mel) {
     rc = compress_filterbank(mel_fb_host, p->n_freq, cfg->n_mels, &t);
-    if (rc == EVF_OK && p->mode != MODE_GENERIC && p->mode != MODE_DECIMATED) rc = build_walk_tables(cfg->n_mels, &t);
+    if (rc == EVF_OK && p->mode != MODE_GENERIC && p->mode != MODE_DECIMATED) rc = build_walk_tables(cfg->n_mels, p->mode == MODE_HALF ? 8 : 16, &t);
     if (rc != EVF_OK) {  // not a bank of adjacent triangular filters (or too many of them): dense projection
       triangular = false;
       p->mode = MODE_GENERIC;
@@ -472,7 +473,7 @@ int evf_plan_create(const evf_config* cfg, const float* window_host, const float
       delete p;
       return rc;
     }
-    p->frames_per_tile = 2 * p->warps;  // tiles of the phase streams: 16 jobs of two frames
+    p->frames_per_tile = 2 * p->warps;  // tiles of the phase streams: 8 jobs of two frames
     p->smem_bytes = p->dec_smem_bytes;
     *plan_out = p;
     return EVF_OK;

@@ -8,10 +8,12 @@
 //   everyvoice/preprocessor/preprocessor.py:302-309            extract_energy
 //
 // Work decomposition
-//   grid   : persistent, one CTA of 16 warps per SM, static round-robin over frame tiles
-//   tile   : 16 FFT jobs of one utterance = 32 consecutive frames (n_fft 1024: two real
-//            frames ride as re/im of one complex FFT) or 16 frames (n_fft 2048: one frame
-//            = 1024 complex points + real-FFT split); warp w owns job w of every tile
+//   grid   : persistent, two CTAs of 8 warps per SM (the register file allows 16 warps; two small CTAs
+//            instead of one: shorter tiles leave fewer idle job slots at utterance ends and the two
+//            rings drift independently), static round-robin over frame tiles
+//   tile   : 8 FFT jobs of one utterance = 16 consecutive frames (n_fft 1024: two real
+//            frames ride as re/im of one complex FFT) or 8 frames (n_fft 2048: one frame
+//            = 1024 complex points + real-FFT split); warp w owns job slot (w + iteration) % 8
 //   ring   : the tile's sample span ((FR-1)*hop + n_fft samples; every sample leaves HBM once,
 //            the 4x frame overlap is served from shared memory) is fetched with cp.async.bulk
 //            (TMA 1-D) into a ring of input buffers; "full" is an mbarrier per buffer, "empty"
@@ -19,7 +21,7 @@
 //            (before the FFT), and the LAST warp to release refills it with the tile after
 //            next (reflect padding at the utterance edges = index mirroring on the few margin
 //            words, by that warp).  There is NO block-wide barrier in the steady state: the
-//            16 warps drift apart, so one warp's shared-memory phases (sample loads, the
+//            warps drift apart, so one warp's shared-memory phases (sample loads, the
 //            transpose, the mel walk) overlap the FMA-bound butterflies of the others.
 //   job    : window * samples -> registers, 32x32 four-step FFT (in-register radix-2 DFT-32,
 //            transpose + twiddle through the warp's private scratch), real-FFT separation with
@@ -46,6 +48,19 @@ namespace {
 
 using TileInfo = TileDesc;  // host-built, 32 bytes, one per tile (evfeat_internal.h)
 
+// compile-time loop indices for the fully unrolled register-array code
+template <int V>
+struct IntC {
+  static constexpr int value = V;
+};
+template <int B, int E, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(IntC<B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+
 template <int MODE, int SPEC, typename SampleT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const FeatParams p) {
   using MT = ModeTraits<MODE>;
@@ -65,7 +80,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
   float4* s_tw4 = reinterpret_cast<float4*>(smem + p.off_tw);
   const float2* s_wpost = reinterpret_cast<const float2*>(smem + p.off_wpost);
   const float2* s_wtab = reinterpret_cast<const float2*>(smem + p.off_wtab);
-  const unsigned* s_gtab = reinterpret_cast<const unsigned*>(smem + p.off_gtab);
+  const uint2* s_gtab = reinterpret_cast<const uint2*>(smem + p.off_gtab);
   const unsigned* s_ltab = reinterpret_cast<const unsigned*>(smem + p.off_ltab);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + p.off_bar);  // full[0], full[1]
   int* s_cnt = reinterpret_cast<int*>(smem + p.off_bar + 4);         // released-by counters
@@ -95,7 +110,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
   if constexpr (kMel) {
     for (int i = tid; i < p.n_chunk * 32; i += kThreads) reinterpret_cast<float2*>(smem + p.off_wtab)[i] = p.wtab[i];
     for (int i = tid; i < (p.n_heads + 1) * p.m_pad; i += kThreads)
-      reinterpret_cast<unsigned*>(smem + p.off_gtab)[i] = p.gtab[i];
+      reinterpret_cast<uint2*>(smem + p.off_gtab)[i] = p.gtab[i];
     if (tid < 32) reinterpret_cast<unsigned*>(smem + p.off_ltab)[tid] = p.ltab[tid];
   }
   // pad words of the scratch and never-flushed slots (empty intervals, the zero slot) stay zero
@@ -288,92 +303,119 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
         }
       }
 
-#pragma unroll
-      for (int j = 0; j <= 16; ++j) {
+      // one row of the separation: bins k = k1 + R1 * j of the warp's jobs (j is a compile-time register index)
+      auto sep_row = [&](auto jc) {
+        constexpr int j = decltype(jc)::value;
         const int k = k1 + R1 * j;
-        // warp-uniform: does any lane of this row own a bin that is consumed?
-        bool need = R1 * j < kcap;
-        if constexpr (kHalf) need = need || (1024 - 32 * j - 31 < kcap);
-        if (need) {
-          float zr, zi, pr, pi;
-          if (j < 16) {
-            zr = re[j];
-            zi = im[j];
-            // lane 0 is its own partner, with a different register (bin 32*(32-j) instead of 32*(31-j)+32-lane)
-            const float sr = (k1 == 0) ? re[(32 - j) & 31] : re[31 - j];
-            const float si = (k1 == 0) ? im[(32 - j) & 31] : im[31 - j];
-            pr = __shfl_sync(0xffffffffu, sr, src_lane);
-            pi = __shfl_sync(0xffffffffu, si, src_lane);
-          } else {  // bin 512 (lane 0 only): its own mirror
-            zr = pr = re[16];
-            zi = pi = im[16];
-          }
-          if (j < 16 || k1 == 0) {
-            if constexpr (kPack) {
-              // window was pre-scaled by 1/2: X_a = Z[k] + conj(Z[N-k]), X_b = (Z[k] - conj(Z[N-k])) / i
-              const float ar = zr + pr, ai = zi - pi;
-              const float br = zi + pi, bi = pr - zr;
-              if constexpr (SPEC == EVF_SPEC_RAW) {
-                if (a_valid) reinterpret_cast<float2*>(ga)[k] = make_float2(ar, ai);
-                if (b_valid) reinterpret_cast<float2*>(gb)[k] = make_float2(br, bi);
+        float zr, zi, pr, pi;
+        if (j < 16) {
+          zr = re[j];
+          zi = im[j];
+          // lane 0 is its own partner, with a different register (bin 32*(32-j) instead of 32*(31-j)+32-lane)
+          const float sr = (k1 == 0) ? re[(32 - j) & 31] : re[31 - j];
+          const float si = (k1 == 0) ? im[(32 - j) & 31] : im[31 - j];
+          pr = __shfl_sync(0xffffffffu, sr, src_lane);
+          pi = __shfl_sync(0xffffffffu, si, src_lane);
+        } else {  // bin 512 (lane 0 only): its own mirror
+          zr = pr = re[16];
+          zi = pi = im[16];
+        }
+        if (j < 16 || k1 == 0) {
+          if constexpr (kPack) {
+            // window was pre-scaled by 1/2: X_a = Z[k] + conj(Z[N-k]), X_b = (Z[k] - conj(Z[N-k])) / i
+            const float ar = zr + pr, ai = zi - pi;
+            const float br = zi + pi, bi = pr - zr;
+            if constexpr (SPEC == EVF_SPEC_RAW) {
+              if (a_valid) reinterpret_cast<float2*>(ga)[k] = make_float2(ar, ai);
+              if (b_valid) reinterpret_cast<float2*>(gb)[k] = make_float2(br, bi);
+            } else {
+              float pa = fmaf(ar, ar, ai * ai);
+              float pb = fmaf(br, br, bi * bi);
+              if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
+                pa = fast_sqrt(pa + 1e-9f);
+                pb = fast_sqrt(pb + 1e-9f);
+              }
+              if constexpr (kMel) {
+                P2[k] = make_float2(pa, pb);
               } else {
-                float pa = fmaf(ar, ar, ai * ai);
-                float pb = fmaf(br, br, bi * bi);
-                if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
-                  pa = fast_sqrt(pa + 1e-9f);
-                  pb = fast_sqrt(pb + 1e-9f);
-                }
-                if constexpr (kMel) {
-                  P2[k] = make_float2(pa, pb);
-                } else {
-                  const float va = compress(pa, p.apply_log, p.log_clip);
-                  const float vb = compress(pb, p.apply_log, p.log_clip);
-                  if (a_valid) ga[k] = va;
-                  esum_a = fmaf(va, va, esum_a);
-                  if (b_valid) {
-                    gb[k] = vb;
-                    esum_b = fmaf(vb, vb, esum_b);
-                  }
+                const float va = compress(pa, p.apply_log, p.log_clip);
+                const float vb = compress(pb, p.apply_log, p.log_clip);
+                if (a_valid) ga[k] = va;
+                esum_a = fmaf(va, va, esum_a);
+                if (b_valid) {
+                  gb[k] = vb;
+                  esum_b = fmaf(vb, vb, esum_b);
                 }
               }
+            }
+          } else {
+            // X[k] = E - T, X[M-k] = conj(E + T), E = Z[k] + conj(Z[M-k]), T = i * w_k * (Z[k] - conj(Z[M-k]))
+            const float er = zr + pr, ei = zi - pi;
+            const float orr = zr - pr, oi = zi + pi;
+            const float2 w = s_wpost[k];  // (cos, -sin)(2 pi k / 2048)
+            const float tr = -fmaf(w.x, oi, w.y * orr);
+            const float ti = fmaf(w.x, orr, -w.y * oi);
+            const float x0r = er - tr, x0i = ei - ti;      // bin k
+            const float x1r = er + tr, x1i = -(ei + ti);   // bin 1024 - k
+            const int km = 1024 - k;
+            const bool has_mirror = (j < 16);  // k == 512 is its own mirror
+            if constexpr (SPEC == EVF_SPEC_RAW) {
+              reinterpret_cast<float2*>(ga)[k] = make_float2(x0r, x0i);
+              if (has_mirror) reinterpret_cast<float2*>(ga)[km] = make_float2(x1r, x1i);
             } else {
-              // X[k] = E - T, X[M-k] = conj(E + T), E = Z[k] + conj(Z[M-k]), T = i * w_k * (Z[k] - conj(Z[M-k]))
-              const float er = zr + pr, ei = zi - pi;
-              const float orr = zr - pr, oi = zi + pi;
-              const float2 w = s_wpost[k];  // (cos, -sin)(2 pi k / 2048)
-              const float tr = -fmaf(w.x, oi, w.y * orr);
-              const float ti = fmaf(w.x, orr, -w.y * oi);
-              const float x0r = er - tr, x0i = ei - ti;      // bin k
-              const float x1r = er + tr, x1i = -(ei + ti);   // bin 1024 - k
-              const int km = 1024 - k;
-              const bool has_mirror = (j < 16);  // k == 512 is its own mirror
-              if constexpr (SPEC == EVF_SPEC_RAW) {
-                reinterpret_cast<float2*>(ga)[k] = make_float2(x0r, x0i);
-                if (has_mirror) reinterpret_cast<float2*>(ga)[km] = make_float2(x1r, x1i);
+              float p0 = fmaf(x0r, x0r, x0i * x0i);
+              float p1 = fmaf(x1r, x1r, x1i * x1i);
+              if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
+                p0 = fast_sqrt(p0 + 1e-9f);
+                p1 = fast_sqrt(p1 + 1e-9f);
+              }
+              if constexpr (kMel) {
+                if (k < kcap) P1[k] = p0;
+                if (has_mirror && km < kcap) P1[km] = p1;
               } else {
-                float p0 = fmaf(x0r, x0r, x0i * x0i);
-                float p1 = fmaf(x1r, x1r, x1i * x1i);
-                if constexpr (SPEC == EVF_SPEC_MEL_LIBROSA) {
-                  p0 = fast_sqrt(p0 + 1e-9f);
-                  p1 = fast_sqrt(p1 + 1e-9f);
-                }
-                if constexpr (kMel) {
-                  if (k < kcap) P1[k] = p0;
-                  if (has_mirror && km < kcap) P1[km] = p1;
-                } else {
-                  const float v0 = compress(p0, p.apply_log, p.log_clip);
-                  ga[k] = v0;
-                  esum_a = fmaf(v0, v0, esum_a);
-                  if (has_mirror) {
-                    const float v1 = compress(p1, p.apply_log, p.log_clip);
-                    ga[km] = v1;
-                    esum_a = fmaf(v1, v1, esum_a);
-                  }
+                const float v0 = compress(p0, p.apply_log, p.log_clip);
+                ga[k] = v0;
+                esum_a = fmaf(v0, v0, esum_a);
+                if (has_mirror) {
+                  const float v1 = compress(p1, p.apply_log, p.log_clip);
+                  ga[km] = v1;
+                  esum_a = fmaf(v1, v1, esum_a);
                 }
               }
             }
           }
         }
+      };
+      if constexpr (kMel && !kHalf) {
+        // rows j < ceil(kcap / R1) are consumed (warp-uniform).  One computed jump into the unrolled rows, highest row
+        // first, instead of a test per row (the rows only store to the P column: their order is free)
+        switch ((kcap + R1 - 1) / R1) {
+          default: sep_row(IntC<16>{}); [[fallthrough]];
+          case 16: sep_row(IntC<15>{}); [[fallthrough]];
+          case 15: sep_row(IntC<14>{}); [[fallthrough]];
+          case 14: sep_row(IntC<13>{}); [[fallthrough]];
+          case 13: sep_row(IntC<12>{}); [[fallthrough]];
+          case 12: sep_row(IntC<11>{}); [[fallthrough]];
+          case 11: sep_row(IntC<10>{}); [[fallthrough]];
+          case 10: sep_row(IntC<9>{}); [[fallthrough]];
+          case 9: sep_row(IntC<8>{}); [[fallthrough]];
+          case 8: sep_row(IntC<7>{}); [[fallthrough]];
+          case 7: sep_row(IntC<6>{}); [[fallthrough]];
+          case 6: sep_row(IntC<5>{}); [[fallthrough]];
+          case 5: sep_row(IntC<4>{}); [[fallthrough]];
+          case 4: sep_row(IntC<3>{}); [[fallthrough]];
+          case 3: sep_row(IntC<2>{}); [[fallthrough]];
+          case 2: sep_row(IntC<1>{}); [[fallthrough]];
+          case 1: sep_row(IntC<0>{});
+        }
+      } else {
+        static_for<0, 17>([&](auto jc) {
+          constexpr int j = decltype(jc)::value;
+          // warp-uniform: does any lane of this row own a bin that is consumed?
+          bool need = R1 * j < kcap;
+          if constexpr (kHalf) need = need || (1024 - 32 * j - 31 < kcap);
+          if (need) sep_row(jc);
+        });
       }
 
       if constexpr (kMel) {
@@ -438,13 +480,14 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
         const int nh = p.n_heads;
         const int m_pad = p.m_pad;
         for (int m = lane; m < n_mels; m += 32) {
-          const unsigned* gp = s_gtab + m;
+          const uint2* gp = s_gtab + m;
+          const char* sb = reinterpret_cast<const char*>(slots);
           if constexpr (kPack) {
             float va = 0.f, vb = 0.f;
             for (int c = 0; c <= nh; ++c, gp += m_pad) {
-              const unsigned g = *gp;
-              const float2 r = reinterpret_cast<const float2*>(slots + (g & 0xffffu))[0];
-              const float2 f = reinterpret_cast<const float2*>(slots + (g >> 16))[1];
+              const uint2 g = *gp;  // byte offsets of {rise a, rise b} and of {fall a, fall b}
+              const float2 r = *reinterpret_cast<const float2*>(sb + g.x);
+              const float2 f = *reinterpret_cast<const float2*>(sb + g.y);
               va += r.x;
               vb += r.y;
               va += f.x;
@@ -461,9 +504,9 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
           } else {
             float va = 0.f;
             for (int c = 0; c <= nh; ++c, gp += m_pad) {
-              const unsigned g = *gp;
-              va += slots[g & 0xffffu].x;
-              va += slots[g >> 16].y;
+              const uint2 g = *gp;
+              va += *reinterpret_cast<const float*>(sb + g.x);
+              va += *reinterpret_cast<const float*>(sb + g.y);
             }
             va = compress(va, apply_log, clip);
             gja[m] = va;
@@ -561,7 +604,7 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
   const int fpj = (mode == MODE_HALF) ? 1 : 2;  // frames per job
   const int jobs = mode_jobs_per_warp(mode);
   const int fr = warps * mode_frames_per_warp(mode);
-  const long long limit = (228 * 1024) / kCtasPerSm - 1024;  // one CTA per SM: 227 KB
+  const long long limit = (228 * 1024) / kCtasPerSm - 1024;  // kCtasPerSm resident CTAs, 1 KB reserved for each
   auto up4 = [](int w) { return (w + 3) & ~3; };
   c->n_chunk = t.n_chunk;
   c->n_heads = t.n_heads;
@@ -601,7 +644,7 @@ int features_smem_bytes(int mode, int spec_type, int warps, int hop, int n_fft, 
     if (mel) {
       w += 2 * 32 * t.n_chunk;
       c->off_gtab = w;
-      w += up4((t.n_heads + 1) * t.m_pad);
+      w += up4(2 * (t.n_heads + 1) * t.m_pad);
       c->off_ltab = w;
       w += 32;
     }

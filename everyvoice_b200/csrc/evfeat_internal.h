@@ -56,7 +56,7 @@ struct FeatParams {
   const float2* wpost;   // MODE_HALF: exp(-2 pi i k / n_fft), k = 0..512
   // mel projection (per-warp bin walk, see evfeat_features.cu):
   const float2* wtab;    // [n_chunk][32] {rising weight (sign bit = flush after this bin), falling weight} of bin n_chunk*lane + i
-  const unsigned* gtab;  // [(n_heads + 1)][m_pad] per filter: slot of the c-th rising partial | slot of the c-th falling partial << 16
+  const uint2* gtab;  // [(n_heads + 1)][m_pad] per filter: byte offsets (from the warp's slot area) of its c-th rising and c-th falling partial
   const unsigned* ltab;  // [32] per lane: slot of the first flush | slot of the second flush << 16 (later ones follow consecutively)
   int hop;
   int n_mels;
@@ -85,7 +85,7 @@ struct PlanTables {
   std::vector<int> kstart;        // n_mels + 2: interval j owns bins [kstart[j], kstart[j + 1])
   std::vector<int> jk;            // k_used + 1 interval of every bin (+ sentinel)
   std::vector<float2> wtab;       // n_chunk * 32
-  std::vector<unsigned> gtab;     // (n_heads + 1) * m_pad
+  std::vector<uint2> gtab;        // (n_heads + 1) * m_pad
   std::vector<unsigned> ltab;     // 32
   int k_used = 0, n_chunk = 1, n_heads = 0, m_pad = 32, n_slots = 34;
 };
