@@ -91,7 +91,7 @@ class CorpusPipeline:
 
     def __init__(self, transform: SpectralTransform, sample_offsets, device=None, sample_dtype=torch.float32,
                  durations=None, phone_offsets=None, chunk_bytes: int = 16 << 20, want_energy: bool = True,
-                 resources: PipelineResources | None = None):
+                 resources: PipelineResources | None = None, head_chunk_bytes: int | None = None):
         self.tf = transform
         self.device = _require_cuda(device if device is not None else transform._device)
         self.res = resources if resources is not None else PipelineResources(self.device)
@@ -107,8 +107,11 @@ class CorpusPipeline:
         self.total_samples = int(off[-1] - off[0])
         esize = 2 if sample_dtype == torch.int16 else 4
         # ---- chunk plan: consecutive utterances, about chunk_bytes of samples each ---------------
-        # Small chunks at both ends: the first kernel waits for the first chunk's H2D and the last D2H for the last
-        # chunk's kernel, so the pipeline's fill and drain shrink with them (chunk_bytes / 8, / 4, / 2 ... / 2, / 4, / 8).
+        # Small chunks at the END only (... / 2, / 4, / 8): the last D2H waits for the last chunk's kernel, so the drain
+        # shrinks with them.  The FIRST chunks are full-sized (head_chunk_bytes): the step is bound by the copy-in
+        # engine, and the first two copies must outlast the host's batch planning, or the engine idles until the
+        # host is back to enqueue chunk 2 (measured: 0.55 ms of a 5.7 ms step with a 2 / 4 / 8 MB ramp-up,
+        # profiles/r02z_e2e_timeline.txt).
         # ONE batch descriptor for the shard (built lazily by run(), after the first copies are in flight); chunks
         # are utterance ranges of it (evf_features_run_range)
         self._batch = None
@@ -117,7 +120,7 @@ class CorpusPipeline:
         align = 16 // esize
         total = int(off[-1] - off[0])
         u = 0
-        ramp = full // 8
+        ramp = max(1, (head_chunk_bytes if head_chunk_bytes is not None else chunk_bytes) // esize)
         while u < self.n_utts:
             left = total - int(off[u] - off[0])
             limit = max(1, min(ramp, full, max(left // 2, full // 8)))
@@ -215,8 +218,6 @@ class CorpusPipeline:
             for i, c in enumerate(self.chunks):
                 b = i & 1
                 ns, nf = c.s1 - c.s0, c.f1 - c.f0
-                if i >= 2:
-                    copy_in(i)
                 # -- kernels (output buffer b is free once chunk i-2 has been copied out)
                 s_compute.wait_event(ev_in[b])
                 if i >= 2:
@@ -237,6 +238,10 @@ class CorpusPipeline:
                                                     C.c_void_p(self._d_phone_off.data_ptr() + 8 * c.u0),
                                                     c.u1 - c.u0, C.c_void_p(self._d_phone.data_ptr()), st))
                 ev_comp[b].record(s_compute)
+                # -- the copy-in engine bounds the step: hand it chunk i+2 (into the buffer these kernels free) before
+                #    anything else is enqueued
+                if i + 2 < len(self.chunks):
+                    copy_in(i + 2)
                 # -- D2H
                 s_out.wait_event(ev_comp[b])
                 with torch.cuda.stream(s_out):
@@ -295,7 +300,8 @@ class FlowPipeline:
 
     def __init__(self, transform: SpectralTransform, raw_offsets, sr: int, hop_size: int, device=None,
                  sample_dtype=torch.int16, durations=None, phone_offsets=None, chunk_bytes: int = 16 << 20,
-                 normalize: bool = True, resources: PipelineResources | None = None):
+                 normalize: bool = True, resources: PipelineResources | None = None,
+                 head_chunk_bytes: int | None = None):
         from .audio import LOUDNESS_GATE_LKFS, LOUDNESS_REFINE_BAND, k_weighting_coefficients
 
         self.tf = transform
@@ -323,11 +329,11 @@ class FlowPipeline:
         self.scratch_offsets = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
         esize = 2 if sample_dtype == torch.int16 else 4
         self.esize = esize
-        # ---- chunk plan over the RAW layout (what is copied in), ramped like CorpusPipeline's -------------------
+        # ---- chunk plan over the RAW layout (what is copied in): full-sized head, ramped-down tail like CorpusPipeline's
         self.chunks: list[_Chunk] = []
         full = max(1, chunk_bytes // esize)
         total = int(raw[-1] - raw[0])
-        u, ramp = 0, full // 8
+        u, ramp = 0, max(1, (head_chunk_bytes if head_chunk_bytes is not None else chunk_bytes) // esize)
         while u < n:
             left = total - int(raw[u] - raw[0])
             limit = max(1, min(ramp, full, max(left // 2, full // 8)))

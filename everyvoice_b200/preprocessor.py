@@ -281,7 +281,7 @@ class Preprocessor:
                                          want_energy=want_energy)
 
     def make_corpus_pipeline(self, sample_offsets, sample_dtype=torch.float32, durations=None, phone_offsets=None,
-                             output=False, chunk_bytes: int = 16 << 20):
+                             output=False, chunk_bytes: int = 16 << 20, head_chunk_bytes: int | None = None):
         """Host-buffer front door for a whole shard (``pipeline.CorpusPipeline``): H2D of the
         next chunk, the kernels of this one and D2H of the previous one overlap on three streams."""
         from .pipeline import CorpusPipeline, PipelineResources
@@ -292,10 +292,10 @@ class Preprocessor:
         if res is None or res.device != device:
             res = self._pipeline_resources = PipelineResources(device)   # buffers / streams live across batches
         return CorpusPipeline(transform, sample_offsets, device, sample_dtype, durations, phone_offsets, chunk_bytes,
-                              resources=res)
+                              resources=res, head_chunk_bytes=head_chunk_bytes)
 
     def make_flow_pipeline(self, raw_offsets, sr: int, sample_dtype=torch.int16, durations=None, phone_offsets=None,
-                           normalize=True, chunk_bytes: int = 16 << 20):
+                           normalize=True, chunk_bytes: int = 16 << 20, head_chunk_bytes: int | None = None):
         """The whole ``process_audio -> process_spec -> process_energy -> statistics`` flow for one batch of loaded
         wavs as one chunked pipeline with the loudness gate consumed on the device (``pipeline.FlowPipeline``)."""
         from .pipeline import FlowPipeline, PipelineResources
@@ -305,7 +305,8 @@ class Preprocessor:
         if res is None or res.device != device:
             res = self._pipeline_resources = PipelineResources(device)
         return FlowPipeline(self.input_spectral_transform, raw_offsets, sr, self.audio_config.fft_hop_size, device,
-                            sample_dtype, durations, phone_offsets, chunk_bytes, normalize, resources=res)
+                            sample_dtype, durations, phone_offsets, chunk_bytes, normalize, resources=res,
+                            head_chunk_bytes=head_chunk_bytes)
 
     def process_energy_batch(self, feats: RaggedFeatures, durations=None, phone_offsets=None):
         """The in-memory core of ``process_energy`` (preprocessor.py:641-650): frame energy, and
