@@ -441,9 +441,11 @@ def test_gathered_stats_merge_and_normalise_on_device(cuda_device):
     assert torch.equal(single, mine)  # [5] and [world, 5] forms agree bit for bit
 
 
+@pytest.mark.parametrize("head", [None, 25_000])
 @pytest.mark.parametrize("dtype", ["f32", "s16"])
-def test_corpus_pipeline_equals_single_batch(cuda_device, dtype):
-    """The chunked three-stream host pipeline returns exactly what one resident batch does."""
+def test_corpus_pipeline_equals_single_batch(cuda_device, dtype, head):
+    """The chunked three-stream host pipeline returns exactly what one resident batch does (first chunks full-sized
+    -- the default -- or ramped up from ``head_chunk_bytes``)."""
     import everyvoice_b200 as ev
     from everyvoice_b200 import synth
 
@@ -464,8 +466,10 @@ def test_corpus_pipeline_equals_single_batch(cuda_device, dtype):
     d_packed, p_off = synth.pack_ragged(durs)
     host = torch.from_numpy(packed).pin_memory()
     pipe = pre.make_corpus_pipeline(off, tdt, torch.from_numpy(d_packed.astype(np.int64)), p_off,
-                                    chunk_bytes=200_000)  # forces ~10 chunks
+                                    chunk_bytes=200_000, head_chunk_bytes=head)  # forces ~10 chunks
     assert len(pipe.chunks) >= 5
+    first = (pipe.chunks[0].s1 - pipe.chunks[0].s0) * pipe.esize
+    assert first <= (head if head is not None else 200_000) or pipe.chunks[0].u1 == pipe.chunks[0].u0 + 1
     h_spec = torch.empty((pipe.total_frames, 80), dtype=torch.float32).pin_memory()
     h_energy = torch.empty(pipe.total_frames, dtype=torch.float32).pin_memory()
     h_phone = torch.empty(pipe.n_phones, dtype=torch.float32).pin_memory()
