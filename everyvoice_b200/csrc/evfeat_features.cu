@@ -479,39 +479,63 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) features_kernel(const 
         const float clip = p.log_clip;
         const int nh = p.n_heads;
         const int m_pad = p.m_pad;
-        for (int m = lane; m < n_mels; m += 32) {
-          const uint2* gp = s_gtab + m;
+        // the number of partials per interval (nh + 1) is a property of the plan: the common small counts get a fully
+        // unrolled row body (no inner loop control), anything else the run-time loop.  Fixed summation order either way.
+        auto gather_rows = [&](auto cc) {
+          constexpr int C = decltype(cc)::value;  // partials per interval, 0 = run-time count
           const char* sb = reinterpret_cast<const char*>(slots);
-          if constexpr (kPack) {
-            float va = 0.f, vb = 0.f;
-            for (int c = 0; c <= nh; ++c, gp += m_pad) {
-              const uint2 g = *gp;  // byte offsets of {rise a, rise b} and of {fall a, fall b}
-              const float2 r = *reinterpret_cast<const float2*>(sb + g.x);
-              const float2 f = *reinterpret_cast<const float2*>(sb + g.y);
-              va += r.x;
-              vb += r.y;
-              va += f.x;
-              vb += f.y;
+          const uint2* gp0 = s_gtab + lane;
+          float* oa = gja + lane;
+          float* ob = gjb + lane;
+          for (int m = lane; m < n_mels; m += 32, gp0 += 32, oa += 32, ob += 32) {
+            const uint2* gp = gp0;
+            if constexpr (kPack) {
+              float va = 0.f, vb = 0.f;
+              auto add = [&](const uint2 g) {  // byte offsets of {rise a, rise b} and of {fall a, fall b}
+                const float2 r = *reinterpret_cast<const float2*>(sb + g.x);
+                const float2 f = *reinterpret_cast<const float2*>(sb + g.y);
+                va += r.x;
+                vb += r.y;
+                va += f.x;
+                vb += f.y;
+              };
+              if constexpr (C > 0) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) add(gp[c * m_pad]);
+              } else {
+                for (int c = 0; c <= nh; ++c, gp += m_pad) add(*gp);
+              }
+              va = compress(va, apply_log, clip);
+              vb = compress(vb, apply_log, clip);
+              *oa = va;
+              ea = fmaf(va, va, ea);
+              if (jb_valid) {
+                *ob = vb;
+                eb = fmaf(vb, vb, eb);
+              }
+            } else {
+              float va = 0.f;
+              auto add = [&](const uint2 g) {
+                va += *reinterpret_cast<const float*>(sb + g.x);
+                va += *reinterpret_cast<const float*>(sb + g.y);
+              };
+              if constexpr (C > 0) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) add(gp[c * m_pad]);
+              } else {
+                for (int c = 0; c <= nh; ++c, gp += m_pad) add(*gp);
+              }
+              va = compress(va, apply_log, clip);
+              *oa = va;
+              ea = fmaf(va, va, ea);
             }
-            va = compress(va, apply_log, clip);
-            vb = compress(vb, apply_log, clip);
-            gja[m] = va;
-            ea = fmaf(va, va, ea);
-            if (jb_valid) {
-              gjb[m] = vb;
-              eb = fmaf(vb, vb, eb);
-            }
-          } else {
-            float va = 0.f;
-            for (int c = 0; c <= nh; ++c, gp += m_pad) {
-              const uint2 g = *gp;
-              va += *reinterpret_cast<const float*>(sb + g.x);
-              va += *reinterpret_cast<const float*>(sb + g.y);
-            }
-            va = compress(va, apply_log, clip);
-            gja[m] = va;
-            ea = fmaf(va, va, ea);
           }
+        };
+        switch (nh) {
+          case 0: gather_rows(IntC<1>{}); break;
+          case 1: gather_rows(IntC<2>{}); break;
+          case 2: gather_rows(IntC<3>{}); break;
+          default: gather_rows(IntC<0>{}); break;
         }
           if constexpr (J == 1) {
             esum_a = ea;
